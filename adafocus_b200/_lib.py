@@ -1,0 +1,134 @@
+"""ctypes binding of include/adafocus_b200.h.
+
+The product path has no fallback: if the shared library is missing or a CUDA device is absent, loading / context
+creation raises.  Nothing here imports oracle/.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libadafocus_b200.so")
+
+AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6 = 0, 1, 2
+
+
+class AfError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """struct af_conv_desc"""
+    _fields_ = [
+        ("in_", c_void_p), ("w", c_void_p), ("scale", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+        ("out", c_void_p),
+        ("n", c_int32), ("h", c_int32), ("w_", c_int32), ("cin", c_int32), ("cout", c_int32),
+        ("kh", c_int32), ("kw", c_int32), ("stride", c_int32), ("pad", c_int32),
+        ("block_n", c_int32), ("act", c_int32), ("out_f32", c_int32),
+        ("in_stride", c_int64), ("out_stride", c_int64), ("res_stride", c_int64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/adafocus_b200.h
+SIGNATURES = {
+    "af_version": (c_int, []),
+    "af_last_error": (c_char_p, []),
+    "af_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
+    "af_ctx_destroy": (c_int, [c_void_p]),
+    "af_ctx_sm_count": (c_int, [c_void_p]),
+    "af_plan_begin": (c_int, [c_void_p]),
+    "af_plan_end": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "af_plan_run": (c_int, [c_void_p, c_void_p]),
+    "af_plan_num_launches": (c_int, [c_void_p]),
+    "af_plan_destroy": (c_int, [c_void_p]),
+    "af_crop_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "af_action_to_yx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_void_p]),
+    "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),
+    "af_dwconv3x3_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_void_p]),
+    "af_maxpool3x3s2_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_avgpool_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                    c_void_p]),
+    "af_nhwc_f16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "af_nchw_f32_to_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_gru_gates": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                             c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "af_policy_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "af_policy_head_continuous": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_void_p]),
+    "af_tsm_shift_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_consensus_avg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "af_fill_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
+    "af_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every symbol; raises AfError if it is missing (there is no other path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AfError(
+            f"{LIB_PATH} not found: build it with `python -m adafocus_b200.build` (nvcc, sm_100a). "
+            "adafocus_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = load().af_last_error()
+        raise AfError(f"{what} failed ({code}): {msg.decode() if msg else ''}")
+
+
+class Context:
+    """Owns one af_ctx (one per device)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = c_void_p()
+        check(self.lib.af_ctx_create(byref(h), int(device)), "af_ctx_create")
+        self.handle = h
+        self.device = int(device)
+        self.sm_count = self.lib.af_ctx_sm_count(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.af_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Plan:
+    """A recorded launch sequence (af_plan)."""
+
+    def __init__(self, lib, handle, keepalive):
+        self.lib = lib
+        self.handle = handle
+        self.keepalive = keepalive   # tensors whose pointers the plan replays on
+        self.num_launches = lib.af_plan_num_launches(handle)
+
+    def run(self, stream):
+        check(self.lib.af_plan_run(self.handle, c_void_p(stream)), "af_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.af_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

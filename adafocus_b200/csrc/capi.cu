@@ -1,0 +1,397 @@
+// C ABI (include/adafocus_b200.h): context, plan recorder, tensor-map construction, kernel dispatch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/adafocus_b200.h"
+#include "conv_gemm.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+  return AF_ERR_CUDA;
+}
+
+using Launch = std::function<cudaError_t(cudaStream_t)>;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct af_plan {
+  std::vector<Launch> launches;
+};
+
+struct af_ctx {
+  int device = 0;
+  int sm_count = 0;
+  bool recording = false;
+  af_plan* current = nullptr;
+  EncodeTiledFn encode_tiled = nullptr;
+};
+
+namespace {
+
+int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
+  if (ctx == nullptr) return fail(AF_ERR_INVALID, std::string(name) + ": null ctx");
+  if (ctx->recording) {
+    ctx->current->launches.push_back(std::move(fn));
+    return AF_OK;
+  }
+  cudaError_t e = fn(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, name);
+  return AF_OK;
+}
+
+bool encode_map(af_ctx* ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, std::string* err) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank),
+                                 const_cast<void*>(base), dims, strides_bytes, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] base %p",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    *err = buf;
+    return false;
+  }
+  return true;
+}
+
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Pick the 128-pixel output box (TW x TH x TN, powers of two) that covers the output with the fewest tiles;
+// ties go to the wider box (longer contiguous runs per TMA row).
+void choose_tile(int N, int Ho, int Wo, int* TW, int* TH, int* TN) {
+  long long best_cost = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tn = 128 / (tw * th);
+      const long long cost = static_cast<long long>(ceil_div(Wo, tw)) * ceil_div(Ho, th) * ceil_div(N, tn);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        *TW = tw;
+        *TH = th;
+        *TN = tn;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int af_version(void) { return AF_VERSION; }
+const char* af_last_error(void) { return g_last_error.c_str(); }
+
+int af_ctx_create(af_ctx** out, int device) {
+  if (out == nullptr) return fail(AF_ERR_INVALID, "af_ctx_create: null out");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return fail_cuda(e, "af_ctx_create: cudaGetDeviceCount (no CPU fallback exists)");
+  if (device < 0 || device >= count) return fail(AF_ERR_INVALID, "af_ctx_create: bad device index");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail_cuda(e, "af_ctx_create: cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    return fail(AF_ERR_CUDA, "af_ctx_create: device is not sm_100 (Blackwell B200); this library has no other path");
+  }
+  af_ctx* ctx = new af_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    delete ctx;
+    return fail(AF_ERR_CUDA, "af_ctx_create: cuTensorMapEncodeTiled entry point not available");
+  }
+  ctx->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = ctx;
+  return AF_OK;
+}
+
+int af_ctx_destroy(af_ctx* ctx) {
+  if (ctx == nullptr) return AF_OK;
+  if (ctx->current != nullptr) delete ctx->current;
+  delete ctx;
+  return AF_OK;
+}
+
+int af_ctx_sm_count(const af_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int af_plan_begin(af_ctx* ctx) {
+  if (ctx == nullptr) return fail(AF_ERR_INVALID, "af_plan_begin: null ctx");
+  if (ctx->recording) return fail(AF_ERR_STATE, "af_plan_begin: already recording");
+  ctx->current = new af_plan();
+  ctx->recording = true;
+  return AF_OK;
+}
+
+int af_plan_end(af_ctx* ctx, af_plan** out) {
+  if (ctx == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_plan_end: null argument");
+  if (!ctx->recording) return fail(AF_ERR_STATE, "af_plan_end: not recording");
+  *out = ctx->current;
+  ctx->current = nullptr;
+  ctx->recording = false;
+  return AF_OK;
+}
+
+int af_plan_run(af_plan* plan, void* stream) {
+  if (plan == nullptr) return fail(AF_ERR_INVALID, "af_plan_run: null plan");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (size_t i = 0; i < plan->launches.size(); ++i) {
+    cudaError_t e = plan->launches[i](s);
+    if (e != cudaSuccess) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "af_plan_run: launch %zu", i);
+      return fail_cuda(e, buf);
+    }
+  }
+  return AF_OK;
+}
+
+int af_plan_num_launches(const af_plan* plan) { return plan ? static_cast<int>(plan->launches.size()) : 0; }
+
+int af_plan_destroy(af_plan* plan) {
+  delete plan;
+  return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+int af_crop_nchw_f32(af_ctx* ctx, const float* img, const float* action, const int32_t* yx, float* out,
+                     int32_t* yx_out, int N, int C, int H, int W, int P, void* stream) {
+  if (img == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_crop_nchw_f32: null tensor");
+  if ((action == nullptr) == (yx == nullptr))
+    return fail(AF_ERR_INVALID, "af_crop_nchw_f32: exactly one of action / yx must be given");
+  if (N < 0 || C <= 0 || P <= 0 || P > H || P > W)
+    return fail(AF_ERR_INVALID, "af_crop_nchw_f32: need 0 < P <= min(H, W)");
+  return dispatch(ctx, stream, "af_crop_nchw_f32", [=](cudaStream_t s) {
+    return af::launch_crop_nchw_f32(img, action, yx, out, yx_out, N, C, H, W, P, s);
+  });
+}
+
+int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H, int P, void* stream) {
+  if (action == nullptr || yx == nullptr || P > H) return fail(AF_ERR_INVALID, "af_action_to_yx: bad argument");
+  return dispatch(ctx, stream, "af_action_to_yx",
+                  [=](cudaStream_t s) { return af::launch_action_to_yx(action, yx, N, H, P, s); });
+}
+
+int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* out, int N, int H, int W, int P, int KH,
+                   int KW, int stride, int pad, int Kpad, void* stream) {
+  if (frames == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_stem_im2col: null tensor");
+  if (Kpad % 8 != 0 || Kpad < KH * KW * 3 || P > H || P > W || stride < 1)
+    return fail(AF_ERR_INVALID, "af_stem_im2col: bad geometry");
+  const int Ho = (P + 2 * pad - KH) / stride + 1, Wo = (P + 2 * pad - KW) / stride + 1;
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_stem_im2col", [=](cudaStream_t s) {
+    return af::launch_stem_im2col(frames, yx, o, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad, s);
+  });
+}
+
+int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
+  if (ctx == nullptr || d == nullptr) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: null argument");
+  if (d->in == nullptr || d->w == nullptr || d->out == nullptr || d->scale == nullptr || d->bias == nullptr)
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: null tensor");
+  if (d->block_n < 16 || d->block_n > af::kConvMaxBlockN || d->block_n % 16 != 0)
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: block_n must be a multiple of 16 in [16,256]");
+  if (d->stride != 1 && d->stride != 2) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: stride must be 1 or 2");
+  if (d->cin % 8 != 0 || d->in_stride % 8 != 0 || d->in_stride < d->cin)
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: cin and in_stride must be multiples of 8");
+  if (d->cout < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: cout < 1");
+  if (d->out_stride % 8 != 0 || (d->residual != nullptr && d->res_stride % 8 != 0))
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: out_stride / res_stride must be multiples of 8");
+  if (d->n < 1 || d->h < 1 || d->w_ < 1 || d->kh < 1 || d->kw < 1)
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: bad geometry");
+  if (d->stride == 2 && (d->h < 2 || d->w_ < 2))
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: stride-2 needs h, w >= 2");
+
+  af::ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n;
+  p.Ho = (d->h + 2 * d->pad - d->kh) / d->stride + 1;
+  p.Wo = (d->w_ + 2 * d->pad - d->kw) / d->stride + 1;
+  if (p.Ho < 1 || p.Wo < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: empty output");
+  p.Cout = d->cout;
+  choose_tile(p.N, p.Ho, p.Wo, &p.TW, &p.TH, &p.TN);
+  p.tiles_w = ceil_div(p.Wo, p.TW);
+  p.tiles_h = ceil_div(p.Ho, p.TH);
+  p.tiles_n = ceil_div(p.N, p.TN);
+  p.BN = d->block_n;
+  p.n_blocks = ceil_div(d->cout, d->block_n);
+  p.KH = d->kh;
+  p.KW = d->kw;
+  p.stride = d->stride;
+  p.pad = d->pad;
+  p.cblks = ceil_div(d->cin, af::kConvBlockK);
+  p.scale = d->scale;
+  p.bias = d->bias;
+  p.residual = static_cast<const __half*>(d->residual);
+  p.res_stride = d->res_stride;
+  p.out = d->out;
+  p.out_stride = d->out_stride;
+  p.out_f32 = d->out_f32;
+  p.act = d->act;
+
+  af::ConvTensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  const __half* in = static_cast<const __half*>(d->in);
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.TW),
+                             static_cast<cuuint32_t>(p.TH), static_cast<cuuint32_t>(p.TN)};
+  const cuuint64_t pix_b = static_cast<cuuint64_t>(d->in_stride) * 2;
+  if (d->stride == 1) {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
+                                static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    if (!encode_map(ctx, &maps.a[0], in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  } else {
+    for (int ph = 0; ph < 2; ++ph) {
+      for (int pw = 0; pw < 2; ++pw) {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>((d->w_ - pw + 1) / 2),
+                                    static_cast<cuuint64_t>((d->h - ph + 1) / 2), static_cast<cuuint64_t>(d->n)};
+        const cuuint64_t strides[3] = {pix_b * 2, pix_b * d->w_ * 2, pix_b * d->w_ * d->h};
+        const __half* base = in + (static_cast<long long>(ph) * d->w_ + pw) * d->in_stride;
+        if (!encode_map(ctx, &maps.a[ph * 2 + pw], base, 4, dims, strides, box, &err))
+          return fail(AF_ERR_CUDA, err);
+      }
+    }
+  }
+  {
+    const cuuint64_t kpad = static_cast<cuuint64_t>(d->kh) * d->kw * p.cblks * af::kConvBlockK;
+    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(p.n_blocks) * p.BN};
+    const cuuint64_t strides[1] = {kpad * 2};
+    const cuuint32_t bbox[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.BN)};
+    if (!encode_map(ctx, &maps.b, d->w, 2, dims, strides, bbox, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  const int sms = ctx->sm_count;
+  return dispatch(ctx, stream, "af_conv2d_nhwc_f16",
+                  [=](cudaStream_t s) { return af::launch_conv_gemm(maps, p, sms, s); });
+}
+
+int af_dwconv3x3_nhwc_f16(af_ctx* ctx, const void* in, const float* w9c, const float* scale, const float* bias,
+                          void* out, int N, int H, int W, int C, int stride, int act, void* stream) {
+  if (in == nullptr || w9c == nullptr || scale == nullptr || bias == nullptr || out == nullptr)
+    return fail(AF_ERR_INVALID, "af_dwconv3x3_nhwc_f16: null tensor");
+  if (C % 8 != 0 || (stride != 1 && stride != 2)) return fail(AF_ERR_INVALID, "af_dwconv3x3_nhwc_f16: bad shape");
+  const __half* i = static_cast<const __half*>(in);
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_dwconv3x3_nhwc_f16", [=](cudaStream_t s) {
+    return af::launch_dwconv3x3(i, w9c, scale, bias, o, N, H, W, C, stride, act, s);
+  });
+}
+
+int af_maxpool3x3s2_nhwc_f16(af_ctx* ctx, const void* in, void* out, int N, int H, int W, int C, void* stream) {
+  if (in == nullptr || out == nullptr || C % 8 != 0) return fail(AF_ERR_INVALID, "af_maxpool3x3s2_nhwc_f16: bad argument");
+  const __half* i = static_cast<const __half*>(in);
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_maxpool3x3s2_nhwc_f16",
+                  [=](cudaStream_t s) { return af::launch_maxpool3x3s2(i, o, N, H, W, C, s); });
+}
+
+int af_avgpool_nhwc_f16(af_ctx* ctx, const void* in, float* out_f32, int64_t out_f32_stride, void* out_f16,
+                        int64_t out_f16_stride, int N, int HW, int C, void* stream) {
+  if (in == nullptr || (out_f32 == nullptr && out_f16 == nullptr) || C % 8 != 0 || HW < 1)
+    return fail(AF_ERR_INVALID, "af_avgpool_nhwc_f16: bad argument");
+  const __half* i = static_cast<const __half*>(in);
+  __half* o16 = static_cast<__half*>(out_f16);
+  return dispatch(ctx, stream, "af_avgpool_nhwc_f16", [=](cudaStream_t s) {
+    return af::launch_avgpool(i, out_f32, out_f32_stride, o16, out_f16_stride, N, HW, C, s);
+  });
+}
+
+int af_nhwc_f16_to_nchw_f32(af_ctx* ctx, const void* in, float* out, int N, int HW, int C, void* stream) {
+  if (in == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_nhwc_f16_to_nchw_f32: null tensor");
+  if (N > 65535) return fail(AF_ERR_INVALID, "af_nhwc_f16_to_nchw_f32: N > 65535");
+  const __half* i = static_cast<const __half*>(in);
+  return dispatch(ctx, stream, "af_nhwc_f16_to_nchw_f32",
+                  [=](cudaStream_t s) { return af::launch_nhwc_f16_to_nchw_f32(i, out, N, HW, C, s); });
+}
+
+int af_nchw_f32_to_nhwc_f16(af_ctx* ctx, const float* in, void* out, int N, int C, int HW, int Cpad, void* stream) {
+  if (in == nullptr || out == nullptr || Cpad < C) return fail(AF_ERR_INVALID, "af_nchw_f32_to_nhwc_f16: bad argument");
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_nchw_f32_to_nhwc_f16",
+                  [=](cudaStream_t s) { return af::launch_nchw_f32_to_nhwc_f16(in, o, N, C, HW, Cpad, s); });
+}
+
+int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* hg, const float* h_prev, float* h_new,
+                 void* h_new_f16, void* hseq_f16, int64_t hseq_stride, float* hseq_f32, int64_t hseq_f32_stride, int B,
+                 int Hd, void* stream) {
+  if (xg == nullptr || hg == nullptr || h_prev == nullptr || h_new == nullptr)
+    return fail(AF_ERR_INVALID, "af_gru_gates: null tensor");
+  __half* a = static_cast<__half*>(h_new_f16);
+  __half* b = static_cast<__half*>(hseq_f16);
+  return dispatch(ctx, stream, "af_gru_gates", [=](cudaStream_t s) {
+    return af::launch_gru_gates(xg, xg_stride, hg, h_prev, h_new, a, b, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd,
+                                s);
+  });
+}
+
+int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,
+                   int32_t* action_idx, float* action_yx, int32_t* yx, void* stream) {
+  if (logits == nullptr || A < 1 || grid_n < 2 || grid_n * grid_n != A || P > H)
+    return fail(AF_ERR_INVALID, "af_policy_head: need A == grid_n^2, grid_n >= 2, P <= H");
+  return dispatch(ctx, stream, "af_policy_head", [=](cudaStream_t s) {
+    return af::launch_policy_head(logits, logit_stride, A, grid_n, rows, H, P, action_idx, action_yx, yx, s);
+  });
+}
+
+int af_policy_head_continuous(af_ctx* ctx, const float* logits, int64_t logit_stride, int rows, int H, int P,
+                              float* action_yx, int32_t* yx, void* stream) {
+  if (logits == nullptr || P > H) return fail(AF_ERR_INVALID, "af_policy_head_continuous: bad argument");
+  return dispatch(ctx, stream, "af_policy_head_continuous", [=](cudaStream_t s) {
+    return af::launch_policy_head_continuous(logits, logit_stride, rows, H, P, action_yx, yx, s);
+  });
+}
+
+int af_tsm_shift_nhwc_f16(af_ctx* ctx, const void* in, void* out, int NT, int T, int HW, int C, int fold,
+                          void* stream) {
+  if (in == nullptr || out == nullptr || in == out || C % 8 != 0 || T < 1 || NT % T != 0 || 2 * fold > C)
+    return fail(AF_ERR_INVALID, "af_tsm_shift_nhwc_f16: bad argument (NT must be a multiple of T, out != in)");
+  const __half* i = static_cast<const __half*>(in);
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_tsm_shift_nhwc_f16",
+                  [=](cudaStream_t s) { return af::launch_tsm_shift(i, o, NT, T, HW, C, fold, s); });
+}
+
+int af_consensus_avg(af_ctx* ctx, const float* in, const float* add, float* out, int B, int T, int C, void* stream) {
+  if (in == nullptr || out == nullptr || T < 1) return fail(AF_ERR_INVALID, "af_consensus_avg: bad argument");
+  return dispatch(ctx, stream, "af_consensus_avg",
+                  [=](cudaStream_t s) { return af::launch_consensus_avg(in, add, out, B, T, C, s); });
+}
+
+int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream) {
+  if (p == nullptr) return fail(AF_ERR_INVALID, "af_fill_f32: null tensor");
+  return dispatch(ctx, stream, "af_fill_f32", [=](cudaStream_t s) { return af::launch_fill_f32(p, v, n, s); });
+}
+
+int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream) {
+  if (in == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_f32_to_f16: null tensor");
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_f32_to_f16", [=](cudaStream_t s) { return af::launch_f32_to_f16(in, o, n, s); });
+}
+
+}  // extern "C"

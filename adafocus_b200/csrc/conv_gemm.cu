@@ -1,0 +1,285 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_gemm.cuh for the algorithm and reference call sites).
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace af {
+
+using namespace ptx;
+
+namespace {
+
+struct __align__(8) ConvSmemCtrl {
+  uint64_t full[kConvMaxStages];
+  uint64_t empty[kConvMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
+constexpr int kCtrlBytes = 256;
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == kActRelu) return fmaxf(x, 0.f);
+  if (act == kActRelu6) return fminf(fmaxf(x, 0.f), 6.f);
+  return x;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-B alignment is required by the 128-B swizzle; dynamic smem base is at least 16-B aligned, so align by hand.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int stage_b_bytes = p.BN * kConvBlockK * 2;
+  const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
+  ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_blocks;
+  const int num_kb = p.KH * p.KW * p.cblks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&ctrl->full[s], 1);
+      mbar_init(&ctrl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctrl->tmem_full[a], 1);
+      mbar_init(&ctrl->tmem_empty[a], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    if (p.stride == 2) {
+      tma_prefetch_desc(&maps.a[1]);
+      tma_prefetch_desc(&maps.a[2]);
+      tma_prefetch_desc(&maps.a[3]);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctrl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nb = tile % p.n_blocks;
+        const int mt = tile / p.n_blocks;
+        const int tw_i = mt % p.tiles_w;
+        const int th_i = (mt / p.tiles_w) % p.tiles_h;
+        const int tn_i = mt / (p.tiles_w * p.tiles_h);
+        const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+        int kb = 0;
+        for (int kh = 0; kh < p.KH; ++kh) {
+          for (int kw = 0; kw < p.KW; ++kw) {
+            int map_idx = 0, ch, cw;
+            if (p.stride == 1) {
+              ch = oh0 + kh - p.pad;
+              cw = ow0 + kw - p.pad;
+            } else {
+              const int rh = kh - p.pad, rw = kw - p.pad;
+              const int ph = rh & 1, pw = rw & 1;           // parity of the input row / column
+              ch = oh0 + ((rh - ph) >> 1);                  // floor((kh-pad)/2) offset inside the parity view
+              cw = ow0 + ((rw - pw) >> 1);
+              map_idx = ph * 2 + pw;
+            }
+            for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
+              mbar_wait(&ctrl->empty[stage], phase ^ 1);
+              uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+              uint8_t* sb = sa + kStageABytes;
+              mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+              tma_load_4d(sa, &maps.a[map_idx], &ctrl->full[stage], cb * kConvBlockK, cw, ch, n0);
+              tma_load_2d(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(p.BN));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&ctrl->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kConvMaxBlockN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctrl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + kStageABytes;
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 16; ++k) {
+            // advance 16 fp16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
+            umma_f16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&ctrl->tmem_full[as]);    // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ============================ epilogue (4 warps) ============================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;      // row of the 128-row tile == TMEM lane
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nb = tile % p.n_blocks;
+      const int mt = tile / p.n_blocks;
+      const int tw_i = mt % p.tiles_w;
+      const int th_i = (mt / p.tiles_w) % p.tiles_h;
+      const int tn_i = mt / (p.tiles_w * p.tiles_h);
+      const int ow = tw_i * p.TW + tw, oh = th_i * p.TH + th, n = tn_i * p.TN + tn;
+      const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
+      const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&ctrl->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(as * kConvMaxBlockN);
+      const int co_base = nb * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int co = co_base + c0 + g * 8;
+          if (co >= p.Cout) continue;
+          float x[8];
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + co));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+          x[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, b0.x);
+          x[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, b0.y);
+          x[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, b0.z);
+          x[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, b0.w);
+          x[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, b1.x);
+          x[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, b1.y);
+          x[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, b1.z);
+          x[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, b1.w);
+          const bool full8 = (co + 8 <= p.Cout);
+          if (p.residual != nullptr) {
+            const __half* rp = p.residual + pix * p.res_stride + co;
+            if (full8) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp));
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(rh[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
+            } else {
+              for (int j = 0; j < 8 && co + j < p.Cout; ++j) x[j] += __half2float(rp[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_stride + co;
+            if (full8) {
+              reinterpret_cast<float4*>(op)[0] = make_float4(x[0], x[1], x[2], x[3]);
+              reinterpret_cast<float4*>(op)[1] = make_float4(x[4], x[5], x[6], x[7]);
+            } else {
+              for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = x[j];
+            }
+          } else {
+            __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_stride + co;
+            if (full8) {
+              uint4 ov;
+              __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+              *reinterpret_cast<uint4*>(op) = ov;
+            } else {
+              for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = __float2half_rn(x[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+size_t conv_gemm_smem_bytes(int BN, int* stages_out) {
+  const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
+  int stages = (kConvSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  if (stages > kConvMaxStages) stages = kConvMaxStages;
+  if (stages < 2) stages = 2;
+  if (stages_out) *stages_out = stages;
+  return static_cast<size_t>(stages) * stage_bytes + kCtrlBytes + 1024;
+}
+
+cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p_in, int sm_count,
+                             cudaStream_t stream) {
+  static_assert(sizeof(ConvSmemCtrl) <= kCtrlBytes, "ctrl block too large");
+  ConvKernelParams p = p_in;
+  int stages = 0;
+  const size_t smem = conv_gemm_smem_bytes(p.BN, &stages);
+  p.stages = stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kConvSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  if (grid < 1) grid = 1;
+  conv_gemm_kernel<<<grid, kConvThreads, smem, stream>>>(maps, p);
+  return cudaGetLastError();
+}
+
+}  // namespace af

@@ -1,0 +1,62 @@
+// tcgen05 implicit-GEMM convolution for NHWC fp16 activations (sm_100a).
+//
+//   out[n, oh, ow, co] = act( scale[co] * sum_{kh,kw,ci} in[n, oh*s+kh-p, ow*s+kw-p, ci] * w[co, kh, kw, ci]
+//                             + bias[co] (+ residual[n, oh, ow, co]) )
+//
+// GEMM view: M = output pixels (128 per tile = a TW x TH x TN box of the output), N = Cout, K = KH*KW*Cin.
+// The A operand is never materialised: for every filter tap and 64-channel slice one 4-D TMA box
+// {64 ch, TW, TH, TN} of the *input* tensor is loaded at the tap's offset; TMA's out-of-bounds zero fill
+// implements the convolution padding, and stride-2 layers read from four "parity views" of the input
+// (base pointer offset by (h&1, w&1), strides doubled), so the same box shape serves every layer.
+// A box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the K-major
+// SWIZZLE_128B operand layout tcgen05.mma consumes.
+//
+// Replaces the cuDNN convolution + BatchNorm(eval) + ReLU/ReLU6 (+ residual add) call sites of the reference:
+//   ACT/models/resnet.py:94-114 (Bottleneck.forward), ACT/models/mobilenet.py:32-68, ACT/models/ppo.py:33-39.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+
+namespace af {
+
+constexpr int kConvBlockM = 128;
+constexpr int kConvBlockK = 64;          // fp16 elements per k-block = 128 B swizzle span
+constexpr int kConvMaxBlockN = 256;
+constexpr int kConvMaxStages = 8;
+constexpr int kConvThreads = 192;        // warp0: TMA producer, warp1: MMA issuer, warps2-5: epilogue
+constexpr int kConvSmemBudget = 220 * 1024;
+
+enum ConvAct : int { kActNone = 0, kActRelu = 1, kActRelu6 = 2 };
+
+struct ConvKernelParams {
+  // geometry of the output and of the tiling
+  int N, Ho, Wo, Cout;
+  int TW, TH, TN;                  // TW*TH*TN == 128
+  int tiles_w, tiles_h, tiles_n;   // number of boxes along each output dim
+  int n_blocks;                    // ceil(Cout / BN)
+  int BN;                          // tile N (multiple of 16, <= 256)
+  int KH, KW, stride, pad;
+  int cblks;                       // ceil(Cin / 64)
+  int stages;                      // smem pipeline depth
+  // epilogue
+  const float* scale;              // [n_blocks*BN]
+  const float* bias;               // [n_blocks*BN]
+  const __half* residual;          // NHWC, pixel stride res_stride, or nullptr
+  long long res_stride;
+  void* out;                       // NHWC, pixel stride out_stride (elements), fp16 or fp32
+  long long out_stride;
+  int out_f32;
+  int act;
+};
+
+struct ConvTensorMaps {
+  CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
+  CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
+};
+
+cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,
+                             cudaStream_t stream);
+size_t conv_gemm_smem_bytes(int BN, int* stages_out);
+
+}  // namespace af

@@ -1,0 +1,575 @@
+// HBM-bound helper kernels. All activations are NHWC fp16 unless the name says otherwise; math is fp32.
+#include "kernels.cuh"
+
+namespace af {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(long long total, int threads = kThreads) {
+  long long g = (total + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+// The reference evaluates floor(action * (H - P)) on fp32 tensors (ACT/models/utils.py:42): fp32 multiply, fp32
+// floor, truncating cast. Clamped so a malformed action can never index out of bounds.
+__device__ __forceinline__ int coord_from_action(float a, int H, int P) {
+  const float span = static_cast<float>(H - P);
+  int c = static_cast<int>(floorf(a * span));
+  c = max(0, min(c, H - P));
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------ crop
+__device__ __forceinline__ float4 load4_maybe_unaligned(const float* p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(kThreads)
+crop_nchw_f32_vec4_kernel(const float* __restrict__ img, const float* __restrict__ action,
+                          const int32_t* __restrict__ yx, float* __restrict__ out, int32_t* __restrict__ yx_out,
+                          int N, int C, int H, int W, int P) {
+  const int p4 = P >> 2;
+  const int prow = P / ROWS;   // rows handled per "slot": thread covers rows r, r+prow, ...
+  const long long total = static_cast<long long>(N) * C * prow * p4;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px4 = static_cast<int>(idx % p4);
+  long long t = idx / p4;
+  const int py = static_cast<int>(t % prow);
+  t /= prow;
+  const int c = static_cast<int>(t % C);
+  const int n = static_cast<int>(t / C);
+  int y0, x0;
+  if (yx != nullptr) {
+    y0 = max(0, min(yx[2 * n], H - P));
+    x0 = max(0, min(yx[2 * n + 1], W - P));
+  } else {
+    y0 = coord_from_action(action[2 * n], H, P);
+    x0 = min(coord_from_action(action[2 * n + 1], H, P), W - P);
+  }
+  if (yx_out != nullptr && c == 0 && py == 0 && px4 == 0) {
+    yx_out[2 * n] = y0;
+    yx_out[2 * n + 1] = x0;
+  }
+  const float* src = img + ((static_cast<long long>(n) * C + c) * H + y0) * W + x0 + px4 * 4;
+  float* dst = out + (static_cast<long long>(n) * C + c) * P * P + px4 * 4;
+  float4 v[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) v[r] = load4_maybe_unaligned(src + static_cast<long long>(py + r * prow) * W);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) *reinterpret_cast<float4*>(dst + static_cast<long long>(py + r * prow) * P) = v[r];
+}
+
+__global__ void __launch_bounds__(kThreads)
+crop_nchw_f32_scalar_kernel(const float* __restrict__ img, const float* __restrict__ action,
+                            const int32_t* __restrict__ yx, float* __restrict__ out, int32_t* __restrict__ yx_out,
+                            int N, int C, int H, int W, int P) {
+  const long long total = static_cast<long long>(N) * C * P * P;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % P);
+  long long t = idx / P;
+  const int py = static_cast<int>(t % P);
+  t /= P;
+  const int c = static_cast<int>(t % C);
+  const int n = static_cast<int>(t / C);
+  int y0, x0;
+  if (yx != nullptr) {
+    y0 = max(0, min(yx[2 * n], H - P));
+    x0 = max(0, min(yx[2 * n + 1], W - P));
+  } else {
+    y0 = coord_from_action(action[2 * n], H, P);
+    x0 = min(coord_from_action(action[2 * n + 1], H, P), W - P);
+  }
+  if (yx_out != nullptr && c == 0 && py == 0 && px == 0) {
+    yx_out[2 * n] = y0;
+    yx_out[2 * n + 1] = x0;
+  }
+  out[idx] = __ldg(img + ((static_cast<long long>(n) * C + c) * H + y0 + py) * W + x0 + px);
+}
+
+__global__ void action_to_yx_kernel(const float* __restrict__ action, int32_t* __restrict__ yx, int N, int H,
+                                    int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * N) yx[i] = coord_from_action(action[i], H, P);
+}
+
+// ------------------------------------------------------------------------------------------------ stem staging
+__global__ void __launch_bounds__(kThreads)
+stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, __half* __restrict__ out, int N,
+                   int H, int W, int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int kgroups = Kpad >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * kgroups;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kg = static_cast<int>(idx % kgroups);
+  long long pix = idx / kgroups;
+  const int ow = static_cast<int>(pix % Wo);
+  const int oh = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  int y0 = 0, x0 = 0;
+  if (yx != nullptr) {
+    y0 = max(0, min(yx[2 * n], H - P));
+    x0 = max(0, min(yx[2 * n + 1], W - P));
+  }
+  const int kreal = KH * KW * 3;
+  const float* base = frames + static_cast<long long>(n) * 3 * H * W;
+  __align__(16) __half vals[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg * 8 + j;
+    float v = 0.f;
+    if (k < kreal) {
+      const int tap = k / 3;
+      const int c = k - tap * 3;
+      const int kh = tap / KW;
+      const int kw = tap - kh * KW;
+      const int iy = oh * stride + kh - pad;
+      const int ix = ow * stride + kw - pad;
+      if (iy >= 0 && iy < P && ix >= 0 && ix < P)
+        v = __ldg(base + (static_cast<long long>(c) * H + (y0 + iy)) * W + (x0 + ix));
+    }
+    vals[j] = __float2half_rn(v);
+  }
+  *reinterpret_cast<uint4*>(out + pix * Kpad + kg * 8) = *reinterpret_cast<const uint4*>(vals);
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise 3x3
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return fminf(fmaxf(x, 0.f), 6.f);
+  return x;
+}
+
+__global__ void __launch_bounds__(kThreads)
+dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, const float* __restrict__ scale,
+                 const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int C, int stride,
+                 int Ho, int Wo, int act) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * c8n;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % c8n);
+  long long pix = idx / c8n;
+  const int ow = static_cast<int>(pix % Wo);
+  const int oh = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const int c = c8 * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int iy = oh * stride + kh - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ix = ow * stride + kw - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c));
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9c + (kh * 3 + kw) * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9c + (kh * 3 + kw) * C + c + 4));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      const float2 f0 = __half22float2(xh[0]), f1 = __half22float2(xh[1]), f2 = __half22float2(xh[2]),
+                   f3 = __half22float2(xh[3]);
+      acc[0] = fmaf(f0.x, w0.x, acc[0]);
+      acc[1] = fmaf(f0.y, w0.y, acc[1]);
+      acc[2] = fmaf(f1.x, w0.z, acc[2]);
+      acc[3] = fmaf(f1.y, w0.w, acc[3]);
+      acc[4] = fmaf(f2.x, w1.x, acc[4]);
+      acc[5] = fmaf(f2.y, w1.y, acc[5]);
+      acc[6] = fmaf(f3.x, w1.z, acc[6]);
+      acc[7] = fmaf(f3.y, w1.w, acc[7]);
+    }
+  }
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  uint4 ov;
+  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[2 * j], sc[2 * j], bi[2 * j]), act),
+                               act_apply(fmaf(acc[2 * j + 1], sc[2 * j + 1], bi[2 * j + 1]), act));
+  *reinterpret_cast<uint4*>(out + pix * C + c) = ov;
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+__global__ void __launch_bounds__(kThreads)
+maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int Ho,
+                    int Wo) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * c8n;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % c8n);
+  long long pix = idx / c8n;
+  const int ow = static_cast<int>(pix % Wo);
+  const int oh = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const __half2 ninf = __float2half2_rn(-65504.f);
+  __half2 m[4] = {ninf, ninf, ninf, ninf};
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int iy = oh * 2 + kh - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ix = ow * 2 + kw - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c8 * 8));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], xh[j]);
+    }
+  }
+  uint4 ov;
+  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oh2[j] = m[j];
+  *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = ov;
+}
+
+__global__ void __launch_bounds__(kThreads)
+avgpool_kernel(const __half* __restrict__ in, float* __restrict__ out_f32, long long out_f32_stride,
+               __half* __restrict__ out_f16, long long out_f16_stride, int N, int HW, int C) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * c8n;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % c8n);
+  const int n = static_cast<int>(idx / c8n);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const __half* p = in + static_cast<long long>(n) * HW * C + c8 * 8;
+  for (int i = 0; i < HW; ++i) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p + static_cast<long long>(i) * C));
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(xh[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  }
+  const float inv = 1.f / static_cast<float>(HW);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= inv;
+  if (out_f32 != nullptr) {
+    float* o = out_f32 + static_cast<long long>(n) * out_f32_stride + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = acc[j];
+  }
+  if (out_f16 != nullptr) {
+    __half* o = out_f16 + static_cast<long long>(n) * out_f16_stride + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(acc[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void __launch_bounds__(kThreads)
+nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int N, int HW, int C) {
+  // 32x32 smem transpose over (p, c) for one image per blockIdx.z
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads -> 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    tile[r][tx] = (p < HW && c < C) ? __half2float(in[(static_cast<long long>(n) * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (p < HW && c < C) out[(static_cast<long long>(n) * C + c) * HW + p] = tile[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int N, int C, int HW, int Cpad) {
+  const long long total = static_cast<long long>(N) * HW * Cpad;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cpad);
+  const long long np = idx / Cpad;
+  const int p = static_cast<int>(np % HW);
+  const int n = static_cast<int>(np / HW);
+  out[idx] = (c < C) ? __float2half_rn(__ldg(in + (static_cast<long long>(n) * C + c) * HW + p)) : __half(0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ GRU gates
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kThreads)
+gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float* __restrict__ hg,
+                 const float* __restrict__ h_prev, float* __restrict__ h_new, __half* __restrict__ h_new_f16,
+                 __half* __restrict__ hseq_f16, long long hseq_stride, float* __restrict__ hseq_f32,
+                 long long hseq_f32_stride, int B, int Hd) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Hd) return;
+  const int j = static_cast<int>(idx % Hd);
+  const int b = static_cast<int>(idx / Hd);
+  const float* x = xg + static_cast<long long>(b) * xg_stride;
+  const float* h = hg + static_cast<long long>(b) * 3 * Hd;
+  const float r = sigmoidf_(x[j] + h[j]);
+  const float z = sigmoidf_(x[Hd + j] + h[Hd + j]);
+  const float nn = tanhf(x[2 * Hd + j] + r * h[2 * Hd + j]);
+  const float hp = h_prev[idx];
+  const float hn = (1.f - z) * nn + z * hp;
+  h_new[idx] = hn;
+  if (h_new_f16 != nullptr) h_new_f16[idx] = __float2half_rn(hn);
+  if (hseq_f16 != nullptr) hseq_f16[static_cast<long long>(b) * hseq_stride + j] = __float2half_rn(hn);
+  if (hseq_f32 != nullptr) hseq_f32[static_cast<long long>(b) * hseq_f32_stride + j] = hn;
+}
+
+// ------------------------------------------------------------------------------------------------ policy heads
+__global__ void __launch_bounds__(kThreads)
+policy_head_kernel(const float* __restrict__ logits, long long logit_stride, int A, int grid_n, int rows, int H,
+                   int P, int32_t* __restrict__ action_idx, float* __restrict__ action_yx, int32_t* __restrict__ yx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = logits + static_cast<long long>(warp) * logit_stride;
+  // softmax exactly as exp(x - max) / sum, then argmax over the probabilities (first maximum wins).
+  float m = -INFINITY;
+  for (int i = lane; i < A; i += 32) m = fmaxf(m, x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int i = lane; i < A; i += 32) s += expf(x[i] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float best = -1.f;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < A; i += 32) {
+    const float p = expf(x[i] - m) / s;
+    if (p > best) {
+      best = p;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if (lane == 0) {
+    const int iy = best_i / grid_n, ix = best_i % grid_n;
+    // table entries are python doubles k/(n-1) rounded to fp32 (ACT/models/gfv_net.py:272-307)
+    const float ay = static_cast<float>(static_cast<double>(iy) / static_cast<double>(grid_n - 1));
+    const float ax = static_cast<float>(static_cast<double>(ix) / static_cast<double>(grid_n - 1));
+    if (action_idx != nullptr) action_idx[warp] = best_i;
+    if (action_yx != nullptr) {
+      action_yx[2 * warp] = ay;
+      action_yx[2 * warp + 1] = ax;
+    }
+    if (yx != nullptr) {
+      yx[2 * warp] = coord_from_action(ay, H, P);
+      yx[2 * warp + 1] = coord_from_action(ax, H, P);
+    }
+  }
+}
+
+__global__ void policy_head_continuous_kernel(const float* __restrict__ logits, long long logit_stride, int rows,
+                                              int H, int P, float* __restrict__ action_yx,
+                                              int32_t* __restrict__ yx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2) return;
+  const int r = i >> 1, k = i & 1;
+  const float a = sigmoidf_(logits[static_cast<long long>(r) * logit_stride + k]);
+  if (action_yx != nullptr) action_yx[i] = a;
+  if (yx != nullptr) yx[i] = coord_from_action(a, H, P);
+}
+
+// ------------------------------------------------------------------------------------------------ TSM / consensus
+__global__ void __launch_bounds__(kThreads)
+tsm_shift_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NT, int T, int HW, int C, int fold) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(NT) * HW * c8n;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % c8n);
+  const long long fp = idx / c8n;
+  const int p = static_cast<int>(fp % HW);
+  const int f = static_cast<int>(fp / HW);
+  const int t = f % T;
+  const int c = c8 * 8;
+  __align__(16) __half vals[8];
+  const long long frame = static_cast<long long>(HW) * C;
+  const __half* base = in + static_cast<long long>(f) * frame + static_cast<long long>(p) * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cc = c + j;
+    __half v;
+    if (cc < fold) v = (t + 1 < T) ? base[frame + cc] : __half(0.f);                 // from the next frame
+    else if (cc < 2 * fold) v = (t > 0) ? *(base - frame + cc) : __half(0.f);        // from the previous frame
+    else v = base[cc];
+    vals[j] = v;
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<long long>(f) * frame + static_cast<long long>(p) * C + c) =
+      *reinterpret_cast<const uint4*>(vals);
+}
+
+__global__ void consensus_avg_kernel(const float* __restrict__ in, const float* __restrict__ add,
+                                     float* __restrict__ out, int B, int T, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C, b = i / C;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += in[(static_cast<long long>(b) * T + t) * C + c];
+  s /= static_cast<float>(T);
+  if (add != nullptr) s += add[i];
+  out[i] = s;
+}
+
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+}  // namespace
+
+// ==================================================================================================== launchers
+cudaError_t launch_crop_nchw_f32(const float* img, const float* action, const int32_t* yx, float* out,
+                                 int32_t* yx_out, int N, int C, int H, int W, int P, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    if ((P % 16) == 0) {
+      const long long total = static_cast<long long>(N) * C * (P / 4) * (P / 4);
+      crop_nchw_f32_vec4_kernel<4><<<grid_for(total), kThreads, 0, s>>>(img, action, yx, out, yx_out, N, C, H, W, P);
+    } else {
+      const long long total = static_cast<long long>(N) * C * P * (P / 4);
+      crop_nchw_f32_vec4_kernel<1><<<grid_for(total), kThreads, 0, s>>>(img, action, yx, out, yx_out, N, C, H, W, P);
+    }
+  } else {
+    const long long total = static_cast<long long>(N) * C * P * P;
+    crop_nchw_f32_scalar_kernel<<<grid_for(total), kThreads, 0, s>>>(img, action, yx, out, yx_out, N, C, H, W, P);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, int P, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  action_to_yx_kernel<<<grid_for(2LL * N), kThreads, 0, s>>>(action, yx, N, H, P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* out, int N, int H, int W, int P,
+                               int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (Kpad / 8);
+  stem_im2col_kernel<<<grid_for(total), kThreads, 0, s>>>(frames, yx, out, N, H, W, P, KH, KW, stride, pad, Ho, Wo,
+                                                         Kpad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dwconv3x3(const __half* in, const float* w9c, const float* scale, const float* bias, __half* out,
+                             int N, int H, int W, int C, int stride, int act, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  dwconv3x3_kernel<<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, stride, Ho, Wo, act);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool3x3s2(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, N, H, W, C, Ho, Wo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_avgpool(const __half* in, float* out_f32, long long out_f32_stride, __half* out_f16,
+                           long long out_f16_stride, int N, int HW, int C, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(N) * (C / 8);
+  avgpool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out_f32, out_f32_stride, out_f16, out_f16_stride, N, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nhwc_f16_to_nchw_f32(const __half* in, float* out, int N, int HW, int C, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  dim3 grid((C + 31) / 32, (HW + 31) / 32, N);
+  nhwc_f16_to_nchw_f32_kernel<<<grid, kThreads, 0, s>>>(in, out, N, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_f32_to_nhwc_f16(const float* in, __half* out, int N, int C, int HW, int Cpad,
+                                        cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(N) * HW * Cpad;
+  nchw_f32_to_nhwc_f16_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, N, C, HW, Cpad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gru_gates(const float* xg, long long xg_stride, const float* hg, const float* h_prev,
+                             float* h_new, __half* h_new_f16, __half* hseq_f16, long long hseq_stride,
+                             float* hseq_f32, long long hseq_f32_stride, int B, int Hd, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  gru_gates_kernel<<<grid_for(static_cast<long long>(B) * Hd), kThreads, 0, s>>>(
+      xg, xg_stride, hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_policy_head(const float* logits, long long logit_stride, int A, int grid_n, int rows, int H,
+                               int P, int32_t* action_idx, float* action_yx, int32_t* yx, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  policy_head_kernel<<<grid_for(static_cast<long long>(rows) * 32), kThreads, 0, s>>>(
+      logits, logit_stride, A, grid_n, rows, H, P, action_idx, action_yx, yx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_policy_head_continuous(const float* logits, long long logit_stride, int rows, int H, int P,
+                                          float* action_yx, int32_t* yx, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  policy_head_continuous_kernel<<<grid_for(2LL * rows), kThreads, 0, s>>>(logits, logit_stride, rows, H, P,
+                                                                        action_yx, yx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tsm_shift(const __half* in, __half* out, int NT, int T, int HW, int C, int fold,
+                             cudaStream_t s) {
+  if (NT <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(NT) * HW * (C / 8);
+  tsm_shift_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, NT, T, HW, C, fold);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_consensus_avg(const float* in, const float* add, float* out, int B, int T, int C,
+                                 cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  consensus_avg_kernel<<<grid_for(static_cast<long long>(B) * C), kThreads, 0, s>>>(in, add, out, B, T, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  fill_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  f32_to_f16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace af

@@ -1,0 +1,373 @@
+"""Torch-facing wrappers over the C ABI: weight packing (one-off, torch ops) and kernel launches on NHWC fp16
+tensors.  torch is used for device memory and streams only; every compute launch goes through
+libadafocus_b200.so.  Nothing here falls back to torch ops for the hot path."""
+import ctypes
+import math
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6, ConvDesc, check
+
+BLOCK_K = 64
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def default_block_n(cout):
+    """Split Cout into the fewest <=256-wide tiles, each a multiple of 16."""
+    nb = (cout + 255) // 256
+    return min(256, round_up((cout + nb - 1) // nb, 16))
+
+
+class PackedConv:
+    """A convolution / linear layer in kernel layout.
+
+    w     fp16 [cout_pad, kh*kw*cblk*64]   K index = (r*kw+s)*cblk*64 + ci, zero padded
+    scale fp32 [cout_pad], bias fp32 [cout_pad]   (folded BatchNorm or linear bias)
+    """
+
+    def __init__(self, w, scale, bias, cin, cout, kh, kw, stride, pad, block_n, act):
+        self.w, self.scale, self.bias = w, scale, bias
+        self.cin, self.cout, self.kh, self.kw = cin, cout, kh, kw
+        self.stride, self.pad, self.block_n, self.act = stride, pad, block_n, act
+
+
+def fold_bn(bn_weight, bn_bias, running_mean, running_var, eps):
+    """BatchNorm2d in eval mode as y = x*scale + bias (fp32)."""
+    scale = bn_weight.float() / torch.sqrt(running_var.float() + eps)
+    bias = bn_bias.float() - running_mean.float() * scale
+    return scale, bias
+
+
+def pack_conv(weight, scale=None, bias=None, stride=1, pad=0, act=AF_ACT_NONE, block_n=None, device=None,
+              cin_perm=None):
+    """weight: (cout, cin, kh, kw) or (cout, cin) fp32 in torch layout -> PackedConv on `device`.
+
+    cin_perm: optional LongTensor; packed input channel j reads torch input channel cin_perm[j] (used to absorb the
+    NCHW-flatten vs NHWC-flatten difference of ACT/models/ppo.py:36-37)."""
+    w = weight.detach().float()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    device = device or w.device
+    w = w.to(device)
+    cout, cin, kh, kw = w.shape
+    if cin_perm is not None:
+        w = w[:, cin_perm.to(device)]
+    block_n = block_n or default_block_n(cout)
+    cout_pad = round_up(cout, block_n)
+    cblk = (cin + BLOCK_K - 1) // BLOCK_K
+    wp = torch.zeros(cout_pad, kh * kw, cblk * BLOCK_K, dtype=torch.float16, device=device)
+    wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).half()
+    wp = wp.reshape(cout_pad, kh * kw * cblk * BLOCK_K).contiguous()
+    sc = torch.ones(cout_pad, dtype=torch.float32, device=device)
+    bi = torch.zeros(cout_pad, dtype=torch.float32, device=device)
+    if scale is not None:
+        sc[:cout] = scale.detach().float().to(device)
+    if bias is not None:
+        bi[:cout] = bias.detach().float().to(device)
+    return PackedConv(wp, sc, bi, cin, cout, kh, kw, stride, pad, block_n, act)
+
+
+def pack_stem(weight, scale, bias, stride, pad, act, device=None, kpad=None):
+    """3-input-channel stem conv as a GEMM over the im2col matrix produced by af_stem_im2col:
+    k = (r*kw+s)*3 + c."""
+    w = weight.detach().float()
+    device = device or w.device
+    w = w.to(device)
+    cout, cin, kh, kw = w.shape
+    assert cin == 3
+    kreal = kh * kw * 3
+    kpad = kpad or round_up(kreal, BLOCK_K)
+    flat = torch.zeros(cout, kpad, dtype=torch.float32, device=device)
+    flat[:, :kreal] = w.permute(0, 2, 3, 1).reshape(cout, kreal)
+    pc = pack_conv(flat, scale, bias, 1, 0, act, device=device)
+    pc.stem = dict(kh=kh, kw=kw, stride=stride, pad=pad, kpad=kpad)
+    return pc
+
+
+class Workspace:
+    """Size-bucketed reuse of device buffers while a plan is being laid out.  Replay is in stream order, so a
+    buffer may be handed out again as soon as its last reader has been recorded."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free_lists = {}
+        self.all = []
+        self.total_bytes = 0
+
+    def alloc(self, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = round_up(max(n, 1) * torch.empty((), dtype=dtype).element_size(), 512)
+        lst = self.free_lists.get(nbytes)
+        if lst:
+            raw = lst.pop()
+        else:
+            raw = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.all.append(raw)
+            self.total_bytes += nbytes
+        t = raw[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        t._af_raw = raw
+        return t
+
+    def release(self, t):
+        raw = getattr(t, "_af_raw", None)
+        if raw is not None:
+            self.free_lists.setdefault(raw.numel(), []).append(raw)
+            t._af_raw = None
+
+
+class Engine:
+    """One per device: wraps af_ctx and exposes the kernels on torch tensors."""
+
+    def __init__(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.AfError("adafocus_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = _lib.Context(self.index)
+        self.lib = self.ctx.lib
+        self.h = self.ctx.handle
+        self.ws = None          # Workspace while recording
+        self._keep = None
+        self.launch_count = 0   # launches issued eagerly (not recorded)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype):
+        if self.ws is not None:
+            return self.ws.alloc(shape, dtype)
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def release(self, t):
+        if self.ws is not None:
+            self.ws.release(t)
+
+    def begin_plan(self):
+        check(self.lib.af_plan_begin(self.h), "af_plan_begin")
+        self.ws = Workspace(self.device)
+        self._keep = []
+
+    def keep(self, *tensors):
+        if self._keep is not None:
+            self._keep.extend(tensors)
+
+    def end_plan(self):
+        p = c_void_p()
+        check(self.lib.af_plan_end(self.h, byref(p)), "af_plan_end")
+        plan = _lib.Plan(self.lib, p, (self.ws.all, self._keep))
+        plan.workspace_bytes = self.ws.total_bytes
+        self.ws, self._keep = None, None
+        return plan
+
+    def _count(self):
+        if self.ws is None:
+            self.launch_count += 1
+
+    # ------------------------------------------------------------------ kernels
+    def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None):
+        """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given]."""
+        if shape is None:
+            n, h, w, cin = x.shape
+            in_stride = x.stride(2)
+        else:
+            n, h, w, cin, in_stride = shape
+        assert cin == pc.cin, (cin, pc.cin)
+        ho = (h + 2 * pc.pad - pc.kh) // pc.stride + 1
+        wo = (w + 2 * pc.pad - pc.kw) // pc.stride + 1
+        if out is None:
+            out = self.empty((n, ho, wo, pc.cout), torch.float32 if out_f32 else torch.float16)
+            out_stride = pc.cout
+        elif out_stride is None:
+            out_stride = out.stride(-2)
+        d = ConvDesc()
+        d.in_, d.w, d.scale, d.bias = x.data_ptr(), pc.w.data_ptr(), pc.scale.data_ptr(), pc.bias.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.out = out.data_ptr()
+        d.n, d.h, d.w_, d.cin, d.cout = n, h, w, cin, pc.cout
+        d.kh, d.kw, d.stride, d.pad = pc.kh, pc.kw, pc.stride, pc.pad
+        d.block_n = pc.block_n
+        d.act = pc.act if act is None else act
+        d.out_f32 = 1 if out_f32 else 0
+        d.in_stride, d.out_stride = in_stride, out_stride
+        d.res_stride = residual.stride(-2) if residual is not None else 0
+        check(self.lib.af_conv2d_nhwc_f16(self.h, byref(d), self._stream()), "af_conv2d_nhwc_f16")
+        self._count()
+        self.keep(x, pc.w, pc.scale, pc.bias, out, residual)
+        return out
+
+    def linear(self, x2d, pc, out=None, out_f32=False, act=None, out_stride=None):
+        """x2d: fp16 [M, K] (row stride >= K); C = x W^T as the 1x1 'conv' n=1,h=1,w=M."""
+        m, k = x2d.shape
+        if out is None:
+            out = self.empty((m, pc.cout), torch.float32 if out_f32 else torch.float16)
+            out_stride = pc.cout
+        self.conv(x2d, pc, out=out, act=act, out_f32=out_f32, out_stride=out_stride,
+                  shape=(1, 1, m, k, x2d.stride(0)))
+        return out
+
+    def stem(self, frames, pc, yx=None, patch=None):
+        """frames (N,3,H,W) fp32 NCHW -> NHWC fp16 stem output; crop at yx (N,2 int32) of size `patch` fused in."""
+        n, c, h, w = frames.shape
+        assert c == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
+        s = pc.stem
+        p = patch if patch is not None else h
+        ho = (p + 2 * s["pad"] - s["kh"]) // s["stride"] + 1
+        wo = (p + 2 * s["pad"] - s["kw"]) // s["stride"] + 1
+        col = self.empty((n * ho * wo, s["kpad"]), torch.float16)
+        check(self.lib.af_stem_im2col(self.h, _ptr(frames), _ptr(yx), _ptr(col), n, h, w, p, s["kh"], s["kw"],
+                                      s["stride"], s["pad"], s["kpad"], self._stream()), "af_stem_im2col")
+        self._count()
+        self.keep(frames, yx, col)
+        out = self.empty((n, ho, wo, pc.cout), torch.float16)
+        self.conv(col, pc, out=out, out_stride=pc.cout, shape=(1, 1, n * ho * wo, s["kpad"], s["kpad"]))
+        self.release(col)
+        return out
+
+    def dwconv3x3(self, x, w9c, scale, bias, stride, act=AF_ACT_RELU6):
+        n, h, w, c = x.shape
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+        out = self.empty((n, ho, wo, c), torch.float16)
+        check(self.lib.af_dwconv3x3_nhwc_f16(self.h, _ptr(x), _ptr(w9c), _ptr(scale), _ptr(bias), _ptr(out), n, h, w,
+                                             c, stride, act, self._stream()), "af_dwconv3x3_nhwc_f16")
+        self._count()
+        self.keep(x, w9c, scale, bias, out)
+        return out
+
+    def maxpool3x3s2(self, x):
+        n, h, w, c = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        out = self.empty((n, ho, wo, c), torch.float16)
+        check(self.lib.af_maxpool3x3s2_nhwc_f16(self.h, _ptr(x), _ptr(out), n, h, w, c, self._stream()),
+              "af_maxpool3x3s2_nhwc_f16")
+        self._count()
+        self.keep(x, out)
+        return out
+
+    def avgpool(self, x, out_f32=None, out_f32_stride=0, out_f16=None, out_f16_stride=0):
+        n, h, w, c = x.shape
+        check(self.lib.af_avgpool_nhwc_f16(self.h, _ptr(x), _ptr(out_f32), out_f32_stride, _ptr(out_f16),
+                                           out_f16_stride, n, h * w, c, self._stream()), "af_avgpool_nhwc_f16")
+        self._count()
+        self.keep(x, out_f32, out_f16)
+
+    def nhwc_to_nchw_f32(self, x, out=None):
+        n, h, w, c = x.shape
+        if out is None:
+            out = self.empty((n, c, h, w), torch.float32)
+        check(self.lib.af_nhwc_f16_to_nchw_f32(self.h, _ptr(x), _ptr(out), n, h * w, c, self._stream()),
+              "af_nhwc_f16_to_nchw_f32")
+        self._count()
+        self.keep(x, out)
+        return out
+
+    def nchw_to_nhwc_f16(self, x, cpad=None):
+        n, c, h, w = x.shape
+        cpad = cpad or round_up(c, 8)
+        out = self.empty((n, h, w, cpad), torch.float16)
+        check(self.lib.af_nchw_f32_to_nhwc_f16(self.h, _ptr(x), _ptr(out), n, c, h * w, cpad, self._stream()),
+              "af_nchw_f32_to_nhwc_f16")
+        self._count()
+        self.keep(x, out)
+        return out
+
+    def crop(self, img, action=None, yx=None, patch=None, out=None, yx_out=None):
+        n, c, h, w = img.shape
+        assert img.dtype == torch.float32 and img.is_contiguous()
+        if out is None:
+            out = self.empty((n, c, patch, patch), torch.float32)
+        check(self.lib.af_crop_nchw_f32(self.h, _ptr(img), _ptr(action), _ptr(yx), _ptr(out), _ptr(yx_out), n, c, h, w,
+                                        patch, self._stream()), "af_crop_nchw_f32")
+        self._count()
+        self.keep(img, action, yx, out, yx_out)
+        return out
+
+    def action_to_yx(self, action, h, patch):
+        n = action.shape[0]
+        yx = self.empty((n, 2), torch.int32)
+        check(self.lib.af_action_to_yx(self.h, _ptr(action), _ptr(yx), n, h, patch, self._stream()),
+              "af_action_to_yx")
+        self._count()
+        self.keep(action, yx)
+        return yx
+
+    def gru_gates(self, xg, xg_stride, hg, h_prev, h_new, h_new_f16=None, hseq_f16=None, hseq_stride=0,
+                  hseq_f32=None, hseq_f32_stride=0):
+        b, hd = h_prev.shape
+        check(self.lib.af_gru_gates(self.h, _ptr(xg), xg_stride, _ptr(hg), _ptr(h_prev), _ptr(h_new), _ptr(h_new_f16),
+                                    _ptr(hseq_f16), hseq_stride, _ptr(hseq_f32), hseq_f32_stride, b, hd,
+                                    self._stream()), "af_gru_gates")
+        self._count()
+        self.keep(xg, hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_f32)
+
+    def policy_head(self, logits, action_dim, h, patch, action_idx=None, action_yx=None, yx=None):
+        rows = logits.shape[0]
+        grid_n = int(round(math.sqrt(action_dim)))
+        check(self.lib.af_policy_head(self.h, _ptr(logits), logits.stride(0), action_dim, grid_n, rows, h, patch,
+                                      _ptr(action_idx), _ptr(action_yx), _ptr(yx), self._stream()), "af_policy_head")
+        self._count()
+        self.keep(logits, action_idx, action_yx, yx)
+
+    def policy_head_continuous(self, logits, h, patch, action_yx=None, yx=None):
+        rows = logits.shape[0]
+        check(self.lib.af_policy_head_continuous(self.h, _ptr(logits), logits.stride(0), rows, h, patch,
+                                                 _ptr(action_yx), _ptr(yx), self._stream()),
+              "af_policy_head_continuous")
+        self._count()
+        self.keep(logits, action_yx, yx)
+
+    def tsm_shift(self, x, t, fold):
+        nt, h, w, c = x.shape
+        out = self.empty((nt, h, w, c), torch.float16)
+        check(self.lib.af_tsm_shift_nhwc_f16(self.h, _ptr(x), _ptr(out), nt, t, h * w, c, fold, self._stream()),
+              "af_tsm_shift_nhwc_f16")
+        self._count()
+        self.keep(x, out)
+        return out
+
+    def consensus_avg(self, x, b, t, add=None, out=None):
+        c = x.shape[-1]
+        if out is None:
+            out = self.empty((b, c), torch.float32)
+        check(self.lib.af_consensus_avg(self.h, _ptr(x), _ptr(add), _ptr(out), b, t, c, self._stream()),
+              "af_consensus_avg")
+        self._count()
+        self.keep(x, add, out)
+        return out
+
+    def fill(self, t, v):
+        assert t.dtype == torch.float32
+        check(self.lib.af_fill_f32(self.h, _ptr(t), float(v), t.numel(), self._stream()), "af_fill_f32")
+        self._count()
+        self.keep(t)
+
+    def f32_to_f16(self, x, out=None):
+        if out is None:
+            out = self.empty(tuple(x.shape), torch.float16)
+        check(self.lib.af_f32_to_f16(self.h, _ptr(x), _ptr(out), x.numel(), self._stream()), "af_f32_to_f16")
+        self._count()
+        self.keep(x, out)
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device):
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(torch.device("cuda", idx))
+    return _engines[idx]

@@ -1,0 +1,147 @@
+/*
+ * adafocus_b200 -- C ABI of the B200 (sm_100a) AdaFocus offline-inference hot path.
+ *
+ * The reference (blackfeather-wang/AdaFocus @ 8c0f8d2) is pure Python/PyTorch and has no FFI; its boundary for
+ * this path is the Python surface of models/ (GFV.forward / glance / get_patch ...).  This header is the native
+ * boundary that the Python mirror in adafocus_b200/models/ binds with ctypes.  Each entry
+ * point names the reference call site it replaces.  Aliases: ACT/ = "Experiments on ActivityNet, FCVID and
+ * Mini-Kinetics/", STH/ = "Experiments on Something-Something V1&V2/".
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory (torch tensors' data_ptr()); the library never frees or keeps
+ *     them beyond the call, except that a recorded plan replays launches on the same pointers;
+ *   - every call is asynchronous on the given stream (a cudaStream_t passed as void*), never synchronises, and is
+ *     CUDA-graph capturable;
+ *   - return 0 on success, a negative af_status otherwise; af_last_error() gives a thread-local message;
+ *   - activations between layers are NHWC fp16 ("half"), accumulation and epilogues are fp32;
+ *   - there is no CPU fallback: without a CUDA device every launch returns AF_ERR_CUDA.
+ */
+#ifndef ADAFOCUS_B200_H_
+#define ADAFOCUS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AF_VERSION 100
+
+typedef enum af_status {
+  AF_OK = 0,
+  AF_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  AF_ERR_CUDA = -2,    /* CUDA runtime / driver error */
+  AF_ERR_STATE = -3    /* call not valid in the current recording state */
+} af_status;
+
+typedef enum af_act { AF_ACT_NONE = 0, AF_ACT_RELU = 1, AF_ACT_RELU6 = 2 } af_act;
+
+typedef struct af_ctx af_ctx;   /* one per device; calls on one ctx must be externally serialised */
+typedef struct af_plan af_plan; /* a recorded sequence of launches, replayable with fixed pointers */
+
+/* Convolution / GEMM descriptor for af_conv2d_nhwc_f16 (the tcgen05 implicit-GEMM kernel).
+ *   in : NHWC fp16 (n, h, w, cin), pixel stride in_stride elements (>= cin, multiple of 8)
+ *   w  : packed fp16 [cout_pad][kh*kw*cblk*64] with cblk = ceil(cin/64); k = ((r*kw+s)*cblk*64 + ci), zero padded;
+ *        cout_pad = ceil(cout/block_n)*block_n
+ *   out: NHWC fp16 or fp32 (n, ho, wo, cout), pixel stride out_stride
+ *   y  = act(scale[co]*conv + bias[co] (+ residual)), scale/bias have cout_pad entries.
+ * A plain GEMM C[M,N] = A[M,K] W[N,K]^T is the case n=1, h=1, w=M, cin=K, kh=kw=1, stride=1, pad=0. */
+typedef struct af_conv_desc {
+  const void* in;
+  const void* w;
+  const float* scale;
+  const float* bias;
+  const void* residual; /* NHWC fp16 with pixel stride res_stride, or NULL */
+  void* out;
+  int32_t n, h, w_, cin;
+  int32_t cout;
+  int32_t kh, kw, stride, pad;
+  int32_t block_n; /* multiple of 16, <= 256 */
+  int32_t act;     /* af_act */
+  int32_t out_f32; /* 0: fp16 output, 1: fp32 output */
+  int64_t in_stride, out_stride, res_stride;
+} af_conv_desc;
+
+int af_version(void);
+const char* af_last_error(void);
+
+int af_ctx_create(af_ctx** out, int device);
+int af_ctx_destroy(af_ctx* ctx);
+int af_ctx_sm_count(const af_ctx* ctx);
+
+/* Recording: between af_plan_begin and af_plan_end every kernel entry point called on ctx is appended to the plan
+ * (tensor maps and launch geometry are resolved once) instead of being launched.  af_plan_run replays the whole
+ * sequence natively on a stream -- this is how the T-step policy loop and the ~200 layer launches of one forward
+ * (ACT/models/gfv_net.py:95-133) run without returning to Python. */
+int af_plan_begin(af_ctx* ctx);
+int af_plan_end(af_ctx* ctx, af_plan** out);
+int af_plan_run(af_plan* plan, void* stream);
+int af_plan_num_launches(const af_plan* plan);
+int af_plan_destroy(af_plan* plan);
+
+/* get_patch(images, action_sequence, patch_size) -- ACT/models/utils.py:37-51 (= STH/models/utils.py:44-58).
+ * img (N,C,H,W) fp32 NCHW -> out (N,C,P,P) fp32.  Exactly one of action (N,2 fp32 in [0,1], coordinates computed
+ * as floor(a*(H-P)) in fp32 like the reference) and yx (N,2 int32) is non-NULL.  yx_out (N,2 int32) optional. */
+int af_crop_nchw_f32(af_ctx* ctx, const float* img, const float* action, const int32_t* yx, float* out,
+                     int32_t* yx_out, int N, int C, int H, int W, int P, void* stream);
+
+/* floor(action*(H-P)).int() -- ACT/models/utils.py:42. */
+int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H, int P, void* stream);
+
+/* Crop + fp32->fp16 + im2col staging that feeds a 3-channel stem convolution as a GEMM:
+ * ResNet conv1 7x7/2 pad 3 (ACT/models/resnet.py:138) on the patch selected by yx (fused get_patch), or
+ * MobileNet-V2 features[0] 3x3/2 pad 1 (ACT/models/mobilenet.py:105) on the whole frame (yx = NULL, P = H).
+ * frames (N,3,H,W) fp32 -> out [(N*Ho*Wo)][Kpad] fp16, k = (r*KW+s)*3 + c. */
+int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* out, int N, int H, int W, int P,
+                   int KH, int KW, int stride, int pad, int Kpad, void* stream);
+
+/* Conv2d + BatchNorm2d(eval, folded) + ReLU/ReLU6 (+ residual add) -- ACT/models/resnet.py:94-114,
+ * ACT/models/mobilenet.py:32-68, ACT/models/ppo.py:33-39; also every Linear/GRU projection as a 1x1 "conv". */
+int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* desc, void* stream);
+
+/* Depthwise 3x3 pad 1 + folded BN + activation (ACT/models/mobilenet.py:58); w9c fp32 [9][C]. */
+int af_dwconv3x3_nhwc_f16(af_ctx* ctx, const void* in, const float* w9c, const float* scale, const float* bias,
+                          void* out, int N, int H, int W, int C, int stride, int act, void* stream);
+
+/* MaxPool2d(3,2,1) -- ACT/models/resnet.py:141. */
+int af_maxpool3x3s2_nhwc_f16(af_ctx* ctx, const void* in, void* out, int N, int H, int W, int C, void* stream);
+
+/* Global average pool -- ACT/models/resnet.py:223 (avgpool), ACT/models/mobilenet.py:148 (mean([2,3])).
+ * Writes fp32 rows (stride out_f32_stride) and/or fp16 rows (stride out_f16_stride); this is also how the
+ * [global | local] feature concat of ACT/models/gfv_net.py:121,132 is assembled without torch.cat. */
+int af_avgpool_nhwc_f16(af_ctx* ctx, const void* in, float* out_f32, int64_t out_f32_stride, void* out_f16,
+                        int64_t out_f16_stride, int N, int HW, int C, void* stream);
+
+int af_nhwc_f16_to_nchw_f32(af_ctx* ctx, const void* in, float* out, int N, int HW, int C, void* stream);
+int af_nchw_f32_to_nhwc_f16(af_ctx* ctx, const float* in, void* out, int N, int C, int HW, int Cpad, void* stream);
+
+/* One GRU time step's gate math (torch.nn.GRU, gates r,z,n) -- ACT/models/ppo.py:80, ACT/models/gfv_net.py:431.
+ * xg (B,3H) row stride xg_stride = W_ih x + b_ih; hg (B,3H) = W_hh h + b_hh (both produced by af_conv2d_nhwc_f16). */
+int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* hg, const float* h_prev, float* h_new,
+                 void* h_new_f16, void* hseq_f16, int64_t hseq_stride, float* hseq_f32, int64_t hseq_f32_stride,
+                 int B, int Hd, void* stream);
+
+/* softmax -> argmax -> standard action table -> patch origin; ACT/models/ppo.py:84,94,
+ * ACT/models/gfv_net.py:272-307,345-347, ACT/models/utils.py:42.  grid_n = sqrt(action_dim). */
+int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,
+                   int32_t* action_idx, float* action_yx, int32_t* yx, void* stream);
+
+/* STH continuous policy head: action_mean = sigmoid(.) -- STH/models/ppo_continuous.py:61-63,106-107. */
+int af_policy_head_continuous(af_ctx* ctx, const float* logits, int64_t logit_stride, int rows, int H, int P,
+                              float* action_yx, int32_t* yx, void* stream);
+
+/* TemporalShift.shift -- STH/ops/temporal_shift.py:29-46, NHWC fp16, fold = C / shift_div. */
+int af_tsm_shift_nhwc_f16(af_ctx* ctx, const void* in, void* out, int NT, int T, int HW, int C, int fold,
+                          void* stream);
+
+/* ConsensusModule('avg') (+ glancer consensus) -- STH/ops/basic_ops.py:18-27, STH/models/gfv_net.py:170-172. */
+int af_consensus_avg(af_ctx* ctx, const float* in, const float* add, float* out, int B, int T, int C, void* stream);
+
+int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream);
+int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAFOCUS_B200_H_ */
