@@ -1,0 +1,161 @@
+"""MobileNet-V2 glance network (fG): parameter tree + engine runner.
+
+Mirror of ACT/models/mobilenet.py (MobileNetV2 :71-152, get_featmap :146-148): the nn.Module tree only carries
+parameters under the reference's names (`features.N...`, `classifier.1.*`) so reference checkpoints load unchanged;
+the arithmetic runs in adafocus_b200's CUDA kernels (NHWC fp16, tcgen05 1x1 convs + depthwise 3x3 kernels).
+"""
+import torch
+from torch import nn
+
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, pack_conv, pack_stem)
+
+# (expand t, channels c, repeats n, first stride s) -- the MobileNet-V2 paper's table, as at ACT/models/mobilenet.py:89-98
+_MBV2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                 (6, 320, 1, 1))
+
+
+def _round_channels(v, divisor=8):
+    r = max(divisor, int(v + divisor / 2) // divisor * divisor)
+    return r + divisor if r < 0.9 * v else r
+
+
+def _cbr(cin, cout, k=3, stride=1, groups=1):
+    """conv -> BN -> ReLU6 triple; children are named 0/1/2 like the reference's ConvBNReLU."""
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, groups=groups, bias=False),
+                         nn.BatchNorm2d(cout), nn.ReLU6(inplace=True))
+
+
+class InvertedResidual(nn.Module):
+    """Parameter container for one inverted-residual block (`conv` Sequential as in the reference)."""
+
+    def __init__(self, cin, cout, stride, expand):
+        super().__init__()
+        hidden = int(round(cin * expand))
+        self.stride, self.expand, self.cin, self.cout, self.hidden = stride, expand, cin, cout, hidden
+        self.use_res_connect = stride == 1 and cin == cout
+        layers = [] if expand == 1 else [_cbr(cin, hidden, k=1)]
+        layers += [_cbr(hidden, hidden, stride=stride, groups=hidden), nn.Conv2d(hidden, cout, 1, bias=False),
+                   nn.BatchNorm2d(cout)]
+        self.conv = nn.Sequential(*layers)
+
+    def forward(self, x):
+        raise NotImplementedError("InvertedResidual runs inside the fused engine plan (MobileNetV2.get_featmap)")
+
+
+class MobileNetV2(nn.Module):
+    def __init__(self, num_classes=1000, width_mult=1.0, round_nearest=8):
+        super().__init__()
+        cin = _round_channels(32 * width_mult, round_nearest)
+        self.last_channel = _round_channels(1280 * max(1.0, width_mult), round_nearest)
+        feats = [_cbr(3, cin, stride=2)]
+        for t, c, n, s in _MBV2_SETTING:
+            cout = _round_channels(c * width_mult, round_nearest)
+            for i in range(n):
+                feats.append(InvertedResidual(cin, cout, s if i == 0 else 1, t))
+                cin = cout
+        feats.append(_cbr(cin, self.last_channel, k=1))
+        self.features = nn.Sequential(*feats)
+        self.classifier = nn.Sequential(nn.Dropout(0.2), nn.Linear(self.last_channel, num_classes))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.zeros_(m.bias)
+        self._runner = None
+
+    @property
+    def feature_dim(self):
+        return self.last_channel
+
+    def runner(self):
+        """Packed-weight runner, rebuilt when parameters were reloaded / moved."""
+        key = _param_key(self)
+        if self._runner is None or self._runner.key != key:
+            self._runner = MobileNetV2Runner(self, key)
+        return self._runner
+
+    def get_featmap(self, x):
+        """(N,3,H,W) fp32 -> (feature map (N,1280,h,w) fp32, spatial mean (N,1280) fp32), ACT/models/mobilenet.py:146-148."""
+        eng = get_engine(x.device)
+        r = self.runner()
+        fmap = r.run(eng, x.contiguous())
+        n, h, w, c = fmap.shape
+        vec = torch.empty(n, c, dtype=torch.float32, device=x.device)
+        eng.avgpool(fmap, out_f32=vec, out_f32_stride=c)
+        return eng.nhwc_to_nchw_f32(fmap), vec
+
+    def forward(self, x):
+        raise NotImplementedError("classification head of fG is outside the inference hot path (stage-0 training)")
+
+
+def _param_key(module):
+    return tuple((p.data_ptr(), p._version) for p in module.state_dict().values())
+
+
+class MobileNetV2Runner:
+    """Weights of a MobileNetV2 in kernel layout + the layer schedule."""
+
+    def __init__(self, net, key):
+        self.key = key
+        dev = next(net.parameters()).device
+        f = net.features
+        c0, b0 = f[0][0], f[0][1]
+        s, b = fold_bn(b0.weight, b0.bias, b0.running_mean, b0.running_var, b0.eps)
+        self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
+        self.blocks = []
+        for blk in list(f)[1:-1]:
+            seq = list(blk.conv)
+            entry = {"res": blk.use_res_connect, "stride": blk.stride}
+            if blk.expand != 1:
+                cv, bn = seq[0][0], seq[0][1]
+                s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+                entry["expand"] = pack_conv(cv.weight, s, b, act=AF_ACT_RELU6, device=dev)
+                seq = seq[1:]
+            else:
+                entry["expand"] = None
+            dw, bn = seq[0][0], seq[0][1]
+            s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            entry["dw_w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
+            entry["dw_s"], entry["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
+            pw, bn = seq[1], seq[2]
+            s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev)
+            self.blocks.append(entry)
+        cl, bl = f[-1][0], f[-1][1]
+        s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
+        self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
+
+    def run(self, eng, frames, tsm=None):
+        """frames (N,3,H,W) fp32 contiguous -> (N,h,w,1280) NHWC fp16. tsm=(T, shift_div) applies the temporal shift
+        to the input of every residual block's first 1x1 conv (STH/models/gfv_net.py:238-241)."""
+        x = eng.stem(frames, self.stem)
+        for e in self.blocks:
+            inp = x
+            y = x
+            if tsm is not None and e["res"]:
+                y = eng.tsm_shift(y, tsm[0], y.shape[-1] // tsm[1])
+            if e["expand"] is not None:
+                h = eng.conv(y, e["expand"])
+                if y is not inp:
+                    eng.release(y)
+            else:
+                h = y
+            d = eng.dwconv3x3(h, e["dw_w"], e["dw_s"], e["dw_b"], e["stride"])
+            if h is not inp:
+                eng.release(h)
+            x = eng.conv(d, e["project"], residual=inp if e["res"] else None)
+            eng.release(d)
+            eng.release(inp)
+        out = eng.conv(x, self.last)
+        eng.release(x)
+        return out
+
+
+def mobilenet_v2(pretrained=False, progress=True, **kwargs):
+    """Constructor with the reference's signature (ACT/models/mobilenet.py:155-169). ImageNet weights are not
+    downloadable here; `pretrained` is accepted and ignored (checkpoints are loaded by the caller)."""
+    return MobileNetV2(**kwargs)

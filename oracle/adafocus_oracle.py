@@ -1,0 +1,220 @@
+"""ORACLE -- test infrastructure only.  CPU fp32 restatement of the AdaFocus offline-inference hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file; the
+product (adafocus_b200/) never does.  It restates, with plain torch.nn.functional calls on CPU fp32 tensors and
+explicit GRU gate equations, what the reference computes, driven directly by the reference's checkpoint dict
+({'glancer','focuser','fc','policy'}); each function cites the reference lines it follows
+(ACT/ = "Experiments on ActivityNet, FCVID and Mini-Kinetics/", STH/ = "Experiments on Something-Something V1&V2/").
+
+Pinning: the reference ships no tests or golden vectors.  The oracle is pinned against the
+reference's own classes executed in the build container: tests/golden/make_golden.py imports /root/reference, loads
+the same seeded synthetic checkpoint through the reference's load_state_dict sequence and stores its outputs in
+tests/golden/*.npz; tests/test_oracle.py checks this file against those vectors and against the get_patch
+known-answer table of SURVEY.md section 8 (a5).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+
+# MobileNet-V2 block table (expand, channels, repeats, stride): ACT/models/mobilenet.py:89-98
+MBV2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                (6, 320, 1, 1))
+RESNET_LAYERS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+
+
+# ------------------------------------------------------------------------------------------------ crop
+def patch_coordinates(action, image_size, patch_size):
+    """floor(action * (image_size - patch_size)).int() on fp32 -- ACT/models/utils.py:42."""
+    a = np.asarray(action, dtype=np.float32)
+    return np.floor(a * np.float32(image_size - patch_size)).astype(np.int32)
+
+
+def get_patch(images, action_sequence, patch_size):
+    """ACT/models/utils.py:37-51 (= STH/models/utils.py:44-58): per-sample slice at the floored coordinates; rows come
+    from action[:,0], columns from action[:,1]; image_size is images.shape[2] for both axes."""
+    images = np.asarray(images)
+    n = images.shape[0]
+    coord = patch_coordinates(action_sequence, images.shape[2], patch_size)
+    out = np.empty((n, images.shape[1], patch_size, patch_size), dtype=images.dtype)
+    for i in range(n):
+        y, x = int(coord[i, 0]), int(coord[i, 1])
+        out[i] = images[i, :, y:y + patch_size, x:x + patch_size]
+    return out
+
+
+def standard_actions(action_dim):
+    """ACT/models/gfv_net.py:272-307: n x n grid of (row, col) = (iy/(n-1), ix/(n-1)), row-major, stored as fp32."""
+    n = int(round(math.sqrt(action_dim)))
+    return np.array([[iy / (n - 1), ix / (n - 1)] for iy in range(n) for ix in range(n)], dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ CNN pieces
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False,
+                        0.0, BN_EPS)
+
+
+def temporal_shift(x, n_segment, fold_div):
+    """STH/ops/temporal_shift.py:29-46."""
+    nt, c, h, w = x.shape
+    x = x.view(nt // n_segment, n_segment, c, h, w)
+    fold = c // fold_div
+    out = torch.zeros_like(x)
+    out[:, :-1, :fold] = x[:, 1:, :fold]
+    out[:, 1:, fold:2 * fold] = x[:, :-1, fold:2 * fold]
+    out[:, :, 2 * fold:] = x[:, :, 2 * fold:]
+    return out.view(nt, c, h, w)
+
+
+def mobilenet_v2_features(x, sd, prefix="net.features.", tsm=None):
+    """ACT/models/mobilenet.py:32-68,104-118 (ConvBNReLU = conv, BN(eval), ReLU6; InvertedResidual).
+    tsm=(n_segment, fold_div) shifts the input of the first conv of residual blocks (STH/models/gfv_net.py:238-241)."""
+    def cbr(x, p, stride, groups):
+        w = sd[p + "0.weight"]
+        x = F.conv2d(x, w, None, stride, (w.shape[-1] - 1) // 2, 1, groups)
+        return F.relu6(_bn(x, sd, p + "1."))
+
+    x = cbr(x, prefix + "0.", 2, 1)
+    idx, cin = 1, 32
+    for t, c, n, s in MBV2_SETTING:
+        for i in range(n):
+            stride = s if i == 0 else 1
+            p = f"{prefix}{idx}.conv."
+            hidden = cin * t
+            res = stride == 1 and cin == c
+            y = x
+            if tsm is not None and res:
+                y = temporal_shift(y, tsm[0], tsm[1])
+            k = 0
+            if t != 1:
+                y = cbr(y, f"{p}{k}.", 1, 1)
+                k += 1
+            y = cbr(y, f"{p}{k}.", stride, hidden)
+            k += 1
+            y = F.conv2d(y, sd[f"{p}{k}.weight"])
+            y = _bn(y, sd, f"{p}{k + 1}.")
+            x = x + y if res else y
+            cin = c
+            idx += 1
+    return cbr(x, f"{prefix}{idx}.", 1, 1)
+
+
+def mobilenet_v2_get_featmap(x, sd, prefix="net.features."):
+    """ACT/models/mobilenet.py:146-148: (feature map, mean over H,W)."""
+    f = mobilenet_v2_features(x, sd, prefix)
+    return f, f.mean([2, 3])
+
+
+def resnet_trunk(x, sd, prefix="net.", layers=(3, 4, 6, 3), pooled=True, tsm=None):
+    """ACT/models/resnet.py:211-225 with Bottleneck.forward :94-114 (stride on conv2); fc not applied.
+    tsm=(n_segment, fold_div, n_round) shifts conv1's input of every n_round-th block of a stage
+    (STH/ops/temporal_shift.py:113-135, blockres)."""
+    x = F.conv2d(x, sd[prefix + "conv1.weight"], None, 2, 3)
+    x = F.relu(_bn(x, sd, prefix + "bn1."))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, nblocks in enumerate(layers, start=1):
+        for bi in range(nblocks):
+            p = f"{prefix}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            idn = x
+            y = x
+            if tsm is not None and bi % tsm[2] == 0:
+                y = temporal_shift(y, tsm[0], tsm[1])
+            w1 = sd.get(p + "conv1.weight", sd.get(p + "conv1.net.weight"))
+            y = F.relu(_bn(F.conv2d(y, w1), sd, p + "bn1."))
+            y = F.relu(_bn(F.conv2d(y, sd[p + "conv2.weight"], None, stride, 1), sd, p + "bn2."))
+            y = _bn(F.conv2d(y, sd[p + "conv3.weight"]), sd, p + "bn3.")
+            if (p + "downsample.0.weight") in sd:
+                idn = _bn(F.conv2d(x, sd[p + "downsample.0.weight"], None, stride), sd, p + "downsample.1.")
+            x = F.relu(y + idn)
+    if pooled:
+        return F.adaptive_avg_pool2d(x, (1, 1))
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ recurrent pieces
+def gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
+    """torch.nn.GRU single step, gates ordered r,z,n: n = tanh(W_in x + b_in + r*(W_hn h + b_hn)); h' = (1-z)*n + z*h."""
+    gi = x @ w_ih.t() + b_ih
+    gh = h @ w_hh.t() + b_hh
+    hd = h.shape[1]
+    r = torch.sigmoid(gi[:, :hd] + gh[:, :hd])
+    z = torch.sigmoid(gi[:, hd:2 * hd] + gh[:, hd:2 * hd])
+    n = torch.tanh(gi[:, 2 * hd:] + r * gh[:, 2 * hd:])
+    return (1 - z) * n + z * h
+
+
+def policy_encode(state, sd):
+    """ACT/models/ppo.py:33-39: 1x1 conv (no bias) -> ReLU -> Flatten (NCHW order) -> Linear -> ReLU."""
+    s = F.relu(F.conv2d(state, sd["state_encoder.0.weight"]))
+    s = s.flatten(1)
+    return F.relu(s @ sd["state_encoder.3.weight"].t() + sd["state_encoder.3.bias"])
+
+
+def policy_act(state, h, sd):
+    """ACT/models/ppo.py:67-96, eval branch: returns (action index via argmax of softmax probs, new hidden, probs)."""
+    s = policy_encode(state, sd)
+    h = gru_cell(s, h, sd["gru.weight_ih_l0"], sd["gru.weight_hh_l0"], sd["gru.bias_ih_l0"], sd["gru.bias_hh_l0"])
+    probs = torch.softmax(h @ sd["actor.0.weight"].t() + sd["actor.0.bias"], dim=-1)
+    return probs.max(1)[1], h, probs
+
+
+def recurrent_classifier(features, sd):
+    """ACT/models/gfv_net.py:427-435: GRU over (B,T,F) from h0 = 0, dropout(eval) = identity, fc on every step."""
+    b, t, _ = features.shape
+    h = torch.zeros(b, sd["gru.weight_hh_l0"].shape[1])
+    outs = []
+    for i in range(t):
+        h = gru_cell(features[:, i], h, sd["gru.weight_ih_l0"], sd["gru.weight_hh_l0"], sd["gru.bias_ih_l0"],
+                     sd["gru.bias_hh_l0"])
+        outs.append(h)
+    out = torch.stack(outs, 1)
+    logits = out.reshape(b * t, -1) @ sd["fc.weight"].t() + sd["fc.bias"]
+    last_out = logits.reshape(b, t, -1)[:, -1, :].reshape(b, -1)
+    return logits, last_out
+
+
+# ------------------------------------------------------------------------------------------------ whole path (ACT)
+@torch.no_grad()
+def act_forward(inp, scan, ck, patch_size=128, action_dim=49, with_glancer=True, actions_override=None,
+                layers=(3, 4, 6, 3)):
+    """GFV.forward(one_step=True) of the ACT tree -- ACT/models/gfv_net.py:95-133 -- on CPU fp32.
+
+    inp (B,3T,H,W), scan (B,3T,g,g) torch fp32.  Returns a dict with every stage's output.  actions_override
+    (B,T) int64 replaces the policy's argmax (used for staged parity tests)."""
+    inp, scan = inp.float().cpu(), scan.float().cpu()
+    b, tc, h, w = inp.shape
+    t = tc // 3
+    frames = inp.view(b, t, 3, h, w)
+    g = scan.shape[-1]
+    fmap, gvec = mobilenet_v2_get_featmap(scan.view(b * t, 3, g, g), ck["glancer"])          # glance(), :152-158
+    fmap = fmap.view(b, t, *fmap.shape[1:])
+    gvec = gvec.view(b, t, -1)
+    table = torch.from_numpy(standard_actions(action_dim))
+    hid = torch.zeros(b, ck["policy"]["gru.weight_hh_l0"].shape[1])                           # restart_batch, ppo.py:68-70
+    feats, actions, coords, patches, lfeats, probs_all = [], [], [], [], [], []
+    for step in range(t):                                                                     # gfv_net.py:110
+        a, hid, probs = policy_act(fmap[:, step], hid, ck["policy"])
+        if actions_override is not None:
+            a = actions_override[:, step]
+        std = table[a]                                                                        # :345-347
+        img = frames[:, step]
+        coords.append(patch_coordinates(std.numpy(), h, patch_size))
+        patch = torch.from_numpy(get_patch(img.numpy(), std.numpy(), patch_size))             # utils.py:37-51
+        lf = resnet_trunk(patch, ck["focuser"], "net.", layers).view(b, -1)                   # :331
+        feats.append(torch.cat([gvec[:, step], lf], 1) if with_glancer else lf)               # :120-122
+        actions.append(a)
+        patches.append(patch)
+        lfeats.append(lf)
+        probs_all.append(probs)
+    features = torch.stack(feats, 1)                                                          # :132
+    logits, last_out = recurrent_classifier(features, ck["fc"])                               # :133
+    return {
+        "fmap": fmap, "gvec": gvec, "actions": torch.stack(actions, 1), "coords": np.stack(coords, 1),
+        "patches": torch.stack(patches, 1), "lfeat": torch.stack(lfeats, 1), "features": features,
+        "probs": torch.stack(probs_all, 1), "logits": logits, "last_out": last_out,
+    }

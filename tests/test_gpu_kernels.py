@@ -1,0 +1,263 @@
+"""Kernel-level parity on the B200, every launch through the C ABI (ctypes -> libadafocus_b200.so).
+
+Integer / byte work (crop, coordinates, argmax, shift, max-pool) must be bit-exact against the oracle; floating-point
+kernels are compared with a plain PyTorch fp32 reference of the same op on fp16-rounded operands, tolerance stated
+per test."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from adafocus_b200.engine import get_engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return get_engine(torch.device("cuda", 0))
+
+
+DEV = "cuda:0"
+
+
+# ------------------------------------------------------------------------------------------------ crop (bit-exact)
+@pytest.mark.parametrize("p", [96, 128, 144, 130, 224, 1])
+def test_crop_bit_exact_vs_oracle(eng, p):
+    from oracle import adafocus_oracle as orc
+    g = torch.Generator().manual_seed(11 + p)
+    n = 37
+    img = torch.randn(n, 3, 224, 224, generator=g)
+    act = torch.rand(n, 2, generator=g)
+    act[0] = torch.tensor([0.0, 0.0])
+    act[1] = torch.tensor([1.0, 1.0])
+    act[2] = torch.tensor([0.5, 1.0])
+    yx = torch.empty(n, 2, dtype=torch.int32, device=DEV)
+    out = eng.crop(img.to(DEV), action=act.to(DEV), patch=p, yx_out=yx)
+    torch.cuda.synchronize()
+    ref = orc.get_patch(img.numpy(), act.numpy(), p)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(yx.cpu().numpy(), orc.patch_coordinates(act.numpy(), 224, p))
+
+
+def test_crop_kat_and_golden(eng, golden_dir):
+    from oracle import adafocus_oracle as orc
+    kat = np.load(os.path.join(golden_dir, "get_patch_kat.npz"))
+    for n, p in ((7, 128), (7, 96), (7, 160), (7, 192), (5, 144), (6, 112), (8, 176)):
+        grid = torch.from_numpy(orc.standard_actions(n * n)).to(DEV)
+        yx = eng.action_to_yx(grid, 224, p)
+        assert np.array_equal(yx.cpu().numpy(), kat[f"grid{n}_p{p}"])
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(4, 3, 224, 224, generator=g).to(DEV)
+    acts = torch.from_numpy(kat["rand_actions"]).to(DEV)
+    for p in (96, 128, 144, 130):
+        out = eng.crop(img, action=acts, patch=p).cpu()
+        assert np.array_equal(out[:, :, 0, :4].numpy(), kat[f"rand_p{p}_first"])
+        assert np.allclose(out.double().sum(dim=(1, 2, 3)).numpy(), kat[f"rand_p{p}_sum"], rtol=0, atol=1e-6)
+
+
+def test_crop_multichannel_and_empty(eng):
+    from oracle import adafocus_oracle as orc
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(5, 36, 64, 64, generator=g)          # STH: one (y,x) per video crops all 3*T_f channels
+    act = torch.rand(5, 2, generator=g)
+    out = eng.crop(img.to(DEV), action=act.to(DEV), patch=40)
+    assert np.array_equal(out.cpu().numpy(), orc.get_patch(img.numpy(), act.numpy(), 40))
+    empty = eng.crop(torch.empty(0, 3, 32, 32, device=DEV), action=torch.empty(0, 2, device=DEV), patch=16)
+    assert empty.shape == (0, 3, 16, 16)
+    yx = torch.tensor([[3, 7], [0, 0]], dtype=torch.int32, device=DEV)
+    out = eng.crop(img[:2].to(DEV), yx=yx, patch=16).cpu()
+    assert torch.equal(out[0], img[0, :, 3:19, 7:23]) and torch.equal(out[1], img[1, :, :16, :16])
+
+
+def test_crop_rejects_bad_arguments(eng):
+    from adafocus_b200._lib import AfError
+    img = torch.zeros(1, 3, 32, 32, device=DEV)
+    with pytest.raises(AfError):
+        eng.crop(img, action=torch.zeros(1, 2, device=DEV), patch=64)      # P > H
+    with pytest.raises(AfError):
+        eng.crop(img, patch=16)                                            # neither action nor yx
+
+
+def test_public_get_patch_matches_oracle(eng):
+    from adafocus_b200.models.utils import get_patch
+    from oracle import adafocus_oracle as orc
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(64, 3, 224, 224, generator=g)
+    act = torch.from_numpy(orc.standard_actions(49))[torch.randint(0, 49, (64,), generator=g)]
+    out = get_patch(img.to(DEV), act.to(DEV), 128)
+    assert np.array_equal(out.cpu().numpy(), orc.get_patch(img.numpy(), act.numpy(), 128))
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 conv
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, act, residual, out_f32, block_n
+    (1, 1, 128, 64, 64, 1, 1, 0, 0, False, True, 64),
+    (1, 1, 300, 192, 96, 1, 1, 0, 0, False, False, None),
+    (1, 1, 2, 1024, 3072, 1, 1, 0, 0, False, True, 32),        # GRU step: 2 rows, box larger than the tensor
+    (2, 16, 16, 64, 128, 1, 1, 0, 1, False, False, None),
+    (2, 16, 16, 64, 64, 3, 1, 1, 1, True, False, None),
+    (3, 16, 16, 128, 128, 3, 2, 1, 1, False, False, None),
+    (2, 16, 16, 256, 512, 1, 2, 0, 0, False, False, None),
+    (2, 9, 9, 24, 144, 3, 1, 1, 2, False, False, None),
+    (2, 9, 9, 32, 48, 3, 2, 1, 0, False, False, None),
+    (20, 4, 4, 512, 512, 3, 1, 1, 1, True, False, None),
+    (1, 1, 77, 1024, 49, 1, 1, 0, 0, False, True, None),        # actor head: Cout not a multiple of 8
+    (3, 7, 7, 320, 1280, 1, 1, 0, 2, False, False, None),
+    (64, 32, 32, 64, 256, 1, 1, 0, 1, False, False, None),      # > 148 tiles: persistent loop + TMEM double buffer
+    (32, 16, 16, 128, 128, 3, 1, 1, 1, True, False, 64),
+    (5, 18, 18, 128, 128, 3, 2, 1, 1, False, False, None),      # P=144 shapes (36 -> 18 -> 9)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
+def test_conv_vs_torch_fp32(eng, case):
+    from adafocus_b200.engine import pack_conv
+    n, h, w, cin, cout, k, stride, pad, act, res, out_f32, bn = case
+    torch.manual_seed(hash(case) % 1000)
+    x = torch.randn(n, h, w, cin, device=DEV).half()
+    wt = (torch.randn(cout, cin, k, k, device=DEV) / math.sqrt(cin * k * k)).half().float()
+    scale = torch.rand(cout, device=DEV) + 0.5
+    bias = torch.randn(cout, device=DEV) * 0.1
+    pc = pack_conv(wt, scale, bias, stride, pad, act, block_n=bn, device=DEV)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    r = torch.randn(n, ho, wo, cout, device=DEV).half() if res else None
+    cstride = (cout + 7) // 8 * 8
+    out = torch.zeros(n, ho, wo, cstride, device=DEV, dtype=torch.float32 if out_f32 else torch.float16)
+    eng.conv(x, pc, out=out, residual=r, out_f32=out_f32, out_stride=cstride)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride, pad)
+    ref = ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    ref = ref.clamp(min=0) if act == 1 else ref.clamp(0, 6) if act == 2 else ref
+    ref = ref.permute(0, 2, 3, 1)
+    got = out[..., :cout].float()
+    # fp16 operands are identical on both sides; differences are fp32 summation order (+ fp16 output rounding)
+    tol = 1e-3 if out_f32 else 4e-3
+    assert torch.allclose(got, ref, rtol=tol, atol=tol), float((got - ref).abs().max())
+    assert float(out[..., cout:].abs().max() if cstride > cout else 0.0) == 0.0      # padding columns untouched
+
+
+def test_stem_im2col_conv_vs_torch(eng):
+    """Crop fused into the stem staging + 7x7/2 conv as a GEMM == conv2d(get_patch(...))."""
+    from adafocus_b200.engine import pack_stem
+    from oracle import adafocus_oracle as orc
+    torch.manual_seed(4)
+    n, p = 6, 128
+    frames = torch.randn(n, 3, 224, 224, device=DEV)
+    yx = torch.tensor([[0, 0], [96, 96], [16, 80], [48, 0], [95, 1], [33, 64]], dtype=torch.int32, device=DEV)
+    wt = (torch.randn(64, 3, 7, 7, device=DEV) / math.sqrt(147)).half().float()
+    scale, bias = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV) * 0.1
+    pc = pack_stem(wt, scale, bias, stride=2, pad=3, act=1, device=DEV)
+    out = eng.stem(frames, pc, yx=yx, patch=p)
+    patches = torch.stack([frames[i, :, y:y + p, x:x + p] for i, (y, x) in enumerate(yx.tolist())])
+    ref = F.conv2d(patches.half().float(), wt, None, 2, 3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    ref = ref.clamp(min=0).permute(0, 2, 3, 1)
+    assert out.shape == (n, 64, 64, 64)
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3), float((out.float() - ref).abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+@pytest.mark.parametrize("stride,c,hw", [(1, 32, 14), (2, 96, 15), (2, 144, 56), (1, 960, 7)])
+def test_dwconv3x3(eng, stride, c, hw):
+    torch.manual_seed(c)
+    x = torch.randn(3, hw, hw, c, device=DEV).half()
+    w = torch.randn(c, 1, 3, 3, device=DEV) / 3
+    scale, bias = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.1
+    out = eng.dwconv3x3(x, w.reshape(c, 9).t().contiguous(), scale, bias, stride)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride, 1, 1, c)
+    ref = (ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).clamp(0, 6).permute(0, 2, 3, 1)
+    assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("hw", [64, 72, 9])
+def test_maxpool_bit_exact(eng, hw):
+    x = torch.randn(4, hw, hw, 64, device=DEV).half()
+    out = eng.maxpool3x3s2(x)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).half()
+    assert torch.equal(out, ref)
+
+
+def test_avgpool_and_layout(eng):
+    x = torch.randn(9, 7, 7, 1280, device=DEV).half()
+    o32 = torch.zeros(9, 1280, device=DEV)
+    o16 = torch.zeros(9, 3328, device=DEV, dtype=torch.float16)
+    eng.avgpool(x, out_f32=o32, out_f32_stride=1280, out_f16=o16[:, 2048:], out_f16_stride=3328)
+    ref = x.float().mean(dim=(1, 2))
+    assert torch.allclose(o32, ref, rtol=1e-5, atol=1e-6)
+    assert torch.equal(o16[:, 2048:], ref.half()) or torch.allclose(o16[:, 2048:].float(), ref, atol=1e-3)
+    assert float(o16[:, :2048].abs().max()) == 0.0
+    nchw = eng.nhwc_to_nchw_f32(x)
+    assert torch.equal(nchw, x.float().permute(0, 3, 1, 2).contiguous())
+    back = eng.nchw_to_nhwc_f16(nchw)
+    assert torch.equal(back, x)
+
+
+def test_gru_gates_vs_torch(eng):
+    torch.manual_seed(0)
+    b, hd = 5, 1024
+    gru = torch.nn.GRU(hd, hd).to(DEV)
+    x = torch.randn(1, b, hd, device=DEV)
+    h0 = torch.randn(1, b, hd, device=DEV) * 0.5
+    with torch.no_grad():
+        _, h1 = gru(x, h0)
+        xg = x[0] @ gru.weight_ih_l0.t() + gru.bias_ih_l0
+        hg = h0[0] @ gru.weight_hh_l0.t() + gru.bias_hh_l0
+    h_new = torch.empty(b, hd, device=DEV)
+    h16 = torch.empty(b, hd, device=DEV, dtype=torch.float16)
+    eng.gru_gates(xg.contiguous(), 3 * hd, hg.contiguous(), h0[0].contiguous(), h_new, h16)
+    assert torch.allclose(h_new, h1[0], rtol=1e-5, atol=2e-6)
+    assert torch.equal(h16, h_new.half())
+
+
+@pytest.mark.parametrize("a,p", [(49, 128), (25, 96), (36, 160), (64, 192), (100, 144)])
+def test_policy_head_argmax_and_coords(eng, a, p):
+    from oracle import adafocus_oracle as orc
+    torch.manual_seed(a)
+    rows = 301
+    stride = (a + 7) // 8 * 8
+    logits = torch.randn(rows, stride, device=DEV) * 3
+    logits[0, :a] = 1.25                      # all tied -> first index
+    logits[1, 5] = logits[1, 9] = 50.0        # two-way tie -> lower index
+    idx = torch.empty(rows, dtype=torch.int32, device=DEV)
+    ayx = torch.empty(rows, 2, device=DEV)
+    yx = torch.empty(rows, 2, dtype=torch.int32, device=DEV)
+    eng.policy_head(logits, a, 224, p, idx, ayx, yx)
+    probs = torch.softmax(logits[:, :a].cpu(), dim=-1)
+    ref_idx = probs.max(1)[1]
+    assert int(idx[0]) == 0 and int(idx[1]) == 5
+    assert torch.equal(idx.cpu().long()[2:], ref_idx[2:])
+    table = orc.standard_actions(a)
+    std = table[idx.cpu().numpy()]
+    assert np.array_equal(ayx.cpu().numpy(), std)
+    assert np.array_equal(yx.cpu().numpy(), orc.patch_coordinates(std, 224, p))
+
+
+def test_tsm_shift_bit_exact(eng):
+    from oracle import adafocus_oracle as orc
+    for c, t in ((64, 8), (24, 4), (256, 12), (96, 3)):
+        x = torch.randn(2 * t, 5, 5, c, device=DEV).half()
+        out = eng.tsm_shift(x, t, c // 8)
+        ref = orc.temporal_shift(x.float().cpu().permute(0, 3, 1, 2).contiguous(), t, 8).permute(0, 2, 3, 1).half()
+        assert torch.equal(out.cpu(), ref)
+
+
+def test_plan_replay_matches_eager(eng):
+    from adafocus_b200.engine import pack_conv
+    torch.manual_seed(1)
+    x = torch.randn(4, 8, 8, 64, device=DEV).half()
+    pc = pack_conv(torch.randn(64, 64, 3, 3, device=DEV) / 24, None, None, 1, 1, 1, device=DEV)
+    eager = eng.conv(eng.conv(x, pc), pc).clone()
+    eng.begin_plan()
+    y1 = eng.conv(x, pc)
+    y2 = eng.conv(y1, pc)
+    plan = eng.end_plan()
+    assert plan.num_launches == 2
+    y2.zero_()
+    plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, eager)

@@ -1,0 +1,73 @@
+"""The oracle (oracle/adafocus_oracle.py) against golden vectors produced by the reference's own classes
+(tests/golden/make_golden.py) and against the get_patch known-answer table.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from adafocus_b200 import synth
+from adafocus_b200.models.gfv_net import GFV
+from oracle import adafocus_oracle as orc
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def _ck(args):
+    model = GFV(args)
+    return synth.synth_checkpoint_act(model, synth.SEED)
+
+
+def test_get_patch_kat_table(golden_dir):
+    kat = np.load(os.path.join(golden_dir, "get_patch_kat.npz"))
+    # coordinates of the shipped grids
+    expect = {(7, 128): [0, 16, 32, 48, 64, 80, 96], (7, 96): [0, 21, 42, 64, 85, 106, 128],
+              (7, 160): [0, 10, 21, 32, 42, 53, 64], (7, 192): [0, 5, 10, 16, 21, 26, 32],
+              (5, 144): [0, 20, 40, 60, 80]}
+    for (n, p), vals in expect.items():
+        grid = orc.standard_actions(n * n)
+        c = orc.patch_coordinates(grid, 224, p)
+        assert sorted(set(c[:, 0].tolist())) == vals
+        assert np.array_equal(c, kat[f"grid{n}_p{p}"])
+    for n, p in ((6, 112), (8, 176)):
+        assert np.array_equal(orc.patch_coordinates(orc.standard_actions(n * n), 224, p), kat[f"grid{n}_p{p}"])
+    assert orc.patch_coordinates(np.array([[0.5, 1.0]], np.float32), 224, 128).tolist() == [[48, 96]]
+
+
+def test_get_patch_matches_reference_outputs(golden_dir):
+    kat = np.load(os.path.join(golden_dir, "get_patch_kat.npz"))
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(4, 3, 224, 224, generator=g).numpy()
+    acts = kat["rand_actions"]
+    for p in (96, 128, 144, 130):
+        out = orc.get_patch(img, acts, p)
+        assert out.shape == (4, 3, p, p)
+        assert np.array_equal(orc.patch_coordinates(acts, 224, p), kat[f"rand_p{p}_coords"])
+        assert np.array_equal(out[:, :, 0, :4], kat[f"rand_p{p}_first"])
+        assert np.allclose(out.astype(np.float64).sum(axis=(1, 2, 3)), kat[f"rand_p{p}_sum"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,over,batch", [
+    ("t4_p96_b3", dict(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3),
+    ("c3_b2", dict(), 2),
+])
+def test_act_forward_matches_reference(golden_dir, tag, over, batch):
+    gold = np.load(os.path.join(golden_dir, f"act_{tag}.npz"))
+    args = synth.act_args(**over)
+    ck = _ck(args)
+    x = synth.synth_clips(batch, args.num_segments, args.input_size, synth.SEED)
+    assert bool(gold["scan_equals_input"])            # F.interpolate to glance_size=224 is the identity
+    out = orc.act_forward(x, x, ck, args.patch_size, args.action_dim)
+    # integer / byte work: exact
+    assert np.array_equal(out["actions"].numpy(), gold["actions"])
+    assert np.array_equal(out["coords"], gold["coords"])
+    assert np.array_equal(out["patches"][:, :, :, :2, :2].numpy(), gold["patch_corner"])
+    assert np.allclose(out["patches"].double().sum(dim=(2, 3, 4)).numpy(), gold["patch_checksum"], rtol=0, atol=1e-9)
+    # floating point: same fp32 math up to summation order (oneDNN kernels differ with batch shape / threads)
+    np.testing.assert_allclose(out["gvec"].numpy(), gold["gvec"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["fmap"][:, :, ::64].numpy(), gold["fmap_sample"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["lfeat"].numpy(), gold["lfeat"], rtol=1e-4, atol=1e-5)
+    # logits pass through a 16-step GRU written out gate by gate here vs torch's fused GRU in the reference
+    np.testing.assert_allclose(out["logits"].numpy(), gold["logits"], rtol=1e-3, atol=3e-4)
+    np.testing.assert_allclose(out["last_out"].numpy(), gold["last_out"], rtol=1e-3, atol=3e-4)
+    assert np.array_equal(out["last_out"].argmax(1).numpy(), gold["last_out"].argmax(1))
