@@ -41,6 +41,8 @@ SIGNATURES = {
     "af_plan_run": (c_int, [c_void_p, c_void_p]),
     "af_plan_num_launches": (c_int, [c_void_p]),
     "af_plan_destroy": (c_int, [c_void_p]),
+    "af_plan_mark": (c_int, [c_void_p, POINTER(c_int)]),
+    "af_plan_mark_elapsed_ms": (c_int, [c_void_p, c_int, c_int, POINTER(c_float)]),
     "af_crop_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "af_action_to_yx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -124,6 +126,13 @@ class Plan:
 
     def run(self, stream):
         check(self.lib.af_plan_run(self.handle, c_void_p(stream)), "af_plan_run")
+
+    def elapsed_ms(self, mark_a, mark_b):
+        """Device time between two marks of the last completed replay (synchronise first)."""
+        ms = c_float()
+        check(self.lib.af_plan_mark_elapsed_ms(self.handle, int(mark_a), int(mark_b), byref(ms)),
+              "af_plan_mark_elapsed_ms")
+        return ms.value
 
     def __del__(self):
         try:

@@ -35,6 +35,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct af_plan {
   std::vector<Launch> launches;
+  std::vector<cudaEvent_t> marks;
+  int kernel_launches = 0;
+  ~af_plan() {
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
+  }
 };
 
 struct af_ctx {
@@ -51,6 +56,7 @@ int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
   if (ctx == nullptr) return fail(AF_ERR_INVALID, std::string(name) + ": null ctx");
   if (ctx->recording) {
     ctx->current->launches.push_back(std::move(fn));
+    ctx->current->kernel_launches += 1;
     return AF_OK;
   }
   cudaError_t e = fn(static_cast<cudaStream_t>(stream));
@@ -173,7 +179,28 @@ int af_plan_run(af_plan* plan, void* stream) {
   return AF_OK;
 }
 
-int af_plan_num_launches(const af_plan* plan) { return plan ? static_cast<int>(plan->launches.size()) : 0; }
+int af_plan_num_launches(const af_plan* plan) { return plan ? plan->kernel_launches : 0; }
+
+int af_plan_mark(af_ctx* ctx, int* mark_index) {
+  if (ctx == nullptr || !ctx->recording) return fail(AF_ERR_STATE, "af_plan_mark: only valid while recording");
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreate(&ev);
+  if (e != cudaSuccess) return fail_cuda(e, "af_plan_mark: cudaEventCreate");
+  af_plan* plan = ctx->current;
+  plan->marks.push_back(ev);
+  if (mark_index != nullptr) *mark_index = static_cast<int>(plan->marks.size()) - 1;
+  plan->launches.push_back([ev](cudaStream_t s) { return cudaEventRecord(ev, s); });
+  return AF_OK;
+}
+
+int af_plan_mark_elapsed_ms(af_plan* plan, int mark_a, int mark_b, float* ms) {
+  if (plan == nullptr || ms == nullptr || mark_a < 0 || mark_b < 0 ||
+      mark_a >= static_cast<int>(plan->marks.size()) || mark_b >= static_cast<int>(plan->marks.size()))
+    return fail(AF_ERR_INVALID, "af_plan_mark_elapsed_ms: bad mark index");
+  cudaError_t e = cudaEventElapsedTime(ms, plan->marks[mark_a], plan->marks[mark_b]);
+  if (e != cudaSuccess) return fail_cuda(e, "af_plan_mark_elapsed_ms (synchronise the stream first)");
+  return AF_OK;
+}
 
 int af_plan_destroy(af_plan* plan) {
   delete plan;

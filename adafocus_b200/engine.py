@@ -172,6 +172,14 @@ class Engine:
         self.ws, self._keep = None, None
         return plan
 
+    def mark(self, name=None):
+        """Insert a timing mark into the plan being recorded; returns its index (no-op -> None when eager)."""
+        if self.ws is None:
+            return None
+        i = ctypes.c_int()
+        check(self.lib.af_plan_mark(self.h, byref(i)), "af_plan_mark")
+        return i.value
+
     def _count(self):
         if self.ws is None:
             self.launch_count += 1
@@ -288,6 +296,8 @@ class Engine:
         assert img.dtype == torch.float32 and img.is_contiguous()
         if out is None:
             out = self.empty((n, c, patch, patch), torch.float32)
+        if n == 0:
+            return out
         check(self.lib.af_crop_nchw_f32(self.h, _ptr(img), _ptr(action), _ptr(yx), _ptr(out), _ptr(yx_out), n, c, h, w,
                                         patch, self._stream()), "af_crop_nchw_f32")
         self._count()

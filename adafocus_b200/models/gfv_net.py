@@ -232,15 +232,21 @@ class _FusedPlan:
         gdim = model.glancer.feature_dim if model.with_glancer else 0
         eng.begin_plan()
         try:
+            m0 = eng.mark()
             fmap = glancer.run(eng, self.scan.view(b * t, 3, g, g))
             if model.with_glancer:
                 eng.avgpool(fmap, out_f16=self.feat16, out_f16_stride=fdim)
+            m1 = eng.mark()
             self.yx, self.action_idx, self.action_yx = policy.rollout(eng, fmap, b, t, h, p)
             eng.release(fmap)
+            m2 = eng.mark()
             lmap = focuser.run(eng, self.input.view(b * t, 3, h, w), yx=self.yx, patch=p)
             eng.avgpool(lmap, out_f16=self.feat16[:, gdim:], out_f16_stride=fdim)
             eng.release(lmap)
+            m3 = eng.mark()
             clf.sequence(eng, self.feat16, b, t, self.logits)
+            m4 = eng.mark()
+            self.marks = {"fG": (m0, m1), "policy": (m1, m2), "fL": (m2, m3), "head": (m3, m4), "total": (m0, m4)}
         finally:
             self.plan = eng.end_plan()
         self.keys = (_param_key(model.glancer.net), _param_key(model.focuser.net),
@@ -248,6 +254,10 @@ class _FusedPlan:
 
     def run(self):
         self.plan.run(torch.cuda.current_stream(self.input.device).cuda_stream)
+
+    def stage_ms(self):
+        """Device time of each stage in the last completed replay (call after a synchronize)."""
+        return {k: self.plan.elapsed_ms(a, b) for k, (a, b) in self.marks.items()}
 
 
 class GFV(nn.Module):
@@ -293,8 +303,8 @@ class GFV(nn.Module):
         raise NotImplementedError("training stages are outside the inference hot path")
 
     # ------------------------------------------------------------------ fused stage-3 inference
-    def fused_plan(self, b, t, h, w, g, device, share_scan):
-        key = (b, t, h, w, g, share_scan, str(device))
+    def fused_plan(self, b, t, h, w, g, device, share_scan, slot=0):
+        key = (b, t, h, w, g, share_scan, str(device), slot)
         plan = self._plans.get(key)
         if plan is not None:
             cur = (_param_key(self.glancer.net), _param_key(self.focuser.net),

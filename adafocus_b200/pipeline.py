@@ -1,0 +1,54 @@
+"""End-to-end evaluation from HOST buffers: the call a user of the reference's validate() loop makes.
+
+`StreamingEvaluator.run(batches)` takes pinned host tensors in the reference's input contract -- (B, 3T, H, W) fp32,
+ImageNet-normalised, as produced by the reference's DataLoader (ACT/ops/transforms.py:303-336) -- copies each batch
+host->device, runs the fused stage-3 forward (ACT/main_dist.py:367-371) and copies the per-clip logits back to the
+host.  Two input slots and two CUDA streams overlap the H2D copy of batch i+1 with the compute of batch i; the policy
+loop, the crop and all ~190 layer launches replay natively from one recorded plan per slot.
+"""
+import torch
+
+
+class StreamingEvaluator:
+    def __init__(self, model, batch, device, slots=2):
+        self.model, self.batch, self.device = model, batch, torch.device(device)
+        t, s = model.num_segments, model.input_size
+        self.plans = [model.fused_plan(batch, t, s, s, model.glance_size, self.device, True, slot=i)
+                      for i in range(slots)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.compute_stream = torch.cuda.Stream(self.device)
+        self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(slots)]
+        self.num_classes = self.plans[0].num_classes
+        self.t = t
+        self.out_host = [torch.empty(batch, self.num_classes, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.h2d_bytes = batch * 3 * t * s * s * 4
+        self.d2h_bytes = batch * self.num_classes * 4
+
+    def run(self, host_batches, collect=True):
+        """host_batches: iterable of pinned (B,3T,H,W) fp32 CPU tensors.  Returns the list of (B,C) host logits
+        (last time step, the reference's `pred`)."""
+        results = []
+        n = len(self.plans)
+        for s in range(n):
+            self.consumed[s].record(self.compute_stream)
+        for i, hb in enumerate(host_batches):
+            s = i % n
+            plan = self.plans[s]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.consumed[s])        # slot's previous compute has read its input
+                plan.input.copy_(hb, non_blocking=True)
+                self.copied[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self.copied[s])
+                plan.run()
+                self.consumed[s].record(self.compute_stream)
+                last = plan.logits.view(self.batch, self.t, -1)[:, -1, : self.num_classes]
+                if collect:
+                    out = torch.empty(self.batch, self.num_classes, dtype=torch.float32).pin_memory()
+                else:
+                    out = self.out_host[s]
+                out.copy_(last, non_blocking=True)
+                results.append(out)
+        self.compute_stream.synchronize()
+        return results

@@ -77,7 +77,11 @@ int af_ctx_sm_count(const af_ctx* ctx);
 int af_plan_begin(af_ctx* ctx);
 int af_plan_end(af_ctx* ctx, af_plan** out);
 int af_plan_run(af_plan* plan, void* stream);
-int af_plan_num_launches(const af_plan* plan);
+int af_plan_num_launches(const af_plan* plan); /* kernel launches per replay (marks excluded) */
+/* Timing marks: while recording, af_plan_mark inserts a CUDA event record at this point of the sequence; after a
+ * replay has completed, af_plan_mark_elapsed_ms gives the device time between two marks of that replay. */
+int af_plan_mark(af_ctx* ctx, int* mark_index);
+int af_plan_mark_elapsed_ms(af_plan* plan, int mark_a, int mark_b, float* ms);
 int af_plan_destroy(af_plan* plan);
 
 /* get_patch(images, action_sequence, patch_size) -- ACT/models/utils.py:37-51 (= STH/models/utils.py:44-58).

@@ -1,0 +1,188 @@
+"""Path-level parity on the B200: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs and
+against the committed golden vectors of the reference's own classes.
+
+Bars (stated here, measured in profiles/): integer / index work -- policy actions, crop coordinates, cropped bytes,
+class index -- bit-exact; floating point -- fp16 tensor-core operands with fp32 accumulation against an fp32 oracle:
+  logits: max |err| <= 5e-3 * max(1, max|logit|) and rms(err)/rms(logit) <= 2e-3   (observed ~3e-3 / ~8e-4)
+  fG / fL features: rms(err)/rms(ref) <= 4e-3                                       (observed ~1.7e-3 / ~4e-4)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel_rms(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+
+
+def _model(over, batch):
+    from adafocus_b200 import synth
+    from adafocus_b200.models.gfv_net import GFV
+    args = synth.act_args(**over)
+    model = GFV(args)
+    ck = synth.synth_checkpoint_act(model)
+    synth.load_checkpoint_act(model, ck)
+    model = model.to(DEV)
+    assert model.eval() is None          # reference quirk: GFV.train() returns None (ACT/models/gfv_net.py:60-62)
+    x = synth.synth_clips(batch, args.num_segments, args.input_size)
+    return args, model, ck, x
+
+
+@pytest.fixture(scope="module")
+def c3():
+    from oracle import adafocus_oracle as orc
+    args, model, ck, x = _model({}, 2)
+    torch.set_num_threads(os.cpu_count() or 8)
+    ref = orc.act_forward(x, x, ck, args.patch_size, args.action_dim)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        logits, last = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)
+    torch.cuda.synchronize()
+    return dict(args=args, model=model, ck=ck, x=x, xd=xd, ref=ref, logits=logits, last=last)
+
+
+def test_end_to_end_vs_oracle(c3):
+    ref, model, args = c3["ref"], c3["model"], c3["args"]
+    plan = model.last_plan
+    b, t = 2, args.num_segments
+    assert c3["logits"].shape == (b * t, args.num_classes) and c3["last"].shape == (b, args.num_classes)
+    acts = plan.action_idx.view(b, t).cpu().long()
+    assert torch.equal(acts, ref["actions"])                                        # policy argmax: exact
+    assert np.array_equal(plan.yx.view(b, t, 2).cpu().numpy(), ref["coords"])       # crop origins: exact
+    assert np.array_equal(plan.action_yx.view(b, t, 2).cpu().numpy(),
+                          orc_table(args.action_dim)[ref["actions"].numpy()])
+    scale = max(1.0, float(ref["logits"].abs().max()))
+    assert float((c3["logits"].cpu() - ref["logits"]).abs().max()) <= 5e-3 * scale
+    assert _rel_rms(c3["logits"], ref["logits"]) <= 2e-3
+    assert torch.equal(c3["last"].argmax(1).cpu(), ref["last_out"].argmax(1))       # class index: exact
+    assert torch.equal(c3["last"], c3["logits"].view(b, t, -1)[:, -1])
+
+
+def orc_table(action_dim):
+    from oracle import adafocus_oracle as orc
+    return orc.standard_actions(action_dim)
+
+
+def test_end_to_end_vs_reference_golden(c3, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "act_c3_b2.npz"))
+    plan = c3["model"].last_plan
+    assert np.array_equal(plan.action_idx.view(2, 16).cpu().numpy(), gold["actions"])
+    assert np.array_equal(plan.yx.view(2, 16, 2).cpu().numpy(), gold["coords"])
+    scale = max(1.0, float(np.abs(gold["logits"]).max()))
+    assert np.abs(c3["logits"].cpu().numpy() - gold["logits"]).max() <= 5e-3 * scale
+    assert np.array_equal(c3["last"].argmax(1).cpu().numpy(), gold["last_out"].argmax(1))
+
+
+def test_staged_glance(c3):
+    """fG alone: GFV.glance() returns the reference's layout (B,T,1280,7,7) fp32 + (B,T,1280)."""
+    fmap, vec = c3["model"].glance(c3["xd"])
+    assert fmap.shape == (2, 16, 1280, 7, 7) and fmap.dtype == torch.float32 and vec.shape == (2, 16, 1280)
+    assert _rel_rms(fmap, c3["ref"]["fmap"]) <= 4e-3
+    assert _rel_rms(vec, c3["ref"]["gvec"]) <= 2e-3
+
+
+def test_staged_focus_on_oracle_patches(c3):
+    """fL alone on the oracle's patches (independent of the policy): ResNet.get_featmap(pooled=True)."""
+    p = c3["args"].patch_size
+    patches = c3["ref"]["patches"].reshape(32, 3, p, p).to(DEV)
+    feat = c3["model"].focuser.net.get_featmap(patches, pooled=True)
+    assert feat.shape == (32, 2048, 1, 1)
+    assert _rel_rms(feat.view(2, 16, -1), c3["ref"]["lfeat"]) <= 4e-3
+
+
+def test_staged_policy_on_oracle_features(c3):
+    """pi alone, reference call pattern (one act() per step with Memory), fed with the ORACLE's fp32 glance maps."""
+    from adafocus_b200.models.ppo import Memory
+    pol = c3["model"].focuser.policy
+    mem = Memory()
+    fmap = c3["ref"]["fmap"].to(DEV)
+    got = []
+    for step in range(16):
+        a = pol.select_action(fmap[:, step].contiguous(), mem, restart_batch=(step == 0), training=False)
+        got.append(a.cpu())
+    assert torch.equal(torch.stack(got, 1), c3["ref"]["actions"])
+    assert len(mem.hidden) == 17
+
+
+def test_staged_classifier_on_oracle_features(c3):
+    logits, last = c3["model"].classifier(c3["ref"]["features"].to(DEV))
+    assert _rel_rms(logits, c3["ref"]["logits"]) <= 2e-3
+    assert torch.equal(last.argmax(1).cpu(), c3["ref"]["last_out"].argmax(1))
+
+
+def test_reference_style_step_loop_matches_fused(c3):
+    """Drive the model exactly like the reference's Python loop (ACT/models/gfv_net.py:104-133): glance, then per step
+    focuser(input, state, restart_batch) and torch.cat -- must agree with the fused plan."""
+    model, xd = c3["model"], c3["xd"]
+    b, t = 2, 16
+    frames = xd.view(b, t, 3, 224, 224)
+    fmap, vec = model.glance(xd)
+    feats = []
+    for step in range(t):
+        lf, (_, std) = model.focuser(input=frames[:, step].contiguous(), state=fmap[:, step].contiguous(),
+                                     restart_batch=(step == 0), training=False)
+        feats.append(torch.cat([vec[:, step], lf.view(b, -1)], 1))
+    logits, last = model.classifier(torch.stack(feats, 1))
+    assert float((logits - c3["logits"]).abs().max()) <= 5e-3
+    assert torch.equal(last.argmax(1), c3["last"].argmax(1))
+
+
+def test_small_config_vs_golden_and_determinism(golden_dir):
+    from oracle import adafocus_oracle as orc
+    over = dict(num_segments=4, patch_size=96, action_dim=36, num_classes=51)
+    args, model, ck, x = _model(over, 3)
+    xd = x.to(DEV)
+    out1 = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)
+    out2 = model(input=xd.clone(), scan=xd.clone(), training=False, backbone_pred=False, one_step=True, gpu=0)
+    assert torch.equal(out1[0], out2[0]) and torch.equal(out1[1], out2[1])        # two eval forwards are identical
+    gold = np.load(os.path.join(golden_dir, "act_t4_p96_b3.npz"))
+    plan = model.last_plan
+    assert np.array_equal(plan.action_idx.view(3, 4).cpu().numpy(), gold["actions"])
+    assert np.array_equal(plan.yx.view(3, 4, 2).cpu().numpy(), gold["coords"])
+    assert np.abs(out1[0].cpu().numpy() - gold["logits"]).max() <= 5e-3 * max(1.0, float(np.abs(gold["logits"]).max()))
+    assert np.array_equal(out1[1].argmax(1).cpu().numpy(), gold["last_out"].argmax(1))
+
+
+def test_weights_reload_invalidates_packed_copy():
+    from adafocus_b200 import synth
+    args, model, ck, x = _model(dict(num_segments=2, patch_size=96, action_dim=25, num_classes=10), 1)
+    xd = x.to(DEV)
+    a = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)[0].clone()
+    ck2 = synth.synth_checkpoint_act(model, seed=99)
+    synth.load_checkpoint_act(model, ck2)
+    b = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)[0].clone()
+    assert not torch.equal(a, b)
+    synth.load_checkpoint_act(model, ck)
+    c = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)[0]
+    assert torch.equal(a, c)
+
+
+def test_full_size_properties():
+    """cfg3 at bench size (64 clips): size-independent properties -- per-clip independence (a clip's logits do not
+    depend on its batch mates), crop round trip through the public get_patch, determinism."""
+    from adafocus_b200.models.utils import get_patch
+    args, model, ck, x8 = _model({}, 8)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    xd = torch.randn(64, 48, 224, 224, device=DEV, generator=g)
+    xd[:8] = x8.to(DEV)
+    big = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)
+    plan = model.last_plan
+    yx = plan.yx.clone()
+    ayx = plan.action_yx.clone()
+    big = (big[0].clone(), big[1].clone())
+    small = model(input=xd[:8].contiguous(), scan=xd[:8].contiguous(), training=False, backbone_pred=False,
+                  one_step=True, gpu=0)
+    assert float((small[1] - big[1][:8]).abs().max()) <= 1e-5          # same kernels, same per-row arithmetic
+    assert torch.equal(small[1].argmax(1), big[1][:8].argmax(1))
+    frames = xd.view(64 * 16, 3, 224, 224)
+    patches = get_patch(frames, ayx, 128)
+    i = 777
+    y0, x0 = yx[i].tolist()
+    assert torch.equal(patches[i], frames[i, :, y0:y0 + 128, x0:x0 + 128])
+    assert int(yx.min()) >= 0 and int(yx.max()) <= 96
