@@ -313,6 +313,15 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
     const cuuint32_t bbox[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.BN)};
     if (!encode_map(ctx, &maps.b, d->w, 2, dims, strides, bbox, &err)) return fail(AF_ERR_CUDA, err);
   }
+  // fp16 outputs leave through the smem-staged TMA store when 64-channel slices never straddle an n-block
+  p.tma_store = (!d->out_f32 && d->cout % 8 == 0 && (p.BN % 64 == 0 || p.n_blocks == 1)) ? 1 : 0;
+  if (p.tma_store) {
+    const cuuint64_t opix_b = static_cast<cuuint64_t>(d->out_stride) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
+                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(p.N)};
+    const cuuint64_t strides[3] = {opix_b, opix_b * p.Wo, opix_b * p.Wo * p.Ho};
+    if (!encode_map(ctx, &maps.out, d->out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
   const int sms = ctx->sm_count;
   return dispatch(ctx, stream, "af_conv2d_nhwc_f16",
                   [=](cudaStream_t s) { return af::launch_conv_gemm(maps, p, sms, s); });

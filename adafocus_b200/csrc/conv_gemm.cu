@@ -19,6 +19,9 @@ struct __align__(8) ConvSmemCtrl {
 
 constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
 constexpr int kCtrlBytes = 256;
+constexpr int kScaleBiasBytes = 2 * kConvMaxBlockN * 4;       // per-tile scale / bias staged in smem
+constexpr int kEpilogueThreads = 128;
+constexpr int kEpilogueBarrier = 1;                           // named barrier id of the 4 epilogue warps
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActRelu) return fmaxf(x, 0.f);
@@ -35,7 +38,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
   const int stage_b_bytes = p.BN * kConvBlockK * 2;
   const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
-  ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;            // 16 KiB, 1024-B aligned
+  float* s_scale = reinterpret_cast<float*>(staging + kConvStagingBytes);
+  float* s_bias = s_scale + kConvMaxBlockN;
+  ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(staging + kConvStagingBytes + kScaleBiasBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -58,6 +64,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
+    if (p.tma_store) tma_prefetch_desc(&maps.out);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -154,6 +161,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     // ============================ epilogue (4 warps) ============================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;      // row of the 128-row tile == TMEM lane
+    const int et = threadIdx.x - 64;          // 0..127 among the epilogue threads
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
@@ -164,82 +172,157 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const int tw_i = mt % p.tiles_w;
       const int th_i = (mt / p.tiles_w) % p.tiles_h;
       const int tn_i = mt / (p.tiles_w * p.tiles_h);
-      const int ow = tw_i * p.TW + tw, oh = th_i * p.TH + th, n = tn_i * p.TN + tn;
+      const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+      const int ow = ow0 + tw, oh = oh0 + th, n = n0 + tn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
       const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&ctrl->tmem_full[as], aphase);
-      tc_fence_after();
+      const int co_base = nb * p.BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * kConvMaxBlockN);
-      const int co_base = nb * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (!valid) continue;
+      if (p.tma_store) {
+        // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
+        // every thread passed the previous tile's last barrier after its last read of s_scale / s_bias
+        for (int i = et; i < kConvMaxBlockN; i += kEpilogueThreads) {
+          const bool in = i < p.BN;
+          s_scale[i] = in ? __ldg(p.scale + co_base + i) : 0.f;
+          s_bias[i] = in ? __ldg(p.bias + co_base + i) : 0.f;
+        }
+        named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
+        mbar_wait(&ctrl->tmem_full[as], aphase);
+        tc_fence_after();
+        const int nslices = (p.BN + 63) >> 6;
+        for (int sl = 0; sl < nslices; ++sl) {
+          const int c0 = sl * 64;
+          uint4 rv[8];
+          const bool has_res = (p.residual != nullptr) && valid;
+          if (has_res) {
+            const __half* rp = p.residual + pix * p.res_stride + co_base + c0;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int co = co_base + c0 + g * 8;
-          if (co >= p.Cout) continue;
-          float x[8];
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + co));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
-          x[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, b0.x);
-          x[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, b0.y);
-          x[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, b0.z);
-          x[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, b0.w);
-          x[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, b1.x);
-          x[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, b1.y);
-          x[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, b1.z);
-          x[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, b1.w);
-          const bool full8 = (co + 8 <= p.Cout);
-          if (p.residual != nullptr) {
-            const __half* rp = p.residual + pix * p.res_stride + co;
-            if (full8) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp));
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+            for (int g = 0; g < 8; ++g) {
+              rv[g] = (co_base + c0 + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
+                                                         : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          uint32_t v0[32], v1[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v0);
+          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32), v1);
+          tmem_ld_wait();
+          if (sl == nslices - 1) {
+            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
+          }
+          uint4 ov[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float x[8];
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c0 + g * 8);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + c0 + g * 8 + 4);
+            const float4 bi0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8);
+            const float4 bi1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
+            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float biv[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = g * 8 + j;
+              const uint32_t raw = (c < 32) ? v0[c] : v1[c - 32];
+              x[j] = fmaf(__uint_as_float(raw), scv[j], biv[j]);
+            }
+            if (has_res) {
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv[g]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __half22float2(rh[j]);
                 x[2 * j] += f.x;
                 x[2 * j + 1] += f.y;
               }
-            } else {
-              for (int j = 0; j < 8 && co + j < p.Cout; ++j) x[j] += __half2float(rp[j]);
             }
+            __half2* oh2 = reinterpret_cast<__half2*>(&ov[g]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              oh2[j] = __floats2half2_rn(apply_act(x[2 * j], p.act), apply_act(x[2 * j + 1], p.act));
           }
+          // the previous slice's TMA store must have finished reading the staging buffer
+          if (et == 0) tma_store_wait_read0();
+          named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
+          uint8_t* srow = staging + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
-          if (p.out_f32) {
-            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_stride + co;
-            if (full8) {
-              reinterpret_cast<float4*>(op)[0] = make_float4(x[0], x[1], x[2], x[3]);
-              reinterpret_cast<float4*>(op)[1] = make_float4(x[4], x[5], x[6], x[7]);
-            } else {
-              for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = x[j];
-            }
-          } else {
-            __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_stride + co;
-            if (full8) {
-              uint4 ov;
-              __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) = ov[g];     // 128-B swizzle, conflict-free
+          fence_proxy_async();
+          named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
+          if (et == 0) {
+            tma_store_4d(&maps.out, staging, co_base + c0, ow0, oh0, n0);
+            tma_store_commit();
+          }
+        }
+      } else {
+        // ---- fp32 (or odd-shaped) output: direct global stores, one row per thread
+        mbar_wait(&ctrl->tmem_full[as], aphase);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-              *reinterpret_cast<uint4*>(op) = ov;
-            } else {
-              for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = __float2half_rn(x[j]);
+            for (int g = 0; g < 2; ++g) {
+              const int co = co_base + c0 + g * 8;
+              if (co >= p.Cout) continue;
+              float x[8];
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + co));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
+              x[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, b0.x);
+              x[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, b0.y);
+              x[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, b0.z);
+              x[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, b0.w);
+              x[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, b1.x);
+              x[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, b1.y);
+              x[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, b1.z);
+              x[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, b1.w);
+              const bool full8 = (co + 8 <= p.Cout);
+              if (p.residual != nullptr) {
+                const __half* rp = p.residual + pix * p.res_stride + co;
+                for (int j = 0; j < 8 && co + j < p.Cout; ++j) x[j] += __half2float(rp[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], p.act);
+              if (p.out_f32) {
+                float* op = reinterpret_cast<float*>(p.out) + pix * p.out_stride + co;
+                if (full8) {
+                  reinterpret_cast<float4*>(op)[0] = make_float4(x[0], x[1], x[2], x[3]);
+                  reinterpret_cast<float4*>(op)[1] = make_float4(x[4], x[5], x[6], x[7]);
+                } else {
+                  for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = x[j];
+                }
+              } else {
+                __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_stride + co;
+                if (full8) {
+                  uint4 o4;
+                  __half2* oh2 = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                  *reinterpret_cast<uint4*>(op) = o4;
+                } else {
+                  for (int j = 0; j < 8 && co + j < p.Cout; ++j) op[j] = __float2half_rn(x[j]);
+                }
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
     }
+    if (p.tma_store && et == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
   }
 
   tc_fence_before();
@@ -254,11 +337,12 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 size_t conv_gemm_smem_bytes(int BN, int* stages_out) {
   const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
-  int stages = (kConvSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  const int fixed = kConvStagingBytes + kScaleBiasBytes + kCtrlBytes + 1024;   // 1024: manual alignment slack
+  int stages = (kConvSmemBudget - fixed) / stage_bytes;
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   if (stages < 2) stages = 2;
   if (stages_out) *stages_out = stages;
-  return static_cast<size_t>(stages) * stage_bytes + kCtrlBytes + 1024;
+  return static_cast<size_t>(stages) * stage_bytes + fixed;
 }
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p_in, int sm_count,

@@ -25,7 +25,8 @@ constexpr int kConvBlockK = 64;          // fp16 elements per k-block = 128 B sw
 constexpr int kConvMaxBlockN = 256;
 constexpr int kConvMaxStages = 8;
 constexpr int kConvThreads = 192;        // warp0: TMA producer, warp1: MMA issuer, warps2-5: epilogue
-constexpr int kConvSmemBudget = 220 * 1024;
+constexpr int kConvSmemBudget = 227 * 1024;   // max dynamic shared memory per CTA on sm_100
+constexpr int kConvStagingBytes = 128 * 128;  // one 128-row x 64-channel fp16 slice of the output tile
 
 enum ConvAct : int { kActNone = 0, kActRelu = 1, kActRelu6 = 2 };
 
@@ -48,11 +49,13 @@ struct ConvKernelParams {
   long long out_stride;
   int out_f32;
   int act;
+  int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
 };
 
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
+  CUtensorMap out;    // output tensor {Cout, Wo, Ho, N}, box {64, TW, TH, TN} (only when tma_store)
 };
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,

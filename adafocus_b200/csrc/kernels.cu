@@ -100,43 +100,61 @@ __global__ void action_to_yx_kernel(const float* __restrict__ action, int32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------ stem staging
+// One block stages a strip of up to 64 output pixels of one output row: the (3 x KH x span) input window is read
+// once, coalesced along x, converted to fp16 into shared memory (zero for conv padding outside the P x P patch), and
+// the im2col rows are then assembled from shared memory and written as 16-byte chunks (coalesced along k).
+constexpr int kStemStrip = 64;
+constexpr int kStemMaxWindow = 3 * 7 * ((kStemStrip - 1) * 2 + 7);   // 3 ch x 7 rows x 133 cols
+constexpr int kStemMaxK = 256;
+
 __global__ void __launch_bounds__(kThreads)
 stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, __half* __restrict__ out, int N,
                    int H, int W, int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad) {
-  const int kgroups = Kpad >> 3;
-  const long long total = static_cast<long long>(N) * Ho * Wo * kgroups;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int kg = static_cast<int>(idx % kgroups);
-  long long pix = idx / kgroups;
-  const int ow = static_cast<int>(pix % Wo);
-  const int oh = static_cast<int>((pix / Wo) % Ho);
-  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  __shared__ __half s_win[kStemMaxWindow];
+  __shared__ short s_off[kStemMaxK];
+  const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kStemStrip;
+  const int strip = min(kStemStrip, Wo - ow0);
+  const int span = (strip - 1) * stride + KW;
+  const int kreal = KH * KW * 3;
   int y0 = 0, x0 = 0;
   if (yx != nullptr) {
     y0 = max(0, min(yx[2 * n], H - P));
     x0 = max(0, min(yx[2 * n + 1], W - P));
   }
-  const int kreal = KH * KW * 3;
-  const float* base = frames + static_cast<long long>(n) * 3 * H * W;
-  __align__(16) __half vals[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = kg * 8 + j;
-    float v = 0.f;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int off = -1;
     if (k < kreal) {
-      const int tap = k / 3;
-      const int c = k - tap * 3;
-      const int kh = tap / KW;
-      const int kw = tap - kh * KW;
-      const int iy = oh * stride + kh - pad;
-      const int ix = ow * stride + kw - pad;
-      if (iy >= 0 && iy < P && ix >= 0 && ix < P)
-        v = __ldg(base + (static_cast<long long>(c) * H + (y0 + iy)) * W + (x0 + ix));
+      const int tap = k / 3, c = k - tap * 3;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      off = (c * KH + kh) * span + kw;
     }
-    vals[j] = __float2half_rn(v);
+    s_off[k] = static_cast<short>(off);
   }
-  *reinterpret_cast<uint4*>(out + pix * Kpad + kg * 8) = *reinterpret_cast<const uint4*>(vals);
+  const float* base = frames + static_cast<long long>(n) * 3 * H * W;
+  const int iy0 = oh * stride - pad, ix0 = ow0 * stride - pad;
+  const int win = 3 * KH * span;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) {
+    const int xx = i % span;
+    const int cr = i / span;
+    const int r = cr % KH, c = cr / KH;
+    const int iy = iy0 + r, ix = ix0 + xx;
+    float v = 0.f;
+    if (iy >= 0 && iy < P && ix >= 0 && ix < P) v = __ldg(base + (c * H + (y0 + iy)) * W + (x0 + ix));
+    s_win[i] = __float2half_rn(v);
+  }
+  __syncthreads();
+  const int kgroups = Kpad >> 3;
+  const long long row0 = (static_cast<long long>(n) * Ho + oh) * Wo + ow0;
+  for (int item = threadIdx.x; item < strip * kgroups; item += blockDim.x) {
+    const int owl = item / kgroups, kg = item - owl * kgroups;
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int off = s_off[kg * 8 + j];
+      vals[j] = off >= 0 ? s_win[off + owl * stride] : __half(0.f);
+    }
+    *reinterpret_cast<uint4*>(out + (row0 + owl) * Kpad + kg * 8) = *reinterpret_cast<const uint4*>(vals);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
@@ -146,45 +164,60 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
+// Each thread produces WO horizontally adjacent output pixels x 8 channels: the 3 x ((WO-1)*S+3) input window is
+// loaded once (16-byte loads) and the 9 per-channel weights once, instead of 9 loads per output pixel.
+template <int S, int WO>
 __global__ void __launch_bounds__(kThreads)
 dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, const float* __restrict__ scale,
-                 const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int C, int stride,
-                 int Ho, int Wo, int act) {
-  const int c8n = C >> 3;
-  const long long total = static_cast<long long>(N) * Ho * Wo * c8n;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+                 const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int C, int Ho,
+                 int Wo, int act) {
+  constexpr int COLS = (WO - 1) * S + 3;
+  const unsigned c8n = static_cast<unsigned>(C) >> 3;
+  const unsigned wblocks = (static_cast<unsigned>(Wo) + WO - 1) / WO;
+  const unsigned total = static_cast<unsigned>(N) * Ho * wblocks * c8n;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % c8n);
-  long long pix = idx / c8n;
-  const int ow = static_cast<int>(pix % Wo);
-  const int oh = static_cast<int>((pix / Wo) % Ho);
-  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-  const int c = c8 * 8;
-  float acc[8];
+  const unsigned c8 = idx % c8n;
+  unsigned t = idx / c8n;
+  const int ow0 = static_cast<int>(t % wblocks) * WO;
+  t /= wblocks;
+  const int oh = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  const int c = static_cast<int>(c8) * 8;
+  float acc[WO][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int o = 0; o < WO; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  const int ix0 = ow0 * S - 1;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
-    const int iy = oh * stride + kh - 1;
+    const int iy = oh * S + kh - 1;
     if (iy < 0 || iy >= H) continue;
+    const __half* rowp = in + (static_cast<long long>(n) * H + iy) * W * C + c;
+    float xin[COLS][8];
+#pragma unroll
+    for (int cc = 0; cc < COLS; ++cc) {
+      const int ix = ix0 + cc;
+      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+      if (ix >= 0 && ix < W) xv = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(ix) * C));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(xh[j]);
+        xin[cc][2 * j] = f.x;
+        xin[cc][2 * j + 1] = f.y;
+      }
+    }
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int ix = ow * stride + kw - 1;
-      if (ix < 0 || ix >= W) continue;
-      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c));
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9c + (kh * 3 + kw) * C + c));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9c + (kh * 3 + kw) * C + c + 4));
-      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-      const float2 f0 = __half22float2(xh[0]), f1 = __half22float2(xh[1]), f2 = __half22float2(xh[2]),
-                   f3 = __half22float2(xh[3]);
-      acc[0] = fmaf(f0.x, w0.x, acc[0]);
-      acc[1] = fmaf(f0.y, w0.y, acc[1]);
-      acc[2] = fmaf(f1.x, w0.z, acc[2]);
-      acc[3] = fmaf(f1.y, w0.w, acc[3]);
-      acc[4] = fmaf(f2.x, w1.x, acc[4]);
-      acc[5] = fmaf(f2.y, w1.y, acc[5]);
-      acc[6] = fmaf(f3.x, w1.z, acc[6]);
-      acc[7] = fmaf(f3.y, w1.w, acc[7]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int o = 0; o < WO; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(xin[o * S + kw][j], wv[j], acc[o][j]);
     }
   }
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
@@ -193,13 +226,18 @@ dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, c
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
   const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
   const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  uint4 ov;
-  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+  __half* orow = out + ((static_cast<long long>(n) * Ho + oh) * Wo + ow0) * C + c;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[2 * j], sc[2 * j], bi[2 * j]), act),
-                               act_apply(fmaf(acc[2 * j + 1], sc[2 * j + 1], bi[2 * j + 1]), act));
-  *reinterpret_cast<uint4*>(out + pix * C + c) = ov;
+  for (int o = 0; o < WO; ++o) {
+    if (ow0 + o >= Wo) break;
+    uint4 ov;
+    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[o][2 * j], sc[2 * j], bi[2 * j]), act),
+                                 act_apply(fmaf(acc[o][2 * j + 1], sc[2 * j + 1], bi[2 * j + 1]), act));
+    *reinterpret_cast<uint4*>(orow + static_cast<long long>(o) * C) = ov;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
@@ -475,9 +513,9 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
 cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* out, int N, int H, int W, int P,
                                int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  const long long total = static_cast<long long>(N) * Ho * Wo * (Kpad / 8);
-  stem_im2col_kernel<<<grid_for(total), kThreads, 0, s>>>(frames, yx, out, N, H, W, P, KH, KW, stride, pad, Ho, Wo,
-                                                         Kpad);
+  if (KH > 7 || KW > 7 || stride > 2 || Kpad > kStemMaxK || N > 65535 || Ho > 65535) return cudaErrorInvalidValue;
+  dim3 grid((Wo + kStemStrip - 1) / kStemStrip, Ho, N);
+  stem_im2col_kernel<<<grid, kThreads, 0, s>>>(frames, yx, out, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad);
   return cudaGetLastError();
 }
 
@@ -485,8 +523,13 @@ cudaError_t launch_dwconv3x3(const __half* in, const float* w9c, const float* sc
                              int N, int H, int W, int C, int stride, int act, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
-  dwconv3x3_kernel<<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, stride, Ho, Wo, act);
+  constexpr int WO = 4;
+  const long long total = static_cast<long long>(N) * Ho * ((Wo + WO - 1) / WO) * (C / 8);
+  if (total >= (1LL << 32)) return cudaErrorInvalidValue;
+  if (stride == 1)
+    dwconv3x3_kernel<1, WO><<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
+  else
+    dwconv3x3_kernel<2, WO><<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
   return cudaGetLastError();
 }
 

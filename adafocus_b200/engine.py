@@ -22,9 +22,12 @@ def round_up(a, b):
 
 
 def default_block_n(cout):
-    """Split Cout into the fewest <=256-wide tiles, each a multiple of 16."""
+    """Split Cout into the fewest <=256-wide tiles; a single tile is a multiple of 16, several tiles are multiples
+    of 64 so that the 64-channel TMA-store slices of the epilogue never straddle two tiles."""
     nb = (cout + 255) // 256
-    return min(256, round_up((cout + nb - 1) // nb, 16))
+    if nb == 1:
+        return round_up(cout, 16)
+    return min(256, round_up((cout + nb - 1) // nb, 64))
 
 
 class PackedConv:

@@ -132,6 +132,12 @@ if __name__ == "__main__":
     ref = import_reference_act()
     get_patch_kat(ref)
     # config 3 shape: T=16, P=128, 49 actions, 200 classes; 2 clips
-    run_reference(ref, synth.act_args(), 2, "c3_b2")
+    model = run_reference(ref, synth.act_args(), 2, "c3_b2")
+    import json
+    keys = {"glancer": model.glancer.state_dict(), "focuser": model.focuser.state_dict(),
+            "fc": model.classifier.state_dict(), "policy": model.focuser.policy.policy.state_dict(),
+            "model": model.state_dict()}
+    with open(os.path.join(HERE, "ref_state_keys.json"), "w") as f:
+        json.dump({part: [(k, list(v.shape)) for k, v in sd.items()] for part, sd in keys.items()}, f)
     # a second, differently shaped configuration: T=4, P=96, 36 actions, 51 classes; 3 clips
     run_reference(ref, synth.act_args(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3, "t4_p96_b3")
