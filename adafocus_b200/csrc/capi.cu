@@ -327,6 +327,17 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
                   [=](cudaStream_t s) { return af::launch_conv_gemm(maps, p, sms, s); });
 }
 
+int af_stem_conv3x3s2_c32(af_ctx* ctx, const float* frames, const float* w27, const float* scale, const float* bias,
+                          void* out, int N, int H, int W, int act, void* stream) {
+  if (frames == nullptr || w27 == nullptr || scale == nullptr || bias == nullptr || out == nullptr)
+    return fail(AF_ERR_INVALID, "af_stem_conv3x3s2_c32: null tensor");
+  if (H < 2 || W < 2) return fail(AF_ERR_INVALID, "af_stem_conv3x3s2_c32: bad geometry");
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_stem_conv3x3s2_c32", [=](cudaStream_t s) {
+    return af::launch_stem_conv3x3s2(frames, w27, scale, bias, o, N, H, W, act, s);
+  });
+}
+
 int af_dwconv3x3_nhwc_f16(af_ctx* ctx, const void* in, const float* w9c, const float* scale, const float* bias,
                           void* out, int N, int H, int W, int C, int stride, int act, void* stream) {
   if (in == nullptr || w9c == nullptr || scale == nullptr || bias == nullptr || out == nullptr)

@@ -19,9 +19,9 @@ struct __align__(8) ConvSmemCtrl {
 
 constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
 constexpr int kCtrlBytes = 256;
-constexpr int kScaleBiasBytes = 2 * kConvMaxBlockN * 4;       // per-tile scale / bias staged in smem
-constexpr int kEpilogueThreads = 128;
-constexpr int kEpilogueBarrier = 1;                           // named barrier id of the 4 epilogue warps
+constexpr int kEpilogueThreads = 128;                         // per epilogue group (4 warps = 4 TMEM lane quarters)
+constexpr int kEpilogueGroups = 2;                            // group g drains TMEM accumulator stage g
+constexpr int kEpilogueBarrier = 1;                           // named barrier ids 1, 2 (one per group)
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActRelu) return fmaxf(x, 0.f);
@@ -32,16 +32,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-B alignment is required by the 128-B swizzle; dynamic smem base is at least 16-B aligned, so align by hand.
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  // 1024-B alignment is required by the 128-B swizzle; the dynamic smem window starts 1024-B aligned (no static
+  // __shared__ in this kernel) -- trap rather than silently corrupt if that ever stops holding.
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
   const int stage_b_bytes = p.BN * kConvBlockK * 2;
   const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
-  uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;            // 16 KiB, 1024-B aligned
-  float* s_scale = reinterpret_cast<float*>(staging + kConvStagingBytes);
-  float* s_bias = s_scale + kConvMaxBlockN;
-  ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(staging + kConvStagingBytes + kScaleBiasBytes);
+  uint8_t* staging_base = smem + static_cast<size_t>(p.stages) * stage_bytes;      // 2 x 16 KiB, 1024-B aligned
+  ConvSmemCtrl* ctrl =
+      reinterpret_cast<ConvSmemCtrl*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,7 +57,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&ctrl->tmem_full[a], 1);
-      mbar_init(&ctrl->tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&ctrl->tmem_empty[a], 4);   // one arrive per warp of the epilogue group that owns stage a
     }
     fence_mbar_init();
   }
@@ -158,15 +158,21 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       }
     }
   } else {
-    // ============================ epilogue (4 warps) ============================
+    // ============================ epilogue (2 groups x 4 warps) ============================
+    // Group g only ever handles the tiles whose accumulator lives in TMEM stage g (local tile index it = g, g+2, ..),
+    // so the two groups drain consecutive tiles concurrently, each with its own staging buffer and named barrier.
+    const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;      // row of the 128-row tile == TMEM lane
-    const int et = threadIdx.x - 64;          // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64 - group * kEpilogueThreads;   // 0..127 inside the group
+    const uint32_t bar_id = kEpilogueBarrier + group;
+    uint8_t* group_staging = staging_base + group * p.epi_bufs * kConvStagingBytes;
+    int slice_ctr = 0;                        // slices stored by this group so far (selects the staging buffer)
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int it = group; blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += kEpilogueGroups) {
+      const int tile = blockIdx.x + it * gridDim.x;
       const int nb = tile % p.n_blocks;
       const int mt = tile / p.n_blocks;
       const int tw_i = mt % p.tiles_w;
@@ -176,39 +182,36 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const int ow = ow0 + tw, oh = oh0 + th, n = n0 + tn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
       const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
-      const int as = it & 1;
+      const int as = it & 1;                  // == group
       const uint32_t aphase = (it >> 1) & 1;
       const int co_base = nb * p.BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * kConvMaxBlockN);
       if (p.tma_store) {
         // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
-        // every thread passed the previous tile's last barrier after its last read of s_scale / s_bias
-        for (int i = et; i < kConvMaxBlockN; i += kEpilogueThreads) {
-          const bool in = i < p.BN;
-          s_scale[i] = in ? __ldg(p.scale + co_base + i) : 0.f;
-          s_bias[i] = in ? __ldg(p.bias + co_base + i) : 0.f;
+        const bool has_res = (p.residual != nullptr) && valid;
+        const int nslices = (p.BN + 63) >> 6;
+        uint4 rv[8];
+        if (has_res) {   // residual of the first slice: in flight while the accumulator finishes
+          const __half* rp = p.residual + pix * p.res_stride + co_base;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            rv[g] = (co_base + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
+                                                   : make_uint4(0u, 0u, 0u, 0u);
         }
-        named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
         mbar_wait(&ctrl->tmem_full[as], aphase);
         tc_fence_after();
-        const int nslices = (p.BN + 63) >> 6;
         for (int sl = 0; sl < nslices; ++sl) {
           const int c0 = sl * 64;
-          uint4 rv[8];
-          const bool has_res = (p.residual != nullptr) && valid;
-          if (has_res) {
-            const __half* rp = p.residual + pix * p.res_stride + co_base + c0;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              rv[g] = (co_base + c0 + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
-                                                         : make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
           uint32_t v0[32], v1[32];
           __syncwarp();
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v0);
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32), v1);
+          // folded-BN scale / bias come straight from L1 (same address in every lane -> broadcast); columns past
+          // BN only exist in the last slice of a narrow layer and are clipped by the TMA store
+          const float4* scp = reinterpret_cast<const float4*>(p.scale + co_base + c0);
+          const float4* bip = reinterpret_cast<const float4*>(p.bias + co_base + c0);
+          const int nvec = min(16, (p.BN - c0) >> 2);
           tmem_ld_wait();
           if (sl == nslices - 1) {
             // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -219,13 +222,14 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           uint4 ov[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 sa = (2 * g < nvec) ? __ldg(scp + 2 * g) : z4;
+            const float4 sb = (2 * g + 1 < nvec) ? __ldg(scp + 2 * g + 1) : z4;
+            const float4 ba = (2 * g < nvec) ? __ldg(bip + 2 * g) : z4;
+            const float4 bb = (2 * g + 1 < nvec) ? __ldg(bip + 2 * g + 1) : z4;
+            const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const float biv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
             float x[8];
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c0 + g * 8);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + c0 + g * 8 + 4);
-            const float4 bi0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8);
-            const float4 bi1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
-            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-            const float biv[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int c = g * 8 + j;
@@ -246,15 +250,28 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             for (int j = 0; j < 4; ++j)
               oh2[j] = __floats2half2_rn(apply_act(x[2 * j], p.act), apply_act(x[2 * j + 1], p.act));
           }
-          // the previous slice's TMA store must have finished reading the staging buffer
-          if (et == 0) tma_store_wait_read0();
-          named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
+          if (has_res && sl + 1 < nslices) {   // prefetch the next slice's residual before the store handshake
+            const __half* rp = p.residual + pix * p.res_stride + co_base + c0 + 64;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              rv[g] = (co_base + c0 + 64 + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
+                                                              : make_uint4(0u, 0u, 0u, 0u);
+          }
+          // the TMA store that last used this staging buffer must have finished reading it; with two buffers the
+          // previous slice's store stays in flight while this slice is written
+          uint8_t* staging = group_staging + (p.epi_bufs == 2 ? (slice_ctr & 1) : 0) * kConvStagingBytes;
+          ++slice_ctr;
+          if (et == 0) {
+            if (p.epi_bufs == 2) tma_store_wait_read1();
+            else tma_store_wait_read0();
+          }
+          named_barrier_sync(bar_id, kEpilogueThreads);
           uint8_t* srow = staging + row * 128;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) = ov[g];     // 128-B swizzle, conflict-free
           fence_proxy_async();
-          named_barrier_sync(kEpilogueBarrier, kEpilogueThreads);
+          named_barrier_sync(bar_id, kEpilogueThreads);
           if (et == 0) {
             tma_store_4d(&maps.out, staging, co_base + c0, ow0, oh0, n0);
             tma_store_commit();
@@ -335,13 +352,22 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int BN, int* stages_out) {
+size_t conv_gemm_smem_bytes(int BN, int num_kb, int* stages_out, int* epi_bufs_out) {
   const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
-  const int fixed = kConvStagingBytes + kScaleBiasBytes + kCtrlBytes + 1024;   // 1024: manual alignment slack
+  // Short-K layers are store-bound: give each epilogue group two staging buffers so a TMA store drains while the
+  // next slice is produced.  Long-K layers are MMA-bound: keep the smem for a deeper operand pipeline instead.
+  int epi_bufs = 2;
+  int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kCtrlBytes;
   int stages = (kConvSmemBudget - fixed) / stage_bytes;
+  if (num_kb >= 16 && stages < 4) {
+    epi_bufs = 1;
+    fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kCtrlBytes;
+    stages = (kConvSmemBudget - fixed) / stage_bytes;
+  }
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   if (stages < 2) stages = 2;
   if (stages_out) *stages_out = stages;
+  if (epi_bufs_out) *epi_bufs_out = epi_bufs;
   return static_cast<size_t>(stages) * stage_bytes + fixed;
 }
 
@@ -349,9 +375,10 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
                              cudaStream_t stream) {
   static_assert(sizeof(ConvSmemCtrl) <= kCtrlBytes, "ctrl block too large");
   ConvKernelParams p = p_in;
-  int stages = 0;
-  const size_t smem = conv_gemm_smem_bytes(p.BN, &stages);
+  int stages = 0, epi_bufs = 1;
+  const size_t smem = conv_gemm_smem_bytes(p.BN, p.KH * p.KW * p.cblks, &stages, &epi_bufs);
   p.stages = stages;
+  p.epi_bufs = epi_bufs;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -24,7 +24,7 @@ constexpr int kConvBlockM = 128;
 constexpr int kConvBlockK = 64;          // fp16 elements per k-block = 128 B swizzle span
 constexpr int kConvMaxBlockN = 256;
 constexpr int kConvMaxStages = 8;
-constexpr int kConvThreads = 192;        // warp0: TMA producer, warp1: MMA issuer, warps2-5: epilogue
+constexpr int kConvThreads = 320;        // warp0: TMA producer, warp1: MMA issuer, warps2-5 / 6-9: epilogue groups
 constexpr int kConvSmemBudget = 227 * 1024;   // max dynamic shared memory per CTA on sm_100
 constexpr int kConvStagingBytes = 128 * 128;  // one 128-row x 64-channel fp16 slice of the output tile
 
@@ -50,6 +50,7 @@ struct ConvKernelParams {
   int out_f32;
   int act;
   int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
+  int epi_bufs;                    // staging buffers per epilogue group (1 or 2)
 };
 
 struct ConvTensorMaps {
@@ -60,6 +61,6 @@ struct ConvTensorMaps {
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,
                              cudaStream_t stream);
-size_t conv_gemm_smem_bytes(int BN, int* stages_out);
+size_t conv_gemm_smem_bytes(int BN, int num_kb, int* stages_out, int* epi_bufs_out);
 
 }  // namespace af

@@ -22,6 +22,12 @@ __device__ __forceinline__ int coord_from_action(float a, int H, int P) {
   return c;
 }
 
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return fminf(fmaxf(x, 0.f), 6.f);
+  return x;
+}
+
 // ------------------------------------------------------------------------------------------------ crop
 __device__ __forceinline__ float4 load4_maybe_unaligned(const float* p) {
   if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) return __ldg(reinterpret_cast<const float4*>(p));
@@ -157,13 +163,73 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ depthwise 3x3
-__device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == 1) return fmaxf(x, 0.f);
-  if (act == 2) return fminf(fmaxf(x, 0.f), 6.f);
-  return x;
+// ------------------------------------------------------------------------------------------------ direct 3x3/2 stem
+// MobileNet-V2 features[0] (ACT/models/mobilenet.py:105): 3 -> 32 channels, 3x3, stride 2, pad 1, BN, ReLU6, straight
+// from the fp32 NCHW frame to NHWC fp16.  K = 27 is too thin for a 64-wide MMA k-block, so this layer runs on the
+// FMA pipes: one output pixel x 32 channels per thread, weights broadcast from shared memory.
+constexpr int kStemC = 32;
+
+__global__ void __launch_bounds__(kThreads)
+stem_conv3x3s2_kernel(const float* __restrict__ frames, const float* __restrict__ w27, const float* __restrict__ scale,
+                      const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int Ho, int Wo,
+                      int act) {
+  __shared__ __align__(16) float s_w[27 * kStemC];
+  __shared__ float s_scale[kStemC], s_bias[kStemC];
+  for (int i = threadIdx.x; i < 27 * kStemC; i += blockDim.x) s_w[i] = w27[i];
+  if (threadIdx.x < kStemC) {
+    s_scale[threadIdx.x] = scale[threadIdx.x];
+    s_bias[threadIdx.x] = bias[threadIdx.x];
+  }
+  __syncthreads();
+  const unsigned total = static_cast<unsigned>(N) * Ho * Wo;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ow = static_cast<int>(idx % Wo);
+  const int oh = static_cast<int>((idx / Wo) % Ho);
+  const int n = static_cast<int>(idx / (static_cast<unsigned>(Wo) * Ho));
+  float acc[kStemC];
+#pragma unroll
+  for (int j = 0; j < kStemC; ++j) acc[j] = 0.f;
+  const float* base = frames + static_cast<long long>(n) * 3 * H * W;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oh * 2 + r - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ix = ow * 2 + q - 1;
+      if (ix < 0 || ix >= W) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float x = __ldg(base + (static_cast<long long>(c) * H + iy) * W + ix);
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((r * 3 + q) * 3 + c) * kStemC);
+#pragma unroll
+        for (int j4 = 0; j4 < kStemC / 4; ++j4) {
+          const float4 w = wp[j4];
+          acc[4 * j4 + 0] = fmaf(x, w.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(x, w.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(x, w.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(x, w.w, acc[4 * j4 + 3]);
+        }
+      }
+    }
+  }
+  __half* op = out + static_cast<long long>(idx) * kStemC;
+#pragma unroll
+  for (int g = 0; g < kStemC / 8; ++g) {
+    uint4 ov;
+    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = g * 8 + 2 * j;
+      oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[c], s_scale[c], s_bias[c]), act),
+                                 act_apply(fmaf(acc[c + 1], s_scale[c + 1], s_bias[c + 1]), act));
+    }
+    reinterpret_cast<uint4*>(op)[g] = ov;
+  }
 }
 
+// ------------------------------------------------------------------------------------------------ depthwise 3x3
 // Each thread produces WO horizontally adjacent output pixels x 8 channels: the 3 x ((WO-1)*S+3) input window is
 // loaded once (16-byte loads) and the 9 per-channel weights once, instead of 9 loads per output pixel.
 template <int S, int WO>
@@ -516,6 +582,16 @@ cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* o
   if (KH > 7 || KW > 7 || stride > 2 || Kpad > kStemMaxK || N > 65535 || Ho > 65535) return cudaErrorInvalidValue;
   dim3 grid((Wo + kStemStrip - 1) / kStemStrip, Ho, N);
   stem_im2col_kernel<<<grid, kThreads, 0, s>>>(frames, yx, out, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const float* scale, const float* bias,
+                                  __half* out, int N, int H, int W, int act, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo;
+  if (total >= (1LL << 32)) return cudaErrorInvalidValue;
+  stem_conv3x3s2_kernel<<<grid_for(total), kThreads, 0, s>>>(frames, w27, scale, bias, out, N, H, W, Ho, Wo, act);
   return cudaGetLastError();
 }
 

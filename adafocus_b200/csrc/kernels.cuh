@@ -19,6 +19,11 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
 cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* out, int N, int H, int W, int P,
                                int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s);
 
+// Direct 3 -> 32 channel 3x3 / stride 2 / pad 1 conv + folded BN + activation, fp32 NCHW frames -> NHWC fp16
+// (MobileNet-V2 features[0], ACT/models/mobilenet.py:105). w27: fp32 [27][32], k = (r*3+s)*3 + c.
+cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const float* scale, const float* bias,
+                                  __half* out, int N, int H, int W, int act, cudaStream_t s);
+
 // Depthwise 3x3 (pad 1) + folded BN + ReLU6, NHWC fp16 (ACT/models/mobilenet.py:58, groups=hidden_dim).
 cudaError_t launch_dwconv3x3(const __half* in, const float* w9c, const float* scale, const float* bias, __half* out,
                              int N, int H, int W, int C, int stride, int act, cudaStream_t s);

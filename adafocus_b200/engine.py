@@ -247,6 +247,18 @@ class Engine:
         self.release(col)
         return out
 
+    def stem_conv3x3s2_c32(self, frames, w27, scale, bias, act=AF_ACT_RELU6):
+        """frames (N,3,H,W) fp32 NCHW -> (N,H/2,W/2,32) NHWC fp16 (MobileNet-V2 features[0])."""
+        n, c, h, w = frames.shape
+        assert c == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        out = self.empty((n, ho, wo, 32), torch.float16)
+        check(self.lib.af_stem_conv3x3s2_c32(self.h, _ptr(frames), _ptr(w27), _ptr(scale), _ptr(bias), _ptr(out), n, h,
+                                             w, act, self._stream()), "af_stem_conv3x3s2_c32")
+        self._count()
+        self.keep(frames, w27, scale, bias, out)
+        return out
+
     def dwconv3x3(self, x, w9c, scale, bias, stride, act=AF_ACT_RELU6):
         n, h, w, c = x.shape
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1

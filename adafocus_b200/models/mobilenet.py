@@ -105,7 +105,13 @@ class MobileNetV2Runner:
         f = net.features
         c0, b0 = f[0][0], f[0][1]
         s, b = fold_bn(b0.weight, b0.bias, b0.running_mean, b0.running_var, b0.eps)
-        self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
+        self.stem_direct = tuple(c0.weight.shape) == (32, 3, 3, 3) and c0.stride == (2, 2)
+        if self.stem_direct:
+            # fp32 [27][32], k = (r*3+s)*3 + c
+            self.stem_w = c0.weight.detach().float().permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
+            self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
+        else:
+            self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
         self.blocks = []
         for blk in list(f)[1:-1]:
             seq = list(blk.conv)
@@ -124,7 +130,27 @@ class MobileNetV2Runner:
             pw, bn = seq[1], seq[2]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev)
+            entry["_proj"] = (pw.weight.detach().float().flatten(1).to(dev), s.to(dev), b.to(dev))
+            entry["_exp"] = None
+            if blk.expand != 1:
+                cv, bne = list(blk.conv)[0][0], list(blk.conv)[0][1]
+                se, be = fold_bn(bne.weight, bne.bias, bne.running_mean, bne.running_var, bne.eps)
+                entry["_exp"] = (cv.weight.detach().float().flatten(1).to(dev), se.to(dev), be.to(dev))
             self.blocks.append(entry)
+        # A linear project conv (+BN) whose only consumer is the next block's expand conv (+BN+ReLU6) -- i.e. neither
+        # block has a residual connection -- composes into ONE 1x1 conv: W = W_e diag(s_p) W_p, bias = s_e (W_e b_p) + b_e.
+        # Exact algebra (no activation in between, ACT/models/mobilenet.py:55-62); the narrow tensor is never stored.
+        for k in range(len(self.blocks) - 1):
+            a, nxt = self.blocks[k], self.blocks[k + 1]
+            if not a["res"] and not nxt["res"] and nxt["_exp"] is not None:
+                wp, sp, bp = a["_proj"]
+                we, se, be = nxt["_exp"]
+                wm = we @ (sp[:, None] * wp)
+                bm = se * (we @ bp) + be
+                a["project"] = None
+                nxt["expand"] = pack_conv(wm, se, bm, act=AF_ACT_RELU6, device=dev)
+        for e in self.blocks:
+            e.pop("_proj"), e.pop("_exp")
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
@@ -132,7 +158,10 @@ class MobileNetV2Runner:
     def run(self, eng, frames, tsm=None):
         """frames (N,3,H,W) fp32 contiguous -> (N,h,w,1280) NHWC fp16. tsm=(T, shift_div) applies the temporal shift
         to the input of every residual block's first 1x1 conv (STH/models/gfv_net.py:238-241)."""
-        x = eng.stem(frames, self.stem)
+        if self.stem_direct:
+            x = eng.stem_conv3x3s2_c32(frames, self.stem_w, self.stem_s, self.stem_b)
+        else:
+            x = eng.stem(frames, self.stem)
         for e in self.blocks:
             inp = x
             y = x
@@ -147,8 +176,11 @@ class MobileNetV2Runner:
             d = eng.dwconv3x3(h, e["dw_w"], e["dw_s"], e["dw_b"], e["stride"])
             if h is not inp:
                 eng.release(h)
-            x = eng.conv(d, e["project"], residual=inp if e["res"] else None)
-            eng.release(d)
+            if e["project"] is None:         # merged into the next block's expand conv
+                x = d
+            else:
+                x = eng.conv(d, e["project"], residual=inp if e["res"] else None)
+                eng.release(d)
             eng.release(inp)
         out = eng.conv(x, self.last)
         eng.release(x)

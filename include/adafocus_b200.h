@@ -100,6 +100,12 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
 int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* out, int N, int H, int W, int P,
                    int KH, int KW, int stride, int pad, int Kpad, void* stream);
 
+/* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
+ * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
+ * w27 fp32 [27][32] with k = (r*3+s)*3 + c; scale / bias fp32 [32]. */
+int af_stem_conv3x3s2_c32(af_ctx* ctx, const float* frames, const float* w27, const float* scale, const float* bias,
+                          void* out, int N, int H, int W, int act, void* stream);
+
 /* Conv2d + BatchNorm2d(eval, folded) + ReLU/ReLU6 (+ residual add) -- ACT/models/resnet.py:94-114,
  * ACT/models/mobilenet.py:32-68, ACT/models/ppo.py:33-39; also every Linear/GRU projection as a 1x1 "conv". */
 int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* desc, void* stream);

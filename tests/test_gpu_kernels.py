@@ -161,6 +161,20 @@ def test_stem_im2col_conv_vs_torch(eng):
     assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3), float((out.float() - ref).abs().max())
 
 
+def test_direct_stem_conv3x3s2_vs_torch(eng):
+    torch.manual_seed(9)
+    for hw in (224, 97):
+        frames = torch.randn(5, 3, hw, hw, device=DEV)
+        wt = torch.randn(32, 3, 3, 3, device=DEV) / math.sqrt(27)
+        scale, bias = torch.rand(32, device=DEV) + 0.5, torch.randn(32, device=DEV) * 0.1
+        w27 = wt.permute(2, 3, 1, 0).reshape(27, 32).contiguous()
+        out = eng.stem_conv3x3s2_c32(frames, w27, scale, bias)
+        ref = F.conv2d(frames, wt, None, 2, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+        ref = ref.clamp(0, 6).permute(0, 2, 3, 1)
+        assert out.shape == ref.shape
+        assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3), float((out.float() - ref).abs().max())
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 @pytest.mark.parametrize("stride,c,hw", [(1, 32, 14), (2, 96, 15), (2, 144, 56), (1, 960, 7)])
 def test_dwconv3x3(eng, stride, c, hw):
