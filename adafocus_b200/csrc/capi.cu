@@ -240,7 +240,7 @@ int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* ou
 
 int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   if (ctx == nullptr || d == nullptr) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: null argument");
-  if (d->in == nullptr || d->w == nullptr || d->out == nullptr || d->scale == nullptr || d->bias == nullptr)
+  if (d->in == nullptr || d->w == nullptr || d->out == nullptr || d->bias == nullptr)
     return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: null tensor");
   if (d->block_n < 16 || d->block_n > af::kConvMaxBlockN || d->block_n % 16 != 0)
     return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: block_n must be a multiple of 16 in [16,256]");

@@ -19,9 +19,16 @@ struct __align__(8) ConvSmemCtrl {
 
 constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
 constexpr int kCtrlBytes = 256;
+constexpr int kAffineBytes = 2 * 2 * kConvMaxBlockN * 4;       // per group: scale[256] + bias[256] fp32
 constexpr int kEpilogueThreads = 128;                         // per epilogue group (4 warps = 4 TMEM lane quarters)
 constexpr int kEpilogueGroups = 2;                            // group g drains TMEM accumulator stage g
 constexpr int kEpilogueBarrier = 1;                           // named barrier ids 1, 2 (one per group)
+
+// single-thread roles (producer / MMA issuer) back off between probes so they do not steal issue slots from the
+// epilogue warps that share their scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActRelu) return fmaxf(x, 0.f);
@@ -40,8 +47,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   const int stage_b_bytes = p.BN * kConvBlockK * 2;
   const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
   uint8_t* staging_base = smem + static_cast<size_t>(p.stages) * stage_bytes;      // 2 x 16 KiB, 1024-B aligned
-  ConvSmemCtrl* ctrl =
-      reinterpret_cast<ConvSmemCtrl*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
+  float* s_affine = reinterpret_cast<float*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
+  ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(reinterpret_cast<uint8_t*>(s_affine) + kAffineBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,7 +114,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               map_idx = ph * 2 + pw;
             }
             for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
-              mbar_wait(&ctrl->empty[stage], phase ^ 1);
+              mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
               uint8_t* sb = sa + kStageABytes;
               mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
@@ -132,11 +139,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&ctrl->tmem_empty[as], aphase ^ 1);
+        mbar_wait_backoff(&ctrl->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kConvMaxBlockN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&ctrl->full[stage], phase);
+          mbar_wait_backoff(&ctrl->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = sa + kStageABytes;
@@ -166,8 +173,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     const int row = quarter * 32 + lane;      // row of the 128-row tile == TMEM lane
     const int et = threadIdx.x - 64 - group * kEpilogueThreads;   // 0..127 inside the group
     const uint32_t bar_id = kEpilogueBarrier + group;
-    uint8_t* group_staging = staging_base + group * p.epi_bufs * kConvStagingBytes;
+    uint8_t* group_staging = staging_base + group * 2 * kConvStagingBytes;
+    float* g_scale = s_affine + group * 2 * kConvMaxBlockN;
+    float* g_bias = g_scale + kConvMaxBlockN;
     int slice_ctr = 0;                        // slices stored by this group so far (selects the staging buffer)
+    int loaded_nb = -1;                       // n-block whose scale / bias currently sit in smem
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
@@ -199,6 +209,17 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             rv[g] = (co_base + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
                                                    : make_uint4(0u, 0u, 0u, 0u);
         }
+        if (nb != loaded_nb) {
+          // per-channel scale / bias of this n-block -> smem (zero past BN so stray columns stay finite).  Every
+          // thread of the group is past the previous tile's last barrier, i.e. past its last read of these arrays.
+          for (int i = et; i < kConvMaxBlockN; i += kEpilogueThreads) {
+            const bool in = i < p.BN;
+            g_scale[i] = (in && p.scale != nullptr) ? __ldg(p.scale + co_base + i) : (in ? 1.f : 0.f);
+            g_bias[i] = in ? __ldg(p.bias + co_base + i) : 0.f;
+          }
+          loaded_nb = nb;
+          named_barrier_sync(bar_id, kEpilogueThreads);
+        }
         mbar_wait(&ctrl->tmem_full[as], aphase);
         tc_fence_after();
         for (int sl = 0; sl < nslices; ++sl) {
@@ -207,11 +228,6 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           __syncwarp();
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v0);
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32), v1);
-          // folded-BN scale / bias come straight from L1 (same address in every lane -> broadcast); columns past
-          // BN only exist in the last slice of a narrow layer and are clipped by the TMA store
-          const float4* scp = reinterpret_cast<const float4*>(p.scale + co_base + c0);
-          const float4* bip = reinterpret_cast<const float4*>(p.bias + co_base + c0);
-          const int nvec = min(16, (p.BN - c0) >> 2);
           tmem_ld_wait();
           if (sl == nslices - 1) {
             // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -219,14 +235,14 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
           }
-          uint4 ov[8];
+          uint8_t* staging = group_staging + (slice_ctr & 1) * kConvStagingBytes;
+          ++slice_ctr;
+          uint8_t* srow = staging + row * 128;
+          const float4* scp = reinterpret_cast<const float4*>(g_scale + c0);
+          const float4* bip = reinterpret_cast<const float4*>(g_bias + c0);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 sa = (2 * g < nvec) ? __ldg(scp + 2 * g) : z4;
-            const float4 sb = (2 * g + 1 < nvec) ? __ldg(scp + 2 * g + 1) : z4;
-            const float4 ba = (2 * g < nvec) ? __ldg(bip + 2 * g) : z4;
-            const float4 bb = (2 * g + 1 < nvec) ? __ldg(bip + 2 * g + 1) : z4;
+            const float4 sa = scp[2 * g], sb = scp[2 * g + 1], ba = bip[2 * g], bb = bip[2 * g + 1];
             const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const float biv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
             float x[8];
@@ -245,32 +261,24 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                 x[2 * j + 1] += f.y;
               }
             }
-            __half2* oh2 = reinterpret_cast<__half2*>(&ov[g]);
+            uint4 ov;
+            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               oh2[j] = __floats2half2_rn(apply_act(x[2 * j], p.act), apply_act(x[2 * j + 1], p.act));
+            // this buffer was last read by the store issued two slices ago, which thread 0 waited for before the
+            // previous slice's barrier
+            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) = ov;        // 128-B swizzle, conflict-free
           }
-          if (has_res && sl + 1 < nslices) {   // prefetch the next slice's residual before the store handshake
+          if (has_res && sl + 1 < nslices) {   // prefetch the next slice's residual
             const __half* rp = p.residual + pix * p.res_stride + co_base + c0 + 64;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               rv[g] = (co_base + c0 + 64 + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
                                                               : make_uint4(0u, 0u, 0u, 0u);
           }
-          // the TMA store that last used this staging buffer must have finished reading it; with two buffers the
-          // previous slice's store stays in flight while this slice is written
-          uint8_t* staging = group_staging + (p.epi_bufs == 2 ? (slice_ctr & 1) : 0) * kConvStagingBytes;
-          ++slice_ctr;
-          if (et == 0) {
-            if (p.epi_bufs == 2) tma_store_wait_read1();
-            else tma_store_wait_read0();
-          }
-          named_barrier_sync(bar_id, kEpilogueThreads);
-          uint8_t* srow = staging + row * 128;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) = ov[g];     // 128-B swizzle, conflict-free
           fence_proxy_async();
+          if (et == 0) tma_store_wait_read0();   // the previous slice's store has left the other buffer
           named_barrier_sync(bar_id, kEpilogueThreads);
           if (et == 0) {
             tma_store_4d(&maps.out, staging, co_base + c0, ow0, oh0, n0);
@@ -292,8 +300,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               const int co = co_base + c0 + g * 8;
               if (co >= p.Cout) continue;
               float x[8];
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + co));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
+              const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 s0 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + co)) : one4;
+              const float4 s1 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + co + 4)) : one4;
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co + 4));
               x[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, b0.x);
@@ -353,17 +362,12 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 }  // namespace
 
 size_t conv_gemm_smem_bytes(int BN, int num_kb, int* stages_out, int* epi_bufs_out) {
+  (void)num_kb;
   const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
-  // Short-K layers are store-bound: give each epilogue group two staging buffers so a TMA store drains while the
-  // next slice is produced.  Long-K layers are MMA-bound: keep the smem for a deeper operand pipeline instead.
-  int epi_bufs = 2;
-  int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kCtrlBytes;
+  // two epilogue groups x two 16 KiB staging buffers (a TMA store drains while the next slice is produced)
+  const int epi_bufs = 2;
+  const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes;
   int stages = (kConvSmemBudget - fixed) / stage_bytes;
-  if (num_kb >= 16 && stages < 4) {
-    epi_bufs = 1;
-    fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kCtrlBytes;
-    stages = (kConvSmemBudget - fixed) / stage_bytes;
-  }
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   if (stages < 2) stages = 2;
   if (stages_out) *stages_out = stages;

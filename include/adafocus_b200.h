@@ -45,7 +45,8 @@ typedef struct af_plan af_plan; /* a recorded sequence of launches, replayable w
  *   w  : packed fp16 [cout_pad][kh*kw*cblk*64] with cblk = ceil(cin/64); k = ((r*kw+s)*cblk*64 + ci), zero padded;
  *        cout_pad = ceil(cout/block_n)*block_n
  *   out: NHWC fp16 or fp32 (n, ho, wo, cout), pixel stride out_stride
- *   y  = act(scale[co]*conv + bias[co] (+ residual)), scale/bias have cout_pad entries.
+ *   y  = act(scale[co]*conv + bias[co] (+ residual)), scale/bias have cout_pad entries; scale may be NULL (= 1,
+ *        e.g. when the BatchNorm scale has been folded into the packed weights).
  * A plain GEMM C[M,N] = A[M,K] W[N,K]^T is the case n=1, h=1, w=M, cin=K, kh=kw=1, stride=1, pad=0. */
 typedef struct af_conv_desc {
   const void* in;
