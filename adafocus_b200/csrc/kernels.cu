@@ -138,28 +138,35 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
   }
   const float* base = frames + static_cast<long long>(n) * 3 * H * W;
   const int iy0 = oh * stride - pad, ix0 = ow0 * stride - pad;
-  const int win = 3 * KH * span;
-  for (int i = threadIdx.x; i < win; i += blockDim.x) {
-    const int xx = i % span;
-    const int cr = i / span;
-    const int r = cr % KH, c = cr / KH;
-    const int iy = iy0 + r, ix = ix0 + xx;
-    float v = 0.f;
-    if (iy >= 0 && iy < P && ix >= 0 && ix < P) v = __ldg(base + (c * H + (y0 + iy)) * W + (x0 + ix));
-    s_win[i] = __float2half_rn(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // window rows (c, r): one warp per row, lanes sweep x -> coalesced reads, no per-element div / mod
+  for (int cr = warp; cr < 3 * KH; cr += nwarps) {
+    const int c = cr / KH, r = cr - c * KH;
+    const int iy = iy0 + r;
+    const bool row_ok = (iy >= 0) && (iy < P);
+    const float* rowp = base + (static_cast<long long>(c) * H + (y0 + iy)) * W + x0;
+    __half* dst = s_win + cr * span;
+    for (int xx = lane; xx < span; xx += 32) {
+      const int ix = ix0 + xx;
+      float v = 0.f;
+      if (row_ok && ix >= 0 && ix < P) v = __ldg(rowp + ix);
+      dst[xx] = __float2half_rn(v);
+    }
   }
   __syncthreads();
   const int kgroups = Kpad >> 3;
   const long long row0 = (static_cast<long long>(n) * Ho + oh) * Wo + ow0;
-  for (int item = threadIdx.x; item < strip * kgroups; item += blockDim.x) {
-    const int owl = item / kgroups, kg = item - owl * kgroups;
-    __align__(16) __half vals[8];
+  // one warp per output pixel, lane = 8-wide k group: a warp writes one contiguous im2col row
+  for (int kg = lane; kg < kgroups; kg += 32) {
+    short offs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int off = s_off[kg * 8 + j];
-      vals[j] = off >= 0 ? s_win[off + owl * stride] : __half(0.f);
+    for (int j = 0; j < 8; ++j) offs[j] = s_off[kg * 8 + j];
+    for (int owl = warp; owl < strip; owl += nwarps) {
+      __align__(16) __half vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[j] = offs[j] >= 0 ? s_win[offs[j] + owl * stride] : __half(0.f);
+      *reinterpret_cast<uint4*>(out + (row0 + owl) * Kpad + kg * 8) = *reinterpret_cast<const uint4*>(vals);
     }
-    *reinterpret_cast<uint4*>(out + (row0 + owl) * Kpad + kg * 8) = *reinterpret_cast<const uint4*>(vals);
   }
 }
 
@@ -169,10 +176,11 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
 // FMA pipes: one output pixel x 32 channels per thread, weights broadcast from shared memory.
 constexpr int kStemC = 32;
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 stem_conv3x3s2_kernel(const float* __restrict__ frames, const float* __restrict__ w27, const float* __restrict__ scale,
                       const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int Ho, int Wo,
                       int act) {
+  // two horizontally adjacent output pixels per thread: every weight vector fetched from shared memory feeds 8 FMAs
   __shared__ __align__(16) float s_w[27 * kStemC];
   __shared__ float s_scale[kStemC], s_bias[kStemC];
   for (int i = threadIdx.x; i < 27 * kStemC; i += blockDim.x) s_w[i] = w27[i];
@@ -181,51 +189,66 @@ stem_conv3x3s2_kernel(const float* __restrict__ frames, const float* __restrict_
     s_bias[threadIdx.x] = bias[threadIdx.x];
   }
   __syncthreads();
-  const unsigned total = static_cast<unsigned>(N) * Ho * Wo;
+  const unsigned wpairs = (static_cast<unsigned>(Wo) + 1) >> 1;
+  const unsigned total = static_cast<unsigned>(N) * Ho * wpairs;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ow = static_cast<int>(idx % Wo);
-  const int oh = static_cast<int>((idx / Wo) % Ho);
-  const int n = static_cast<int>(idx / (static_cast<unsigned>(Wo) * Ho));
-  float acc[kStemC];
+  const int ow = static_cast<int>(idx % wpairs) * 2;
+  const int oh = static_cast<int>((idx / wpairs) % Ho);
+  const int n = static_cast<int>(idx / (wpairs * Ho));
+  float acc0[kStemC], acc1[kStemC];
 #pragma unroll
-  for (int j = 0; j < kStemC; ++j) acc[j] = 0.f;
+  for (int j = 0; j < kStemC; ++j) acc0[j] = acc1[j] = 0.f;
   const float* base = frames + static_cast<long long>(n) * 3 * H * W;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int iy = oh * 2 + r - 1;
     if (iy < 0 || iy >= H) continue;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int ix = ow * 2 + q - 1;
-      if (ix < 0 || ix >= W) continue;
+    for (int c = 0; c < 3; ++c) {
+      const float* rowp = base + (static_cast<long long>(c) * H + iy) * W;
+      float xin[5];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float x = __ldg(base + (static_cast<long long>(c) * H + iy) * W + ix);
+      for (int q = 0; q < 5; ++q) {
+        const int ix = ow * 2 + q - 1;
+        xin[q] = (ix >= 0 && ix < W) ? __ldg(rowp + ix) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
         const float4* wp = reinterpret_cast<const float4*>(s_w + ((r * 3 + q) * 3 + c) * kStemC);
+        const float x0 = xin[q], x1 = xin[q + 2];
 #pragma unroll
         for (int j4 = 0; j4 < kStemC / 4; ++j4) {
           const float4 w = wp[j4];
-          acc[4 * j4 + 0] = fmaf(x, w.x, acc[4 * j4 + 0]);
-          acc[4 * j4 + 1] = fmaf(x, w.y, acc[4 * j4 + 1]);
-          acc[4 * j4 + 2] = fmaf(x, w.z, acc[4 * j4 + 2]);
-          acc[4 * j4 + 3] = fmaf(x, w.w, acc[4 * j4 + 3]);
+          acc0[4 * j4 + 0] = fmaf(x0, w.x, acc0[4 * j4 + 0]);
+          acc0[4 * j4 + 1] = fmaf(x0, w.y, acc0[4 * j4 + 1]);
+          acc0[4 * j4 + 2] = fmaf(x0, w.z, acc0[4 * j4 + 2]);
+          acc0[4 * j4 + 3] = fmaf(x0, w.w, acc0[4 * j4 + 3]);
+          acc1[4 * j4 + 0] = fmaf(x1, w.x, acc1[4 * j4 + 0]);
+          acc1[4 * j4 + 1] = fmaf(x1, w.y, acc1[4 * j4 + 1]);
+          acc1[4 * j4 + 2] = fmaf(x1, w.z, acc1[4 * j4 + 2]);
+          acc1[4 * j4 + 3] = fmaf(x1, w.w, acc1[4 * j4 + 3]);
         }
       }
     }
   }
-  __half* op = out + static_cast<long long>(idx) * kStemC;
+  __half* op = out + ((static_cast<long long>(n) * Ho + oh) * Wo + ow) * kStemC;
 #pragma unroll
-  for (int g = 0; g < kStemC / 8; ++g) {
-    uint4 ov;
-    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+  for (int px = 0; px < 2; ++px) {
+    if (ow + px >= Wo) break;
+    const float* acc = px == 0 ? acc0 : acc1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = g * 8 + 2 * j;
-      oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[c], s_scale[c], s_bias[c]), act),
-                                 act_apply(fmaf(acc[c + 1], s_scale[c + 1], s_bias[c + 1]), act));
+    for (int g = 0; g < kStemC / 8; ++g) {
+      uint4 ov;
+      __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = g * 8 + 2 * j;
+        oh2[j] = __floats2half2_rn(act_apply(fmaf(acc[c], s_scale[c], s_bias[c]), act),
+                                   act_apply(fmaf(acc[c + 1], s_scale[c + 1], s_bias[c + 1]), act));
+      }
+      reinterpret_cast<uint4*>(op + px * kStemC)[g] = ov;
     }
-    reinterpret_cast<uint4*>(op)[g] = ov;
   }
 }
 
@@ -589,7 +612,7 @@ cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const f
                                   __half* out, int N, int H, int W, int act, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(N) * Ho * Wo;
+  const long long total = static_cast<long long>(N) * Ho * ((Wo + 1) / 2);
   if (total >= (1LL << 32)) return cudaErrorInvalidValue;
   stem_conv3x3s2_kernel<<<grid_for(total), kThreads, 0, s>>>(frames, w27, scale, bias, out, N, H, W, Ho, Wo, act);
   return cudaGetLastError();
