@@ -46,8 +46,8 @@ SIGNATURES = {
     "af_crop_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "af_action_to_yx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_int, c_int, c_int, c_void_p]),
+    "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p]),
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),
@@ -65,6 +65,7 @@ SIGNATURES = {
     "af_policy_head_continuous": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                           c_void_p]),
     "af_tsm_shift_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_tsm_shift_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_consensus_avg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "af_fill_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
     "af_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

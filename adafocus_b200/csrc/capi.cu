@@ -226,15 +226,15 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
                   [=](cudaStream_t s) { return af::launch_action_to_yx(action, yx, N, H, P, s); });
 }
 
-int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* out, int N, int H, int W, int P, int KH,
-                   int KW, int stride, int pad, int Kpad, void* stream) {
+int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W,
+                   int P, int KH, int KW, int stride, int pad, int Kpad, void* stream) {
   if (frames == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_stem_im2col: null tensor");
   if (Kpad % 8 != 0 || Kpad < KH * KW * 3 || P > H || P > W || stride < 1)
     return fail(AF_ERR_INVALID, "af_stem_im2col: bad geometry");
   const int Ho = (P + 2 * pad - KH) / stride + 1, Wo = (P + 2 * pad - KW) / stride + 1;
   __half* o = static_cast<__half*>(out);
   return dispatch(ctx, stream, "af_stem_im2col", [=](cudaStream_t s) {
-    return af::launch_stem_im2col(frames, yx, o, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad, s);
+    return af::launch_stem_im2col(frames, yx, yx_div, o, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad, s);
   });
 }
 
@@ -422,6 +422,14 @@ int af_tsm_shift_nhwc_f16(af_ctx* ctx, const void* in, void* out, int NT, int T,
   __half* o = static_cast<__half*>(out);
   return dispatch(ctx, stream, "af_tsm_shift_nhwc_f16",
                   [=](cudaStream_t s) { return af::launch_tsm_shift(i, o, NT, T, HW, C, fold, s); });
+}
+
+int af_tsm_shift_nchw_f32(af_ctx* ctx, const float* in, float* out, int NT, int T, int C, int HW, int fold,
+                          void* stream) {
+  if (in == nullptr || out == nullptr || in == out || T < 1 || NT % T != 0 || 2 * fold > C)
+    return fail(AF_ERR_INVALID, "af_tsm_shift_nchw_f32: bad argument (NT must be a multiple of T, out != in)");
+  return dispatch(ctx, stream, "af_tsm_shift_nchw_f32",
+                  [=](cudaStream_t s) { return af::launch_tsm_shift_nchw_f32(in, out, NT, T, C, HW, fold, s); });
 }
 
 int af_consensus_avg(af_ctx* ctx, const float* in, const float* add, float* out, int B, int T, int C, void* stream) {

@@ -114,8 +114,9 @@ constexpr int kStemMaxWindow = 3 * 7 * ((kStemStrip - 1) * 2 + 7);   // 3 ch x 7
 constexpr int kStemMaxK = 256;
 
 __global__ void __launch_bounds__(kThreads)
-stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, __half* __restrict__ out, int N,
-                   int H, int W, int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad) {
+stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, int yx_div,
+                   __half* __restrict__ out, int N, int H, int W, int P, int KH, int KW, int stride, int pad, int Ho,
+                   int Wo, int Kpad) {
   __shared__ __half s_win[kStemMaxWindow];
   __shared__ short s_off[kStemMaxK];
   const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kStemStrip;
@@ -123,9 +124,10 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
   const int span = (strip - 1) * stride + KW;
   const int kreal = KH * KW * 3;
   int y0 = 0, x0 = 0;
-  if (yx != nullptr) {
-    y0 = max(0, min(yx[2 * n], H - P));
-    x0 = max(0, min(yx[2 * n + 1], W - P));
+  if (yx != nullptr) {   // one (y,x) per yx_div consecutive frames (STH: one crop per video division)
+    const int e = n / yx_div;
+    y0 = max(0, min(yx[2 * e], H - P));
+    x0 = max(0, min(yx[2 * e + 1], W - P));
   }
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
     int off = -1;
@@ -551,6 +553,24 @@ tsm_shift_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NT
       *reinterpret_cast<const uint4*>(vals);
 }
 
+// fp32 NCHW form of the shift, for the public TemporalShift.shift() on reference-layout tensors (pure copy)
+__global__ void __launch_bounds__(kThreads)
+tsm_shift_nchw_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int NT, int T, int C, int HW,
+                          int fold) {
+  const long long total = static_cast<long long>(NT) * C * HW;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long chw = static_cast<long long>(C) * HW;
+  const int f = static_cast<int>(idx / chw);
+  const int c = static_cast<int>((idx % chw) / HW);
+  const int t = f % T;
+  float v;
+  if (c < fold) v = (t + 1 < T) ? __ldg(in + idx + chw) : 0.f;
+  else if (c < 2 * fold) v = (t > 0) ? __ldg(in + idx - chw) : 0.f;
+  else v = __ldg(in + idx);
+  out[idx] = v;
+}
+
 __global__ void consensus_avg_kernel(const float* __restrict__ in, const float* __restrict__ add,
                                      float* __restrict__ out, int B, int T, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -599,12 +619,13 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* out, int N, int H, int W, int P,
-                               int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s) {
+cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W,
+                               int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   if (KH > 7 || KW > 7 || stride > 2 || Kpad > kStemMaxK || N > 65535 || Ho > 65535) return cudaErrorInvalidValue;
   dim3 grid((Wo + kStemStrip - 1) / kStemStrip, Ho, N);
-  stem_im2col_kernel<<<grid, kThreads, 0, s>>>(frames, yx, out, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad);
+  stem_im2col_kernel<<<grid, kThreads, 0, s>>>(frames, yx, yx_div < 1 ? 1 : yx_div, out, N, H, W, P, KH, KW, stride,
+                                               pad, Ho, Wo, Kpad);
   return cudaGetLastError();
 }
 
@@ -693,6 +714,14 @@ cudaError_t launch_tsm_shift(const __half* in, __half* out, int NT, int T, int H
   if (NT <= 0) return cudaSuccess;
   const long long total = static_cast<long long>(NT) * HW * (C / 8);
   tsm_shift_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, NT, T, HW, C, fold);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tsm_shift_nchw_f32(const float* in, float* out, int NT, int T, int C, int HW, int fold,
+                                      cudaStream_t s) {
+  if (NT <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(NT) * C * HW;
+  tsm_shift_nchw_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, NT, T, C, HW, fold);
   return cudaGetLastError();
 }
 

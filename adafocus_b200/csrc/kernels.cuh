@@ -16,8 +16,9 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
 
 // Crop + fp32->fp16 + im2col staging of a 3-channel NCHW frame for a KHxKW / stride / pad stem convolution.
 // out[(n*Ho+oh)*Wo+ow][k], k = (kh*KW+kw)*3 + c (zero for k >= KH*KW*3 and for taps outside the P x P window).
-cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, __half* out, int N, int H, int W, int P,
-                               int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s);
+// yx holds one (y,x) per yx_div consecutive frames.
+cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W,
+                               int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s);
 
 // Direct 3 -> 32 channel 3x3 / stride 2 / pad 1 conv + folded BN + activation, fp32 NCHW frames -> NHWC fp16
 // (MobileNet-V2 features[0], ACT/models/mobilenet.py:105). w27: fp32 [27][32], k = (r*3+s)*3 + c.
@@ -63,6 +64,9 @@ cudaError_t launch_policy_head_continuous(const float* logits, long long logit_s
 // in[n,t-1] for fold<=c<2fold, in[n,t] otherwise; zero at the clip ends.
 cudaError_t launch_tsm_shift(const __half* in, __half* out, int NT, int T, int HW, int C, int fold,
                              cudaStream_t s);
+
+cudaError_t launch_tsm_shift_nchw_f32(const float* in, float* out, int NT, int T, int C, int HW, int fold,
+                                      cudaStream_t s);
 
 // out[b, c] = mean_t in[b*T+t, c] (+ add[b, c]) ; STH ConsensusModule('avg') (STH/ops/basic_ops.py:18-27).
 cudaError_t launch_consensus_avg(const float* in, const float* add, float* out, int B, int T, int C,

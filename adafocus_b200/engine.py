@@ -229,7 +229,7 @@ class Engine:
                   shape=(1, 1, m, k, x2d.stride(0)))
         return out
 
-    def stem(self, frames, pc, yx=None, patch=None):
+    def stem(self, frames, pc, yx=None, patch=None, yx_div=1):
         """frames (N,3,H,W) fp32 NCHW -> NHWC fp16 stem output; crop at yx (N,2 int32) of size `patch` fused in."""
         n, c, h, w = frames.shape
         assert c == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
@@ -238,8 +238,8 @@ class Engine:
         ho = (p + 2 * s["pad"] - s["kh"]) // s["stride"] + 1
         wo = (p + 2 * s["pad"] - s["kw"]) // s["stride"] + 1
         col = self.empty((n * ho * wo, s["kpad"]), torch.float16)
-        check(self.lib.af_stem_im2col(self.h, _ptr(frames), _ptr(yx), _ptr(col), n, h, w, p, s["kh"], s["kw"],
-                                      s["stride"], s["pad"], s["kpad"], self._stream()), "af_stem_im2col")
+        check(self.lib.af_stem_im2col(self.h, _ptr(frames), _ptr(yx), int(yx_div), _ptr(col), n, h, w, p, s["kh"],
+                                      s["kw"], s["stride"], s["pad"], s["kpad"], self._stream()), "af_stem_im2col")
         self._count()
         self.keep(frames, yx, col)
         out = self.empty((n, ho, wo, pc.cout), torch.float16)
@@ -358,6 +358,15 @@ class Engine:
         out = self.empty((nt, h, w, c), torch.float16)
         check(self.lib.af_tsm_shift_nhwc_f16(self.h, _ptr(x), _ptr(out), nt, t, h * w, c, fold, self._stream()),
               "af_tsm_shift_nhwc_f16")
+        self._count()
+        self.keep(x, out)
+        return out
+
+    def tsm_shift_nchw_f32(self, x, t, fold):
+        nt, c, h, w = x.shape
+        out = self.empty((nt, c, h, w), torch.float32)
+        check(self.lib.af_tsm_shift_nchw_f32(self.h, _ptr(x), _ptr(out), nt, t, c, h * w, fold, self._stream()),
+              "af_tsm_shift_nchw_f32")
         self._count()
         self.keep(x, out)
         return out

@@ -10,7 +10,7 @@ import math
 import torch
 from torch import nn
 
-from ..engine import AF_ACT_NONE, AF_ACT_RELU, get_engine, pack_conv
+from ..engine import AF_ACT_NONE, AF_ACT_RELU, fold_bn, get_engine, pack_conv
 
 
 class Memory:
@@ -74,32 +74,56 @@ class ActorCritic(nn.Module):
 
 
 class PolicyRunner:
-    def __init__(self, ac, key=None):
+    """Policy weights in kernel layout.  Handles both trees' encoders: ACT (conv 1x1 -> ReLU -> Linear -> ReLU,
+    ACT/models/ppo.py:33-39) and STH (conv 1x1 -> BN2d -> ReLU -> Linear -> BN1d -> ReLU over `fps` glance maps
+    stacked on channels, STH/models/ppo_continuous.py:33-42, STH/models/gfv_net.py:145-147), and both heads:
+    softmax/argmax over a square action grid or the continuous sigmoid head (STH/models/ppo_continuous.py:61-63)."""
+
+    def __init__(self, ac, key=None, map_channels=1280):
         if not ac.policy_conv:
             raise NotImplementedError("only the policy_conv=True encoder (MobileNet-V2 glancer) is implemented")
         self.key = key
-        enc = ac.state_encoder
-        dev = enc[0].weight.device
+        enc = list(ac.state_encoder)
+        conv = enc[0]
+        dev = conv.weight.device
         self.hidden = ac.hidden_state_dim
-        self.action_dim = ac.action_dim
-        self.enc_c = enc[0].weight.shape[0]                      # 32
-        self.enc_conv = pack_conv(enc[0].weight, act=AF_ACT_RELU, device=dev)
-        lin = enc[3]
-        hw = lin.weight.shape[1] // self.enc_c                   # 49
+        self.enc_c = conv.weight.shape[0]
+        cin_total = conv.weight.shape[1]
+        self.map_channels = min(map_channels, cin_total)
+        self.fps = cin_total // self.map_channels            # glance maps per policy state
+        bn2 = next((m for m in enc if isinstance(m, nn.BatchNorm2d)), None)
+        lin = next(m for m in enc if isinstance(m, nn.Linear))
+        bn1 = next((m for m in enc if isinstance(m, nn.BatchNorm1d)), None)
+        # conv over [t*C + c] channels == a (fps x 1) convolution over the frame axis of (M, fps, h*w, C)
+        w4 = conv.weight.detach().float().reshape(self.enc_c, self.fps, self.map_channels).permute(0, 2, 1)[..., None]
+        sc, bi = (None, None)
+        if bn2 is not None:
+            sc, bi = fold_bn(bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var, bn2.eps)
+        self.enc_conv = pack_conv(w4.contiguous(), sc, bi, act=AF_ACT_RELU, device=dev)
+        hw = lin.weight.shape[1] // self.enc_c
         self.hw = hw
         j = torch.arange(hw * self.enc_c)
         perm = (j % self.enc_c) * hw + (j // self.enc_c)         # NHWC-flatten index -> NCHW-flatten index
-        self.enc_fc = pack_conv(lin.weight, None, lin.bias, act=AF_ACT_RELU, device=dev, cin_perm=perm)
+        if bn1 is not None:
+            s1, b1 = fold_bn(bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.eps)
+            lb = lin.bias.detach().float() * s1 + b1 if lin.bias is not None else b1
+            self.enc_fc = pack_conv(lin.weight, s1, lb, act=AF_ACT_RELU, device=dev, cin_perm=perm)
+        else:
+            self.enc_fc = pack_conv(lin.weight, None, lin.bias, act=AF_ACT_RELU, device=dev, cin_perm=perm)
         g = ac.gru
         self.gru_ih = pack_conv(g.weight_ih_l0, None, g.bias_ih_l0, device=dev)
         self.gru_hh = pack_conv(g.weight_hh_l0, None, g.bias_hh_l0, device=dev, block_n=32)
         self.actor = pack_conv(ac.actor[0].weight, None, ac.actor[0].bias, device=dev)
+        self.continuous = isinstance(ac.actor[1], nn.Sigmoid)
+        self.action_dim = ac.actor[0].weight.shape[0]
         self.logit_stride = (self.action_dim + 7) // 8 * 8
 
     def encode(self, eng, fmap):
-        """fmap (M,h,w,C) NHWC fp16 -> GRU input pre-activations W_ih s + b_ih, fp32 (M, 3H)."""
-        m, h, w, c = fmap.shape
-        e = eng.conv(fmap, self.enc_conv)                                    # (M,h,w,32)
+        """fmap (M*fps, h, w, C) NHWC fp16, fps consecutive maps per state -> W_ih s + b_ih, fp32 (M, 3H)."""
+        mf, h, w, c = fmap.shape
+        m = mf // self.fps
+        e = eng.empty((m, 1, h * w, self.enc_c), torch.float16)
+        eng.conv(fmap, self.enc_conv, out=e, out_stride=self.enc_c, shape=(m, self.fps, h * w, c, c))
         s = eng.linear(e.view(m, h * w * self.enc_c), self.enc_fc)           # (M,H) fp16
         eng.release(e)
         xg = eng.linear(s, self.gru_ih, out_f32=True)                        # (M,3H) fp32
@@ -109,12 +133,15 @@ class PolicyRunner:
     def head(self, eng, hseq16, rows, img_h, patch, action_idx, action_yx, yx):
         logits = eng.empty((rows, self.logit_stride), torch.float32)
         eng.linear(hseq16, self.actor, out=logits, out_f32=True, out_stride=self.logit_stride)
-        eng.policy_head(logits, self.action_dim, img_h, patch, action_idx, action_yx, yx)
+        if self.continuous:
+            eng.policy_head_continuous(logits, img_h, patch, action_yx, yx)
+        else:
+            eng.policy_head(logits, self.action_dim, img_h, patch, action_idx, action_yx, yx)
         eng.release(logits)
 
     def rollout(self, eng, fmap, b, t, img_h, patch):
-        """All T steps for B clips; fmap rows are frame-major (b*T + t).  Returns (yx int32 (B*T,2),
-        action_idx int32 (B*T,), standard action fp32 (B*T,2))."""
+        """All t policy steps for b clips; states are row-major (b*t + step).  Returns (yx int32 (b*t,2),
+        action_idx int32 (b*t,) [discrete only], action fp32 (b*t,2))."""
         hd = self.hidden
         xg = self.encode(eng, fmap)
         h = eng.empty((b, hd), torch.float32)
@@ -128,7 +155,7 @@ class PolicyRunner:
             eng.linear(h16, self.gru_hh, out=hg, out_f32=True, out_stride=3 * hd)
             eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h16, hs3[:, step], t * hd)
         yx = eng.empty((b * t, 2), torch.int32)
-        idx = eng.empty((b * t,), torch.int32)
+        idx = None if self.continuous else eng.empty((b * t,), torch.int32)
         ayx = eng.empty((b * t, 2), torch.float32)
         self.head(eng, hseq16, b * t, img_h, patch, idx, ayx, yx)
         for tmp in (xg, h, h16, hg, hseq16):
@@ -136,7 +163,8 @@ class PolicyRunner:
         return yx, idx, ayx
 
     def step(self, eng, fmap, h_prev):
-        """Single step (reference-style call pattern): returns (h_new fp32 (B,H), action index int32 (B,))."""
+        """Single step (reference-style call pattern): returns (h_new fp32 (B,H), action) where action is the int32
+        index (B,) for the discrete head or the fp32 (B,2) action mean for the continuous head."""
         b, hd = h_prev.shape
         xg = self.encode(eng, fmap)
         h16 = eng.f32_to_f16(h_prev)
@@ -144,6 +172,10 @@ class PolicyRunner:
         h_new = torch.empty_like(h_prev)
         hn16 = torch.empty(b, hd, dtype=torch.float16, device=h_prev.device)
         eng.gru_gates(xg, 3 * hd, hg, h_prev, h_new, hn16)
+        if self.continuous:
+            act = torch.empty(b, 2, dtype=torch.float32, device=h_prev.device)
+            self.head(eng, hn16, b, 2, 1, None, act, None)
+            return h_new, act
         idx = torch.empty(b, dtype=torch.int32, device=h_prev.device)
         self.head(eng, hn16, b, 2, 1, idx, None, None)
         return h_new, idx

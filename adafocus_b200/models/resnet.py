@@ -130,10 +130,10 @@ class ResNetRunner:
                     e["ds"] = None
                 self.blocks.append(e)
 
-    def run(self, eng, frames, yx=None, patch=None):
+    def run(self, eng, frames, yx=None, patch=None, yx_div=1):
         """frames (N,3,H,W) fp32; with yx (N,2 int32) + patch the crop of ACT/models/utils.py:37-51 is fused into the
         stem staging.  Returns the layer4 output (N,h,w,2048) NHWC fp16."""
-        x = eng.stem(frames, self.stem, yx=yx, patch=patch)
+        x = eng.stem(frames, self.stem, yx=yx, patch=patch, yx_div=yx_div)
         y = eng.maxpool3x3s2(x)
         eng.release(x)
         x = y

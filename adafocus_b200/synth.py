@@ -43,9 +43,9 @@ def _closes_residual_branch(name):
     if ".bn3." in name:
         return True
     mb = _mbv2_block(name)
-    if mb is not None and mb[0] in _MBV2_RESIDUAL_BLOCKS and mb[1][0] == "conv" and mb[1][1] in ("2", "3") \
-            and len(mb[1]) == 3:
-        return True
+    if mb is not None and mb[0] in _MBV2_RESIDUAL_BLOCKS and mb[1][0] == "conv" and len(mb[1]) == 3:
+        # ACT layout: nested ConvBNReLU -> project BN is conv.2 / conv.3; STH (tonylins) flat layout: conv.7
+        return mb[1][1] in ("2", "3", "7")
     return False
 
 
@@ -57,7 +57,10 @@ def _input_is_linear(name):
     n, rest = mb
     if n == 18:
         return True
-    return n >= 2 and rest[:3] == ["conv", "0", "0"]
+    if n < 2 or rest[0] != "conv" or rest[1] != "0":
+        return False
+    # ACT: features.N.conv.0.0.weight ; STH flat: features.N.conv.0.weight or (TSM-wrapped) features.N.conv.0.net.weight
+    return rest[2:] in (["0", "weight"], ["weight"], ["net", "weight"])
 
 
 def _fill(name, t, sd, g):
@@ -128,6 +131,45 @@ def load_checkpoint_act(model, ck):
     model.classifier.load_state_dict(ck["fc"])
     model.focuser.policy.policy.load_state_dict(ck["policy"])
     model.focuser.policy.policy_old.load_state_dict(ck["policy"])
+
+
+def sth_args(**over):
+    """args namespace for the STH-tree GFV (STH/models/gfv_net.py:21-69) with evaluate.sh's values."""
+    a = dict(num_segments_glancer=8, num_segments_focuser=12, num_classes=174, batch_size=32, patch_size=144,
+             with_glancer=True, feature_map_channels=1280, video_div=1, glance_size=224, action_dim=25,
+             hidden_state_dim=1024, policy_conv=True, gpu=0, ppo_continuous=True, gamma=0.7, policy_lr=0.0003,
+             action_std=0.25, actorcritic_with_bn=True, modality="RGB", base_model="resnet50", partial_bn=False,
+             pretrain="imagenet", is_shift=True, shift_div=8, shift_place="blockres", fc_lr5=False,
+             temporal_pool=False, non_local=False, random_patch=False, dropout=0.5, train_stage=2, evaluate=True,
+             seed=SEED)
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+def synth_checkpoint_sth(model, seed=SEED):
+    """Checkpoint dict in the STH format (STH/evaluate.py:136-146): 'glancer', 'focuser', 'fc', 'policy'.  Call it after
+    the fc of focuser.net.base_model has been stripped (STH/evaluate.py:83) so the keys match what evaluate.py loads."""
+    return {
+        "glancer": synth_state_dict(model.glancer, seed + 11),
+        "focuser": synth_state_dict(model.focuser, seed + 12),
+        "fc": synth_state_dict(model.classifier, seed + 13),
+        "policy": synth_state_dict(model.focuser.policy.policy, seed + 14),
+        "best_acc": 0.0, "epoch": 0,
+    }
+
+
+def load_checkpoint_sth(model, ck):
+    """The reference's loading sequence (STH/evaluate.py:141-146)."""
+    model.glancer.load_state_dict(ck["glancer"], strict=True)
+    model.focuser.load_state_dict(ck["focuser"], strict=True)
+    model.classifier.load_state_dict(ck["fc"], strict=True)
+    model.focuser.policy.policy.load_state_dict(ck["policy"])
+    model.focuser.policy.policy_old.load_state_dict(ck["policy"])
+
+
+def strip_fc_sth(model):
+    """STH/evaluate.py:83."""
+    model.focuser.net.base_model = torch.nn.Sequential(*list(model.focuser.net.base_model.children())[:-1])
 
 
 def synth_clips(batch, frames=16, size=224, seed=SEED, device="cpu"):

@@ -97,9 +97,11 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
 /* Crop + fp32->fp16 + im2col staging that feeds a 3-channel stem convolution as a GEMM:
  * ResNet conv1 7x7/2 pad 3 (ACT/models/resnet.py:138) on the patch selected by yx (fused get_patch), or
  * MobileNet-V2 features[0] 3x3/2 pad 1 (ACT/models/mobilenet.py:105) on the whole frame (yx = NULL, P = H).
- * frames (N,3,H,W) fp32 -> out [(N*Ho*Wo)][Kpad] fp16, k = (r*KW+s)*3 + c. */
-int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, void* out, int N, int H, int W, int P,
-                   int KH, int KW, int stride, int pad, int Kpad, void* stream);
+ * frames (N,3,H,W) fp32 -> out [(N*Ho*Wo)][Kpad] fp16, k = (r*KW+s)*3 + c.  yx has one (y,x) row per yx_div
+ * consecutive frames (1 for ACT; T_f / video_div for STH, where get_patch crops all frames of a division at once,
+ * STH/models/gfv_net.py:141-152,421). */
+int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W,
+                   int P, int KH, int KW, int stride, int pad, int Kpad, void* stream);
 
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
@@ -144,6 +146,10 @@ int af_policy_head_continuous(af_ctx* ctx, const float* logits, int64_t logit_st
 
 /* TemporalShift.shift -- STH/ops/temporal_shift.py:29-46, NHWC fp16, fold = C / shift_div. */
 int af_tsm_shift_nhwc_f16(af_ctx* ctx, const void* in, void* out, int NT, int T, int HW, int C, int fold,
+                          void* stream);
+
+/* The same shift on reference-layout tensors (NT,C,H,W) fp32 -- the public TemporalShift.shift(). */
+int af_tsm_shift_nchw_f32(af_ctx* ctx, const float* in, float* out, int NT, int T, int C, int HW, int fold,
                           void* stream);
 
 /* ConsensusModule('avg') (+ glancer consensus) -- STH/ops/basic_ops.py:18-27, STH/models/gfv_net.py:170-172. */

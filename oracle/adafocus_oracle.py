@@ -103,22 +103,51 @@ def mobilenet_v2_features(x, sd, prefix="net.features.", tsm=None):
     return cbr(x, f"{prefix}{idx}.", 1, 1)
 
 
+def mobilenet_v2_features_flat(x, sd, prefix="net.features.", tsm=None):
+    """STH/models/mobilenetv2.py:7-66 (tonylins layout: InvertedResidual.conv is one flat Sequential) with the temporal
+    shift wrapped around conv[0] of the residual blocks that have an expand conv (STH/models/gfv_net.py:238-241)."""
+    x = F.relu6(_bn(F.conv2d(x, sd[prefix + "0.0.weight"], None, 2, 1), sd, prefix + "0.1."))
+    idx, cin = 1, 32
+    for t, c, n, s in MBV2_SETTING:
+        for i in range(n):
+            stride = s if i == 0 else 1
+            p = f"{prefix}{idx}.conv."
+            res = stride == 1 and cin == c
+            y = x
+            k = 0
+            if t != 1:
+                w = sd.get(p + "0.weight")
+                if w is None:                               # TemporalShift wrapper: conv.0.net.weight
+                    w = sd[p + "0.net.weight"]
+                    y = temporal_shift(y, tsm[0], tsm[1])
+                y = F.relu6(_bn(F.conv2d(y, w), sd, p + "1."))
+                k = 3
+            y = F.relu6(_bn(F.conv2d(y, sd[f"{p}{k}.weight"], None, stride, 1, 1, cin * t), sd, f"{p}{k + 1}."))
+            y = _bn(F.conv2d(y, sd[f"{p}{k + 3}.weight"]), sd, f"{p}{k + 4}.")
+            x = x + y if res else y
+            cin = c
+            idx += 1
+    return F.relu6(_bn(F.conv2d(x, sd[f"{prefix}{idx}.0.weight"]), sd, f"{prefix}{idx}.1."))
+
+
 def mobilenet_v2_get_featmap(x, sd, prefix="net.features."):
     """ACT/models/mobilenet.py:146-148: (feature map, mean over H,W)."""
     f = mobilenet_v2_features(x, sd, prefix)
     return f, f.mean([2, 3])
 
 
-def resnet_trunk(x, sd, prefix="net.", layers=(3, 4, 6, 3), pooled=True, tsm=None):
+def resnet_trunk(x, sd, prefix="net.", layers=(3, 4, 6, 3), pooled=True, tsm=None, names=None):
     """ACT/models/resnet.py:211-225 with Bottleneck.forward :94-114 (stride on conv2); fc not applied.
     tsm=(n_segment, fold_div, n_round) shifts conv1's input of every n_round-th block of a stage
     (STH/ops/temporal_shift.py:113-135, blockres)."""
-    x = F.conv2d(x, sd[prefix + "conv1.weight"], None, 2, 3)
-    x = F.relu(_bn(x, sd, prefix + "bn1."))
+    # names: child names of (conv1, bn1, layer1..4); the fc-stripped nn.Sequential of STH/evaluate.py:83 numbers them
+    names = names or ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4")
+    x = F.conv2d(x, sd[f"{prefix}{names[0]}.weight"], None, 2, 3)
+    x = F.relu(_bn(x, sd, f"{prefix}{names[1]}."))
     x = F.max_pool2d(x, 3, 2, 1)
     for li, nblocks in enumerate(layers, start=1):
         for bi in range(nblocks):
-            p = f"{prefix}layer{li}.{bi}."
+            p = f"{prefix}{names[1 + li]}.{bi}."
             stride = 2 if (li > 1 and bi == 0) else 1
             idn = x
             y = x
@@ -179,6 +208,69 @@ def recurrent_classifier(features, sd):
 
 
 # ------------------------------------------------------------------------------------------------ whole path (ACT)
+SEQ_NAMES = ("0", "1", "4", "5", "6", "7")     # conv1, bn1, layer1..4 inside nn.Sequential(*children[:-1])
+
+
+def policy_act_continuous(state, h, sd):
+    """STH/models/ppo_continuous.py:78-109, eval branch: conv1x1 -> BN2d -> ReLU -> Flatten -> Linear -> BN1d -> ReLU,
+    one GRU step, action_mean = sigmoid(Linear)."""
+    p = "state_encoder."
+    s = F.conv2d(state, sd[p + "0.weight"])
+    if (p + "1.running_mean") in sd:
+        s = F.relu(_bn(s, sd, p + "1.")).flatten(1)
+        s = s @ sd[p + "4.weight"].t() + sd[p + "4.bias"]
+        s = F.relu(F.batch_norm(s, sd[p + "5.running_mean"], sd[p + "5.running_var"], sd[p + "5.weight"],
+                                sd[p + "5.bias"], False, 0.0, BN_EPS))
+    else:
+        s = F.relu(s).flatten(1)
+        s = F.relu(s @ sd[p + "3.weight"].t() + sd[p + "3.bias"])
+    h = gru_cell(s, h, sd["gru.weight_ih_l0"], sd["gru.weight_hh_l0"], sd["gru.bias_ih_l0"], sd["gru.bias_hh_l0"])
+    return torch.sigmoid(h @ sd["actor.0.weight"].t() + sd["actor.0.bias"]), h
+
+
+@torch.no_grad()
+def sth_forward(glancer_images, focuser_images, ck, patch_size=144, t_g=8, t_f=12, video_div=1, shift_div=8,
+                layers=(3, 4, 6, 3), with_glancer=True, rand_actions=None):
+    """STH/evaluate.py:188-201 + STH/models/gfv_net.py:101-225 on CPU fp32: glance, then per video division one
+    continuous policy step, get_patch over all frames of the division, TSM-ResNet, classifier, average consensus.
+    rand_actions (video_div, B, 2): the torch.rand draws of random_patching -> also returns the baseline logits."""
+    gi, fi = glancer_images.float().cpu(), focuser_images.float().cpu()
+    b = gi.shape[0]
+    g = gi.shape[-1]
+    fmap = mobilenet_v2_features_flat(gi.view(b * t_g, 3, g, g), ck["glancer"], "net.features.", (t_g, shift_div))
+    glogit = fmap.mean(3).mean(2) @ ck["glancer"]["net.classifier.weight"].t() + ck["glancer"]["net.classifier.bias"]
+    fmap5 = fmap.view(b, t_g, *fmap.shape[1:])
+    glogit = glogit.view(b, t_g, -1)
+    frames = fi.view(b, t_f, 3, fi.shape[-2], fi.shape[-1])
+    n_round = 2 if layers[2] >= 23 else 1
+    fpg, fpf = t_g // video_div, t_f // video_div
+    hid = torch.zeros(b, ck["policy"]["gru.weight_hh_l0"].shape[1])
+    patches, base_patches, actions, coords, preds, baselines = None, None, [], [], [], []
+
+    def head(pt, nframes):
+        feat = resnet_trunk(pt.reshape(-1, 3, patch_size, patch_size), ck["focuser"], "net.base_model.", layers, True,
+                            (t_f, shift_div, n_round), SEQ_NAMES).flatten(1)
+        logit = (feat @ ck["fc"]["weight"].t() + ck["fc"]["bias"]).view(b, nframes, -1).mean(1)
+        return logit + glogit.mean(1) if with_glancer else logit
+
+    for d in range(video_div):
+        cur_img = frames[:, d * fpf:(d + 1) * fpf].reshape(b, -1, *frames.shape[-2:])
+        cur_map = fmap5[:, d * fpg:(d + 1) * fpg].reshape(b, -1, *fmap5.shape[-2:])
+        a, hid = policy_act_continuous(cur_map, hid, ck["policy"])
+        actions.append(a)
+        coords.append(patch_coordinates(a.numpy(), cur_img.shape[2], patch_size))
+        cur = torch.from_numpy(get_patch(cur_img.numpy(), a.numpy(), patch_size)).view(b, fpf, 3, patch_size, patch_size)
+        if rand_actions is not None:
+            rnd = torch.from_numpy(get_patch(cur_img.numpy(), np.asarray(rand_actions[d]), patch_size))
+            rnd = rnd.view(b, fpf, 3, patch_size, patch_size)
+            base_patches = rnd if patches is None else torch.cat([patches, rnd], 1)
+            baselines.append(head(base_patches, fpf * (d + 1)))
+        patches = cur if patches is None else torch.cat([patches, cur], 1)
+        preds.append(head(patches, fpf * (d + 1)))
+    return {"fmap": fmap5, "glogit": glogit, "actions": torch.stack(actions, 1), "coords": np.stack(coords, 1),
+            "patches": patches, "preds": preds, "pred": preds[-1], "baselines": baselines}
+
+
 @torch.no_grad()
 def act_forward(inp, scan, ck, patch_size=128, action_dim=49, with_glancer=True, actions_override=None,
                 layers=(3, 4, 6, 3)):

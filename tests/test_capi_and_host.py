@@ -120,3 +120,22 @@ def test_gfv_quirks_and_out_of_scope_paths():
         m(input=x, scan=x, backbone_pred=True, one_step=False, glancer=True)
     with pytest.raises(RuntimeError):
         m(input=x, scan=x, training=False, backbone_pred=False, one_step=True)     # CPU tensors: no fallback
+
+
+def test_sth_parameter_names_match_reference(golden_dir):
+    """STH tree: state-dict keys of the mirror (after the fc strip of STH/evaluate.py:83) == the reference's."""
+    from adafocus_b200 import synth
+    from adafocus_b200.models_sth.gfv_net import GFV as GFV_STH
+    ref = json.load(open(os.path.join(golden_dir, "ref_state_keys_sth.json")))
+    m = GFV_STH(synth.sth_args())
+    synth.strip_fc_sth(m)
+    ours = {"glancer": m.glancer.state_dict(), "focuser": m.focuser.state_dict(), "fc": m.classifier.state_dict(),
+            "policy": m.focuser.policy.policy.state_dict(), "model": m.state_dict()}
+    for part, sd in ours.items():
+        assert list(sd.keys()) == [k for k, _ in ref[part]], part
+        assert [list(v.shape) for v in sd.values()] == [s for _, s in ref[part]], part
+    # ResNet-101: TSM on every second block of every stage (n_round = 2, STH/ops/temporal_shift.py:124-135)
+    m101 = GFV_STH(synth.sth_args(base_model="resnet101"))
+    shifted = [k for k in m101.focuser.state_dict() if k.endswith("conv1.net.weight")]
+    assert len(shifted) == 2 + 2 + 12 + 2
+    assert m.eval() is None

@@ -71,3 +71,48 @@ def test_act_forward_matches_reference(golden_dir, tag, over, batch):
     np.testing.assert_allclose(out["logits"].numpy(), gold["logits"], rtol=1e-3, atol=3e-4)
     np.testing.assert_allclose(out["last_out"].numpy(), gold["last_out"], rtol=1e-3, atol=3e-4)
     assert np.array_equal(out["last_out"].argmax(1).numpy(), gold["last_out"].argmax(1))
+
+
+# ------------------------------------------------------------------------------------------------ STH tree
+STH_CASES = [
+    ("r50_p144_b2", dict(), 2),
+    ("div2_p96_b4", dict(video_div=2, num_segments_focuser=8, patch_size=96, actorcritic_with_bn=False,
+                         num_classes=40), 4),
+]
+
+
+def _sth_ck(args):
+    from adafocus_b200.models_sth.gfv_net import GFV as GFV_STH
+    model = GFV_STH(args)
+    synth.strip_fc_sth(model)
+    return synth.synth_checkpoint_sth(model, synth.SEED)
+
+
+@pytest.mark.parametrize("tag,over,batch", STH_CASES)
+def test_sth_forward_matches_reference(golden_dir, tag, over, batch):
+    gold = np.load(os.path.join(golden_dir, f"sth_{tag}.npz"))
+    args = synth.sth_args(**over)
+    ck = _sth_ck(args)
+    gi = synth.synth_clips(batch, args.num_segments_glancer, 224, synth.SEED + 1)
+    fi = synth.synth_clips(batch, args.num_segments_focuser, 224, synth.SEED + 2)
+    out = orc.sth_forward(gi, fi, ck, args.patch_size, args.num_segments_glancer, args.num_segments_focuser,
+                          args.video_div, args.shift_div, rand_actions=gold["rand_draws"])
+    np.testing.assert_allclose(out["fmap"][:, :, ::64].numpy(), gold["fmap_sample"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["glogit"].numpy(), gold["glogit"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["actions"].numpy(), gold["actions"], rtol=0, atol=2e-6)
+    assert np.array_equal(out["coords"], gold["coords"])
+    assert np.allclose(out["patches"].double().sum(dim=(2, 3, 4)).numpy(), gold["patch_checksum"], rtol=0, atol=1e-9)
+    for d in range(args.video_div):
+        np.testing.assert_allclose(out["preds"][d].numpy(), gold["pred_stage3"][d], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(out["preds"][d].numpy(), gold["pred_stage2"][d], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(out["baselines"][d].numpy(), gold["baseline_stage2"][d], rtol=1e-4, atol=2e-5)
+    assert np.array_equal(out["pred"].argmax(1).numpy(), gold["pred_stage3"][-1].argmax(1))
+
+
+def test_temporal_shift_restatement():
+    x = torch.arange(2 * 4 * 8 * 1 * 1, dtype=torch.float32).view(8, 8, 1, 1)
+    y = orc.temporal_shift(x, 4, 8)
+    assert torch.equal(y[0, 0], x[1, 0]) and float(y[3, 0]) == 0.0          # channel 0 comes from t+1, zero at the end
+    assert float(y[0, 1]) == 0.0 and torch.equal(y[1, 1], x[0, 1])          # channel 1 comes from t-1, zero at the start
+    assert torch.equal(y[:, 2:], x[:, 2:])
+    assert float(y[4, 1]) == 0.0 and torch.equal(y[3, 0], torch.zeros(1, 1))   # clips do not leak into each other

@@ -41,7 +41,7 @@ def main():
             def f():
                 from adafocus_b200._lib import check
                 from ctypes import c_void_p
-                check(eng.lib.af_stem_im2col(eng.h, c_void_p(fr.data_ptr()), c_void_p(yx.data_ptr()),
+                check(eng.lib.af_stem_im2col(eng.h, c_void_p(fr.data_ptr()), c_void_p(yx.data_ptr()), 1,
                                              c_void_p(out.data_ptr()), n, 224, 224, 128, 7, 7, 2, 3, 192,
                                              eng._stream()), "im2col")
             timed(f, n * 3 * 128 * 128 * 4 + out.numel() * 2, w)
