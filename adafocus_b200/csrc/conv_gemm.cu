@@ -2,6 +2,8 @@
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace af {
 
 using namespace ptx;
@@ -34,6 +36,58 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActRelu) return fmaxf(x, 0.f);
   if (act == kActRelu6) return fminf(fmaxf(x, 0.f), 6.f);
   return x;
+}
+
+// Epilogue math for 32 accumulator columns of one row: y = act(acc * scale + bias (+ residual)) -> fp16, written as
+// four 16-byte chunks into the 128-byte-swizzled staging row.  ACT and RES are compile-time so the hot loop has no
+// per-element branches; ReLU / ReLU6 clamp on packed half2 after the conversion (exact: the clamp bounds 0 and 6 are
+// representable and rounding is monotonic).
+template <int ACT, bool RES>
+__device__ __forceinline__ void epilogue_half_slice(const uint32_t (&v)[32], const float* __restrict__ sc,
+                                                    const float* __restrict__ bi, const uint4* rv, uint8_t* srow,
+                                                    int row, int chunk0) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 sa = *reinterpret_cast<const float4*>(sc + g * 8), sb = *reinterpret_cast<const float4*>(sc + g * 8 + 4);
+    const float4 ba = *reinterpret_cast<const float4*>(bi + g * 8), bb = *reinterpret_cast<const float4*>(bi + g * 8 + 4);
+    float x[8];
+    x[0] = fmaf(__uint_as_float(v[g * 8 + 0]), sa.x, ba.x);
+    x[1] = fmaf(__uint_as_float(v[g * 8 + 1]), sa.y, ba.y);
+    x[2] = fmaf(__uint_as_float(v[g * 8 + 2]), sa.z, ba.z);
+    x[3] = fmaf(__uint_as_float(v[g * 8 + 3]), sa.w, ba.w);
+    x[4] = fmaf(__uint_as_float(v[g * 8 + 4]), sb.x, bb.x);
+    x[5] = fmaf(__uint_as_float(v[g * 8 + 5]), sb.y, bb.y);
+    x[6] = fmaf(__uint_as_float(v[g * 8 + 6]), sb.z, bb.z);
+    x[7] = fmaf(__uint_as_float(v[g * 8 + 7]), sb.w, bb.w);
+    if (RES) {
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv[g]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(rh[j]);
+        x[2 * j] += f.x;
+        x[2 * j + 1] += f.y;
+      }
+    }
+    uint4 ov;
+    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      if (ACT != kActNone) h = __hmax2(h, __float2half2_rn(0.f));
+      if (ACT == kActRelu6) h = __hmin2(h, __float2half2_rn(6.f));
+      oh2[j] = h;
+    }
+    *reinterpret_cast<uint4*>(srow + (((chunk0 + g) ^ (row & 7)) << 4)) = ov;     // 128-B swizzle, conflict-free
+  }
+}
+
+template <bool RES>
+__device__ __forceinline__ void epilogue_half_slice_act(int act, const uint32_t (&v)[32], const float* sc,
+                                                        const float* bi, const uint4* rv, uint8_t* srow, int row,
+                                                        int chunk0) {
+  if (act == kActRelu) epilogue_half_slice<kActRelu, RES>(v, sc, bi, rv, srow, row, chunk0);
+  else if (act == kActRelu6) epilogue_half_slice<kActRelu6, RES>(v, sc, bi, rv, srow, row, chunk0);
+  else epilogue_half_slice<kActNone, RES>(v, sc, bi, rv, srow, row, chunk0);
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -87,9 +141,13 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous
+  // kernel in the stream; nothing below may read or write global memory before that kernel has completed.
+  pdl_launch_dependents();
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
+      pdl_wait_prior_grid();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -181,6 +239,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
+    pdl_wait_prior_grid();
     for (int it = group; blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += kEpilogueGroups) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int nb = tile % p.n_blocks;
@@ -199,15 +258,37 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                              static_cast<uint32_t>(as * kConvMaxBlockN);
       if (p.tma_store) {
         // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
-        const bool has_res = (p.residual != nullptr) && valid;
+        const bool has_res = (p.residual != nullptr) && valid && !(p.debug_flags & 2);
         const int nslices = (p.BN + 63) >> 6;
-        uint4 rv[8];
-        if (has_res) {   // residual of the first slice: in flight while the accumulator finishes
-          const __half* rp = p.residual + pix * p.res_stride + co_base;
+        // residual of the first TWO slices goes in flight now, long before the accumulator is ready; later slices
+        // are prefetched two slices ahead into the slot that was just consumed
+        uint4 rv_a[8], rv_b[8];
+        const __half* res_row = has_res ? p.residual + pix * p.res_stride + co_base : nullptr;
+        // each lane reads its own row: 32-byte loads halve the number of (uncoalesced) requests when alignment allows
+        const bool res256 = has_res && ((reinterpret_cast<uintptr_t>(p.residual) | (p.res_stride * 2)) & 31) == 0 &&
+                            (p.Cout & 15) == 0 && (co_base & 15) == 0;
+        auto load_res = [&](uint4 (&dst)[8], int col0) {
+          if (res256) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            rv[g] = (co_base + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
-                                                   : make_uint4(0u, 0u, 0u, 0u);
+            for (int g = 0; g < 8; g += 2) {
+              if (co_base + col0 + g * 8 + 16 <= p.Cout) {
+                ldg256_nc(res_row + col0 + g * 8, dst[g], dst[g + 1]);
+              } else {
+                dst[g] = make_uint4(0u, 0u, 0u, 0u);
+                dst[g + 1] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              dst[g] = (co_base + col0 + g * 8 + 8 <= p.Cout)
+                           ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + g * 8))
+                           : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        if (has_res) {
+          load_res(rv_a, 0);
+          if (nslices > 1) load_res(rv_b, 64);
         }
         if (nb != loaded_nb) {
           // per-channel scale / bias of this n-block -> smem (zero past BN so stray columns stay finite).  Every
@@ -222,68 +303,45 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         mbar_wait(&ctrl->tmem_full[as], aphase);
         tc_fence_after();
-        for (int sl = 0; sl < nslices; ++sl) {
+        auto do_slice = [&](int sl, uint4 (&rvx)[8]) {
           const int c0 = sl * 64;
-          uint32_t v0[32], v1[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v0);
-          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32), v1);
-          tmem_ld_wait();
-          if (sl == nslices - 1) {
-            // accumulator fully read: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
-          }
+          // this staging buffer was last read by the store issued two slices ago; thread 0 waited for that store
+          // before the previous slice's barrier
           uint8_t* staging = group_staging + (slice_ctr & 1) * kConvStagingBytes;
           ++slice_ctr;
           uint8_t* srow = staging + row * 128;
-          const float4* scp = reinterpret_cast<const float4*>(g_scale + c0);
-          const float4* bip = reinterpret_cast<const float4*>(g_bias + c0);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 sa = scp[2 * g], sb = scp[2 * g + 1], ba = bip[2 * g], bb = bip[2 * g + 1];
-            const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-            const float biv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = g * 8 + j;
-              const uint32_t raw = (c < 32) ? v0[c] : v1[c - 32];
-              x[j] = fmaf(__uint_as_float(raw), scv[j], biv[j]);
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + hf * 32), v);
+            tmem_ld_wait();
+            if (hf == 1 && sl == nslices - 1) {
+              // accumulator fully read: hand the TMEM stage back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
             }
-            if (has_res) {
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv[g]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(rh[j]);
-                x[2 * j] += f.x;
-                x[2 * j + 1] += f.y;
-              }
-            }
-            uint4 ov;
-            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              oh2[j] = __floats2half2_rn(apply_act(x[2 * j], p.act), apply_act(x[2 * j + 1], p.act));
-            // this buffer was last read by the store issued two slices ago, which thread 0 waited for before the
-            // previous slice's barrier
-            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) = ov;        // 128-B swizzle, conflict-free
+            if (has_res)
+              epilogue_half_slice_act<true>(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, &rvx[hf * 4], srow,
+                                            row, hf * 4);
+            else
+              epilogue_half_slice_act<false>(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, nullptr, srow,
+                                             row, hf * 4);
           }
-          if (has_res && sl + 1 < nslices) {   // prefetch the next slice's residual
-            const __half* rp = p.residual + pix * p.res_stride + co_base + c0 + 64;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              rv[g] = (co_base + c0 + 64 + g * 8 + 8 <= p.Cout) ? __ldg(reinterpret_cast<const uint4*>(rp + g * 8))
-                                                              : make_uint4(0u, 0u, 0u, 0u);
-          }
+          if (has_res && sl + 2 < nslices) load_res(rvx, c0 + 128);   // refill the consumed slot two slices ahead
           fence_proxy_async();
           if (et == 0) tma_store_wait_read0();   // the previous slice's store has left the other buffer
           named_barrier_sync(bar_id, kEpilogueThreads);
-          if (et == 0) {
+          if (et == 0 && !(p.debug_flags & 1)) {
             tma_store_4d(&maps.out, staging, co_base + c0, ow0, oh0, n0);
             tma_store_commit();
           }
+        };
+#pragma unroll 1
+        for (int sl = 0; sl < nslices; sl += 2) {
+          do_slice(sl, rv_a);
+          if (sl + 1 < nslices) do_slice(sl + 1, rv_b);
         }
       } else {
         // ---- fp32 (or odd-shaped) output: direct global stores, one row per thread
@@ -383,6 +441,8 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   const size_t smem = conv_gemm_smem_bytes(p.BN, p.KH * p.KW * p.cblks, &stages, &epi_bufs);
   p.stages = stages;
   p.epi_bufs = epi_bufs;
+  static const int dbg = getenv("AF_CONV_DEBUG") ? atoi(getenv("AF_CONV_DEBUG")) : 0;
+  p.debug_flags = dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -393,8 +453,18 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
   if (grid < 1) grid = 1;
-  conv_gemm_kernel<<<grid, kConvThreads, smem, stream>>>(maps, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = getenv("AF_NO_PDL") == nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel, maps, p);
 }
 
 }  // namespace af

@@ -51,6 +51,7 @@ struct ConvKernelParams {
   int act;
   int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
   int epi_bufs;                    // staging buffers per epilogue group (1 or 2)
+  int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores, 2 = skip residual loads
 };
 
 struct ConvTensorMaps {

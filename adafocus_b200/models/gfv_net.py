@@ -233,16 +233,15 @@ class _FusedPlan:
         eng.begin_plan()
         try:
             m0 = eng.mark()
-            fmap = glancer.run(eng, self.scan.view(b * t, 3, g, g))
+            fmap = glancer.run_chunked(eng, self.scan.view(b * t, 3, g, g), model.fg_chunk)
             if model.with_glancer:
                 eng.avgpool(fmap, out_f16=self.feat16, out_f16_stride=fdim)
             m1 = eng.mark()
             self.yx, self.action_idx, self.action_yx = policy.rollout(eng, fmap, b, t, h, p)
             eng.release(fmap)
             m2 = eng.mark()
-            lmap = focuser.run(eng, self.input.view(b * t, 3, h, w), yx=self.yx, patch=p)
-            eng.avgpool(lmap, out_f16=self.feat16[:, gdim:], out_f16_stride=fdim)
-            eng.release(lmap)
+            focuser.run_pooled_chunked(eng, self.input.view(b * t, 3, h, w), self.feat16[:, gdim:], fdim,
+                                       model.fl_chunk, yx=self.yx, patch=p)
             m3 = eng.mark()
             clf.sequence(eng, self.feat16, b, t, self.logits)
             m4 = eng.mark()
@@ -293,6 +292,10 @@ class GFV(nn.Module):
         else:
             raise NotImplementedError("consensus='fc' (LinearCLassifier) is not used by any shipped configuration")
         self._plans = {}
+        # sub-batch sizes (frames / patches) of the fused plan: intermediates of one sub-batch stay L2-resident
+        import os
+        self.fg_chunk = int(os.environ.get("AF_FG_CHUNK", "0")) or None
+        self.fl_chunk = int(os.environ.get("AF_FL_CHUNK", "0")) or None
 
     def train(self, mode=True):
         # the reference's train() returns None, so `model.eval()` returns None (ACT/models/gfv_net.py:60-62)

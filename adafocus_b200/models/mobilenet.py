@@ -155,7 +155,21 @@ class MobileNetV2Runner:
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
 
-    def run(self, eng, frames, tsm=None):
+    def run_chunked(self, eng, frames, chunk, tsm=None):
+        """run() over sub-batches of `chunk` frames so that every intermediate tensor of a sub-batch stays resident in
+        the 126 MB L2 between the layer that writes it and the layer that reads it (the workspace arena hands the same
+        hot buffers to every sub-batch).  Returns the full (N,h,w,1280) map."""
+        n = frames.shape[0]
+        if chunk is None or chunk >= n:
+            return self.run(eng, frames, tsm=tsm)
+        out = None
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            part = self.run(eng, frames[s0:s1], tsm=tsm, out_full=out, out_slice=(s0, s1), n_total=n)
+            out = part
+        return out
+
+    def run(self, eng, frames, tsm=None, out_full=None, out_slice=None, n_total=None):
         """frames (N,3,H,W) fp32 contiguous -> (N,h,w,1280) NHWC fp16. tsm=(T, shift_div) applies the temporal shift
         to the input of every residual block's first 1x1 conv (STH/models/gfv_net.py:238-241)."""
         if self.stem_direct:
@@ -182,9 +196,15 @@ class MobileNetV2Runner:
                 x = eng.conv(d, e["project"], residual=inp if e["res"] else None)
                 eng.release(d)
             eng.release(inp)
-        out = eng.conv(x, self.last)
+        if out_slice is None:
+            out = eng.conv(x, self.last)
+            eng.release(x)
+            return out
+        if out_full is None:
+            out_full = eng.empty((n_total, x.shape[1], x.shape[2], self.last.cout), torch.float16)
+        eng.conv(x, self.last, out=out_full[out_slice[0]:out_slice[1]], out_stride=self.last.cout)
         eng.release(x)
-        return out
+        return out_full
 
 
 def mobilenet_v2(pretrained=False, progress=True, **kwargs):

@@ -130,6 +130,18 @@ class ResNetRunner:
                     e["ds"] = None
                 self.blocks.append(e)
 
+    def run_pooled_chunked(self, eng, frames, out_f16, out_stride, chunk, yx=None, patch=None, yx_div=1):
+        """Trunk + global average pool over sub-batches of `chunk` patches (L2-resident intermediates, see
+        MobileNetV2Runner.run_chunked); pooled fp16 features go to out_f16 rows (row stride out_stride)."""
+        n = frames.shape[0]
+        chunk = n if chunk is None else max(1, min(chunk, n))
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            sub_yx = None if yx is None else yx[s0 // yx_div:(s1 + yx_div - 1) // yx_div]
+            fmap = self.run(eng, frames[s0:s1], yx=sub_yx, patch=patch, yx_div=yx_div)
+            eng.avgpool(fmap, out_f16=out_f16[s0:s1], out_f16_stride=out_stride)
+            eng.release(fmap)
+
     def run(self, eng, frames, yx=None, patch=None, yx_div=1):
         """frames (N,3,H,W) fp32; with yx (N,2 int32) + patch the crop of ACT/models/utils.py:37-51 is fused into the
         stem staging.  Returns the layer4 output (N,h,w,2048) NHWC fp16."""
