@@ -1,11 +1,39 @@
 // HBM-bound helper kernels. All activations are NHWC fp16 unless the name says otherwise; math is fp32.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace af {
 
 namespace {
 
 constexpr int kThreads = 256;
+
+// Launch with programmatic stream serialization: the kernel may be scheduled while the previous kernel of the stream
+// drains; every kernel launched this way calls pdl_sync() before touching global memory.  kEarly = false launches
+// normally: measured on B200, letting the large multi-wave kernels (depthwise conv, stem staging, pooling) start early
+// costs ~8 % of the fG stage, while the tiny latency-bound ones (GRU gates, heads, fills) gain ~15 %.
+template <bool kEarly = true, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = getenv("AF_NO_PDL") == nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && kEarly) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// Helper kernels are multi-wave and bandwidth-bound: they must NOT release their dependents early (a persistent
+// conv CTA scheduled early would take an SM's registers / shared memory away from this kernel's remaining waves and
+// then idle), so they only wait; the implicit trigger at grid completion releases the next kernel.
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 inline unsigned grid_for(long long total, int threads = kThreads) {
   long long g = (total + threads - 1) / threads;
@@ -117,6 +145,7 @@ __global__ void __launch_bounds__(kThreads)
 stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, int yx_div,
                    __half* __restrict__ out, int N, int H, int W, int P, int KH, int KW, int stride, int pad, int Ho,
                    int Wo, int Kpad) {
+  pdl_sync();
   __shared__ __half s_win[kStemMaxWindow];
   __shared__ short s_off[kStemMaxK];
   const int n = blockIdx.z, oh = blockIdx.y, ow0 = blockIdx.x * kStemStrip;
@@ -182,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 stem_conv3x3s2_kernel(const float* __restrict__ frames, const float* __restrict__ w27, const float* __restrict__ scale,
                       const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int Ho, int Wo,
                       int act) {
+  pdl_sync();
   // two horizontally adjacent output pixels per thread: every weight vector fetched from shared memory feeds 8 FMAs
   __shared__ __align__(16) float s_w[27 * kStemC];
   __shared__ float s_scale[kStemC], s_bias[kStemC];
@@ -262,6 +292,7 @@ __global__ void __launch_bounds__(kThreads)
 dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, const float* __restrict__ scale,
                  const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W, int C, int Ho,
                  int Wo, int act) {
+  pdl_sync();
   constexpr int COLS = (WO - 1) * S + 3;
   const unsigned c8n = static_cast<unsigned>(C) >> 3;
   const unsigned wblocks = (static_cast<unsigned>(Wo) + WO - 1) / WO;
@@ -335,6 +366,7 @@ dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, c
 __global__ void __launch_bounds__(kThreads)
 maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int Ho,
                     int Wo) {
+  pdl_sync();
   const int c8n = C >> 3;
   const long long total = static_cast<long long>(N) * Ho * Wo * c8n;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -370,6 +402,7 @@ maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int
 __global__ void __launch_bounds__(kThreads)
 avgpool_kernel(const __half* __restrict__ in, float* __restrict__ out_f32, long long out_f32_stride,
                __half* __restrict__ out_f16, long long out_f16_stride, int N, int HW, int C) {
+  pdl_sync();
   const int c8n = C >> 3;
   const long long total = static_cast<long long>(N) * c8n;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -444,6 +477,7 @@ gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float*
                  const float* __restrict__ h_prev, float* __restrict__ h_new, __half* __restrict__ h_new_f16,
                  __half* __restrict__ hseq_f16, long long hseq_stride, float* __restrict__ hseq_f32,
                  long long hseq_f32_stride, int B, int Hd) {
+  pdl_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(B) * Hd) return;
   const int j = static_cast<int>(idx % Hd);
@@ -465,6 +499,7 @@ gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float*
 __global__ void __launch_bounds__(kThreads)
 policy_head_kernel(const float* __restrict__ logits, long long logit_stride, int A, int grid_n, int rows, int H,
                    int P, int32_t* __restrict__ action_idx, float* __restrict__ action_yx, int32_t* __restrict__ yx) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -516,6 +551,7 @@ policy_head_kernel(const float* __restrict__ logits, long long logit_stride, int
 __global__ void policy_head_continuous_kernel(const float* __restrict__ logits, long long logit_stride, int rows,
                                               int H, int P, float* __restrict__ action_yx,
                                               int32_t* __restrict__ yx) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 2) return;
   const int r = i >> 1, k = i & 1;
@@ -527,6 +563,7 @@ __global__ void policy_head_continuous_kernel(const float* __restrict__ logits, 
 // ------------------------------------------------------------------------------------------------ TSM / consensus
 __global__ void __launch_bounds__(kThreads)
 tsm_shift_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NT, int T, int HW, int C, int fold) {
+  pdl_sync();
   const int c8n = C >> 3;
   const long long total = static_cast<long long>(NT) * HW * c8n;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -573,6 +610,7 @@ tsm_shift_nchw_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
 
 __global__ void consensus_avg_kernel(const float* __restrict__ in, const float* __restrict__ add,
                                      float* __restrict__ out, int B, int T, int C) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C, b = i / C;
@@ -584,10 +622,12 @@ __global__ void consensus_avg_kernel(const float* __restrict__ in, const float* 
 }
 
 __global__ void fill_f32_kernel(float* p, float v, long long n) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(in[i]);
 }
@@ -624,7 +664,7 @@ cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_di
   if (N <= 0) return cudaSuccess;
   if (KH > 7 || KW > 7 || stride > 2 || Kpad > kStemMaxK || N > 65535 || Ho > 65535) return cudaErrorInvalidValue;
   dim3 grid((Wo + kStemStrip - 1) / kStemStrip, Ho, N);
-  stem_im2col_kernel<<<grid, kThreads, 0, s>>>(frames, yx, yx_div < 1 ? 1 : yx_div, out, N, H, W, P, KH, KW, stride,
+  return launch_pdl<false>(stem_im2col_kernel, dim3(grid), dim3(kThreads), 0, s, frames, yx, yx_div < 1 ? 1 : yx_div, out, N, H, W, P, KH, KW, stride,
                                                pad, Ho, Wo, Kpad);
   return cudaGetLastError();
 }
@@ -635,7 +675,7 @@ cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const f
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * Ho * ((Wo + 1) / 2);
   if (total >= (1LL << 32)) return cudaErrorInvalidValue;
-  stem_conv3x3s2_kernel<<<grid_for(total), kThreads, 0, s>>>(frames, w27, scale, bias, out, N, H, W, Ho, Wo, act);
+  return launch_pdl<false>(stem_conv3x3s2_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, w27, scale, bias, out, N, H, W, Ho, Wo, act);
   return cudaGetLastError();
 }
 
@@ -647,9 +687,9 @@ cudaError_t launch_dwconv3x3(const __half* in, const float* w9c, const float* sc
   const long long total = static_cast<long long>(N) * Ho * ((Wo + WO - 1) / WO) * (C / 8);
   if (total >= (1LL << 32)) return cudaErrorInvalidValue;
   if (stride == 1)
-    dwconv3x3_kernel<1, WO><<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
+    return launch_pdl<false>(dwconv3x3_kernel<1, WO>, dim3(grid_for(total)), dim3(kThreads), 0, s, in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
   else
-    dwconv3x3_kernel<2, WO><<<grid_for(total), kThreads, 0, s>>>(in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
+    return launch_pdl<false>(dwconv3x3_kernel<2, WO>, dim3(grid_for(total)), dim3(kThreads), 0, s, in, w9c, scale, bias, out, N, H, W, C, Ho, Wo, act);
   return cudaGetLastError();
 }
 
@@ -657,7 +697,7 @@ cudaError_t launch_maxpool3x3s2(const __half* in, __half* out, int N, int H, int
   if (N <= 0) return cudaSuccess;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, N, H, W, C, Ho, Wo);
+  return launch_pdl<false>(maxpool3x3s2_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out, N, H, W, C, Ho, Wo);
   return cudaGetLastError();
 }
 
@@ -665,7 +705,7 @@ cudaError_t launch_avgpool(const __half* in, float* out_f32, long long out_f32_s
                            long long out_f16_stride, int N, int HW, int C, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const long long total = static_cast<long long>(N) * (C / 8);
-  avgpool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out_f32, out_f32_stride, out_f16, out_f16_stride, N, HW, C);
+  return launch_pdl(avgpool_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out_f32, out_f32_stride, out_f16, out_f16_stride, N, HW, C);
   return cudaGetLastError();
 }
 
@@ -688,23 +728,21 @@ cudaError_t launch_gru_gates(const float* xg, long long xg_stride, const float* 
                              float* h_new, __half* h_new_f16, __half* hseq_f16, long long hseq_stride,
                              float* hseq_f32, long long hseq_f32_stride, int B, int Hd, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
-  gru_gates_kernel<<<grid_for(static_cast<long long>(B) * Hd), kThreads, 0, s>>>(
-      xg, xg_stride, hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd);
-  return cudaGetLastError();
+  return launch_pdl(gru_gates_kernel, dim3(grid_for(static_cast<long long>(B) * Hd)), dim3(kThreads), 0, s, xg, xg_stride,
+                    hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd);
 }
 
 cudaError_t launch_policy_head(const float* logits, long long logit_stride, int A, int grid_n, int rows, int H,
                                int P, int32_t* action_idx, float* action_yx, int32_t* yx, cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
-  policy_head_kernel<<<grid_for(static_cast<long long>(rows) * 32), kThreads, 0, s>>>(
-      logits, logit_stride, A, grid_n, rows, H, P, action_idx, action_yx, yx);
-  return cudaGetLastError();
+  return launch_pdl(policy_head_kernel, dim3(grid_for(static_cast<long long>(rows) * 32)), dim3(kThreads), 0, s, logits,
+                    logit_stride, A, grid_n, rows, H, P, action_idx, action_yx, yx);
 }
 
 cudaError_t launch_policy_head_continuous(const float* logits, long long logit_stride, int rows, int H, int P,
                                           float* action_yx, int32_t* yx, cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
-  policy_head_continuous_kernel<<<grid_for(2LL * rows), kThreads, 0, s>>>(logits, logit_stride, rows, H, P,
+  return launch_pdl(policy_head_continuous_kernel, dim3(grid_for(2LL * rows)), dim3(kThreads), 0, s, logits, logit_stride, rows, H, P,
                                                                         action_yx, yx);
   return cudaGetLastError();
 }
@@ -713,7 +751,7 @@ cudaError_t launch_tsm_shift(const __half* in, __half* out, int NT, int T, int H
                              cudaStream_t s) {
   if (NT <= 0) return cudaSuccess;
   const long long total = static_cast<long long>(NT) * HW * (C / 8);
-  tsm_shift_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, NT, T, HW, C, fold);
+  return launch_pdl<false>(tsm_shift_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out, NT, T, HW, C, fold);
   return cudaGetLastError();
 }
 
@@ -728,18 +766,18 @@ cudaError_t launch_tsm_shift_nchw_f32(const float* in, float* out, int NT, int T
 cudaError_t launch_consensus_avg(const float* in, const float* add, float* out, int B, int T, int C,
                                  cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
-  consensus_avg_kernel<<<grid_for(static_cast<long long>(B) * C), kThreads, 0, s>>>(in, add, out, B, T, C);
-  return cudaGetLastError();
+  return launch_pdl(consensus_avg_kernel, dim3(grid_for(static_cast<long long>(B) * C)), dim3(kThreads), 0, s, in, add, out,
+                    B, T, C);
 }
 
 cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  fill_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(p, v, n);
+  return launch_pdl(fill_f32_kernel, dim3(grid_for(n)), dim3(kThreads), 0, s, p, v, n);
   return cudaGetLastError();
 }
 cudaError_t launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  f32_to_f16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, out, n);
+  return launch_pdl(f32_to_f16_kernel, dim3(grid_for(n)), dim3(kThreads), 0, s, in, out, n);
   return cudaGetLastError();
 }
 
