@@ -65,7 +65,20 @@ class PatchSampler(nn.Module):
         return get_patch(imgs, action, self.size)
 
     def random_sample(self, imgs):
-        raise NotImplementedError("random patch sampling (numpy host RNG) is outside the inference hot path")
+        """Crop at uniformly random positions -- ACT/models/gfv_net.py:376-381 with ACT/models/utils.py:24-35: per
+        image y then x from np.random.randint(0, size_range) on the HOST generator (same draw order as the reference),
+        then one gather kernel instead of per-image slicing + torch.stack."""
+        import numpy as np
+        n, c, h, w = imgs.shape
+        if self.size == h:
+            return imgs
+        yx = np.empty((n, 2), dtype=np.int32)
+        for i in range(n):
+            yx[i, 0] = np.random.randint(0, h - self.size)
+            yx[i, 1] = np.random.randint(0, w - self.size)
+        from ..engine import get_engine
+        eng = get_engine(imgs.device)
+        return eng.crop(imgs.contiguous(), yx=torch.from_numpy(yx).to(imgs.device), patch=self.size)
 
     def forward(self, *argv, **kwargs):
         raise NotImplementedError
@@ -105,7 +118,9 @@ class Focuser(nn.Module):
         return self.net.get_featmap(patch, pooled=True), (None, standard_action)
 
     def random_patching(self, imgs):
-        raise NotImplementedError("random patching (stage-2 reward baseline) is not on the stage-3 inference path")
+        """Baseline feature of a random patch (stage-2 reward, ACT/models/gfv_net.py:336-338)."""
+        patch = self.patch_sampler.random_sample(imgs)
+        return self.net.get_featmap(patch, pooled=True), None
 
     def predict(self, input):
         return self.net(input)
@@ -364,7 +379,29 @@ class GFV(nn.Module):
         return fmap.view(b, t, c, fh, fw), vec.view(b, t, -1)
 
     def one_step_act(self, img, global_feat_map, global_feat, restart_batch=False, training=True):
-        raise NotImplementedError("stage-2 RL evaluation (one_step_act) is a 'next' item, see DESIGN.md")
+        """One focus step of the stage-2 (RL) validation loop -- ACT/models/gfv_net.py:160-210, driven by
+        ACT/main_dist.py:343-366: policy step + crop + fL, the reward baseline feature, and the step-wise classifier
+        (baseline through test_single_forward, which does not advance the GRU state, then single_forward)."""
+        if training:
+            raise NotImplementedError("training=True samples actions for PPO; only evaluation is implemented")
+        b = img.shape[0]
+        local_feat, pack = self.focuser(input=img, state=global_feat_map, restart_batch=restart_batch, training=False)
+        patch_size_list, action_list = pack if pack is not None else (None, None)
+        local = local_feat.view(b, -1)
+        feature = torch.cat([global_feat, local], dim=1) if self.with_glancer else local
+        feature = feature.unsqueeze(1)
+        if self.rew == "random":
+            base_local, _ = self.focuser.random_patching(img)
+            base_local = base_local.view(b, -1)
+        elif self.rew in ("padding", "prev", "conf"):
+            base_local = torch.zeros(b, self.focuser.feature_dim, device=img.device)
+        else:
+            raise NotImplementedError
+        baseline_feature = torch.cat([global_feat, base_local], dim=1) if self.with_glancer else base_local
+        baseline_feature = baseline_feature.unsqueeze(1)
+        baseline_logits, _ = self.classifier.test_single_forward(baseline_feature, reset=restart_batch)
+        logits, last_out = self.classifier.single_forward(feature, reset=restart_batch)
+        return logits, last_out, patch_size_list, action_list, baseline_logits
 
     @property
     def scale_size(self):

@@ -112,50 +112,68 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampler (the profiling recipe's clocks line); keeps only the samples taken inside the timed region."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+
+    def region_begin(self):
+        self.t0 = time.time()
+
+    def region_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], None, set()
+        import datetime
+        sm_in, sm_all, mx, reasons, power = [], [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk = float(parts[1])
+                mx = float(parts[2])
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        # under load = the upper half of the samples (the sampler also sees the idle edges of the region)
-        med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            sm_all.append(clk)
+            inside = self.t0 is not None and self.t0 - 0.03 <= ts <= self.t1 + 0.03
+            if inside:
+                sm_in.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
+                for nm, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        use = sorted(sm_in) if sm_in else sorted(sm_all)
+        med = use[len(use) // 2] if use else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm_in),
+                "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -206,20 +224,24 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, a.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {}
     barrier()
+    if sampler:
+        sampler.region_begin()
     ev0.record()
     for _ in range(a.steps):
         step()
     ev1.record()
     barrier()
+    if sampler:
+        sampler.region_end()
     clocks = sampler.stop() if sampler else None
     ms_total = ev0.elapsed_time(ev1)
     stage_acc = plan.stage_ms()            # stages of the last timed step, from CUDA-event marks inside the plan
@@ -264,12 +286,33 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
+    # ---- crop / gather roofline (get_patch as one HBM-bound kernel, ACT/models/utils.py:37-51), measured live
+    from adafocus_b200.engine import get_engine
+    eng = get_engine(dev)
+    frames = inp.view(b * t, 3, s, s)
+    acts = torch.rand(b * t, 2, device=dev, generator=gen)
+    patches = torch.empty(b * t, 3, args.patch_size, args.patch_size, device=dev)
+    for _ in range(3):
+        eng.crop(frames, action=acts, patch=args.patch_size, out=patches)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    c0.record()
+    for _ in range(reps):
+        eng.crop(frames, action=acts, patch=args.patch_size, out=patches)
+    c1.record()
+    torch.cuda.synchronize()
+    crop_ms = c0.elapsed_time(c1) / reps
+    crop_bytes = b * t * 2 * 3 * args.patch_size * args.patch_size * 4
+
     tf_peak, hbm_peak, peak_src = measured_peaks()
     fl_ms = stage_acc["fL"]
     fl_tflops = b * t * FL_GFLOP_PER_PATCH * 1e9 / (fl_ms * 1e-3) / 1e12
     roofline = {
         "bound": "tensor", "achieved": fl_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": fl_tflops / tf_peak,
-        "traffic": None, "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM), all fL launches of one step",
+        # dram__bytes_read.sum + dram__bytes_write.sum over the 53 fL conv launches of one step at 64 clips/GPU
+        # (profiles/r1_v5_stage_dram_summary.json); scaled linearly with the number of patches
+        "traffic": 17.177e9 * (b * t) / 1024.0,
+        "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM), all fL launches of one step",
         "how": f"{b * t} patches x {FL_GFLOP_PER_PATCH} GFLOP (ResNet-50 trunk @128^2) / fL stage time {fl_ms:.3f} ms "
                f"measured by CUDA-event marks inside the timed plan replay (includes stem staging, maxpool, avgpool); "
                f"peak = sustained bf16/fp16 dense, {peak_src}",
@@ -283,6 +326,11 @@ def run_ours(a):
                    "l2": f"per-step input {b * 3 * t * s * s * 4 / 2**20:.0f} MiB/GPU exceeds the 126 MB L2; no flush"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": plan.plan.num_launches * a.steps,
         "roofline": roofline, "stages_ms": stage_acc,
+        "crop_roofline": {"bound": "hbm", "achieved": crop_bytes / (crop_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": crop_bytes / (crop_ms * 1e-3) / 1e9 / hbm_peak,
+                          "kernel": "crop_nchw_f32_vec4_kernel (get_patch, fp32 -> fp32)",
+                          "how": f"{b * t} patches x 393216 B (read + write) / {crop_ms * 1e3:.1f} us (CUDA events, "
+                                 f"{reps} launches, source frames {b * 3 * t * s * s * 4 / 2**20:.0f} MiB > L2)"},
         "model_tflops": value * TOTAL_GFLOP_PER_CLIP / 1e3 / world,
     }
     if world == 1 and not a.no_cpu_baseline:

@@ -102,6 +102,34 @@ def run_reference(ref, args, batch, tag):
     return model
 
 
+def run_reference_stage2(ref, args, batch, tag, np_seed=7):
+    """The stage-2 (RL) validation loop of ACT/main_dist.py:343-366: glance, then one_step_act per step; the reward
+    baseline crops come from the numpy host generator."""
+    torch.manual_seed(0)
+    model = ref.GFV(args)
+    ck = synth.synth_checkpoint_act(model, synth.SEED)
+    synth.load_checkpoint_act(model, ck)
+    model.eval()
+    x = synth.synth_clips(batch, args.num_segments, args.input_size, synth.SEED)
+    images = x.view(batch, args.num_segments, 3, args.input_size, args.input_size)
+    np.random.seed(np_seed)
+    preds, bases, acts = [], [], []
+    with torch.no_grad():
+        fmap, gvec = model.glance(x)
+        for t in range(args.num_segments):
+            out, pred, _, action, base = model.one_step_act(images[:, t], fmap[:, t], gvec[:, t], restart_batch=(t == 0),
+                                                            training=False)
+            preds.append(pred.clone())
+            bases.append(base.clone())
+            acts.append(action.clone())
+    out = {"pred": torch.stack(preds, 0).numpy().astype(np.float32),          # (T, B, C)
+           "baseline_logits": torch.stack(bases, 0).numpy().astype(np.float32),
+           "std_actions": torch.stack(acts, 0).numpy().astype(np.float32), "np_seed": np.array(np_seed)}
+    path = os.path.join(HERE, f"act_stage2_{tag}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 def get_patch_kat(ref):
     """Known-answer table for get_patch straight from the reference function (ACT/models/utils.py:37-51)."""
     from models.utils import get_patch
@@ -130,7 +158,13 @@ def get_patch_kat(ref):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref = import_reference_act()
+    if "--stage2-only" in sys.argv:
+        run_reference_stage2(ref, synth.act_args(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3,
+                             "t4_p96_b3")
+        sys.exit(0)
     get_patch_kat(ref)
+    run_reference_stage2(ref, synth.act_args(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3,
+                         "t4_p96_b3")
     # config 3 shape: T=16, P=128, 49 actions, 200 classes; 2 clips
     model = run_reference(ref, synth.act_args(), 2, "c3_b2")
     import json

@@ -186,3 +186,25 @@ def test_full_size_properties():
     y0, x0 = yx[i].tolist()
     assert torch.equal(patches[i], frames[i, :, y0:y0 + 128, x0:x0 + 128])
     assert int(yx.min()) >= 0 and int(yx.max()) <= 96
+
+
+def test_stage2_one_step_act_vs_reference_golden(golden_dir):
+    """ACT stage-2 (RL) validation loop, driven like ACT/main_dist.py:343-366: glance + one_step_act per step with the
+    random-patch reward baseline (numpy host RNG, same seed as the golden run)."""
+    gold = np.load(os.path.join(golden_dir, "act_stage2_t4_p96_b3.npz"))
+    over = dict(num_segments=4, patch_size=96, action_dim=36, num_classes=51)
+    args, model, ck, x = _model(over, 3)
+    xd = x.to(DEV)
+    images = xd.view(3, 4, 3, 224, 224)
+    np.random.seed(int(gold["np_seed"]))
+    with torch.no_grad():
+        fmap, gvec = model.glance(xd)
+        for t in range(4):
+            out, pred, _, action, base = model.one_step_act(images[:, t].contiguous(), fmap[:, t].contiguous(),
+                                                            gvec[:, t].contiguous(), restart_batch=(t == 0),
+                                                            training=False)
+            assert out.shape == (3, 51) and pred.shape == (3, 51) and base.shape == (3, 51)
+            assert np.array_equal(action.cpu().numpy(), gold["std_actions"][t])
+            scale = max(1.0, float(np.abs(gold["pred"][t]).max()))
+            assert np.abs(pred.cpu().numpy() - gold["pred"][t]).max() <= 5e-3 * scale
+            assert np.abs(base.cpu().numpy() - gold["baseline_logits"][t]).max() <= 5e-3 * scale
