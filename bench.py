@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
+                    help="cfg3 = the headline ACT configuration (default); cfg5 = Something-Something shape, "
+                         "TSM-MobileNet-V2 (8 frames) + TSM-ResNet-101 (12 frames, 144^2 patches), extra line only")
     return ap.parse_args()
 
 
@@ -344,9 +347,56 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_cfg5(a):
+    """Secondary workload (BASELINE config 5 shape on one GPU): STH tree, T_g=8, T_f=12, P=144, ResNet-101 fL, C=174,
+    fused forward_eval plan, device-resident inputs.  Not the headline metric; prints its own JSON line."""
+    import torch
+    from adafocus_b200 import synth
+    from adafocus_b200.models_sth.gfv_net import GFV
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    args = synth.sth_args(base_model="resnet101", batch_size=a.batch)
+    model = GFV(args).to(dev)
+    synth.strip_fc_sth(model)
+    synth.load_checkpoint_sth(model, synth.synth_checkpoint_sth(model))
+    model.focuser.policy.policy.to(dev).eval()
+    model.focuser.policy.policy_old.to(dev).eval()
+    model.eval()
+    b = a.batch
+    plan = model.eval_plan(args, b, dev)
+    gen = torch.Generator(device=dev).manual_seed(synth.SEED)
+    plan.glancer_images.copy_(torch.randn(plan.glancer_images.shape, generator=gen, device=dev))
+    plan.focuser_images.copy_(torch.randn(plan.focuser_images.shape, generator=gen, device=dev))
+    for _ in range(max(3, a.warmup)):
+        plan.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        plan.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    stages = plan.stage_ms()
+    gflop_clip = 8 * 0.599 + 12 * 6.583          # SURVEY.md section 8(d)
+    print(json.dumps({
+        "metric": "videos/sec (Sth-Sth shape, 8+12 frames, 144^2 patch, ResNet-101 fL)", "value": b / (ms * 1e-3),
+        "unit": "videos/s", "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "cfg5 shape on 1 GPU: STH tree forward_eval (pred only)", "videos_per_step": b},
+        "stages_ms": stages, "gpu_launches": plan.plan.num_launches * a.steps,
+        "model_tflops": b / (ms * 1e-3) * gflop_clip / 1e3,
+        "roofline": {"bound": "tensor", "achieved": b * 12 * 6.583e9 / (stages["fL"] * 1e-3) / 1e12,
+                     "peak": measured_peaks()[0], "unit": "TFLOP/s",
+                     "frac": b * 12 * 6.583e9 / (stages["fL"] * 1e-3) / 1e12 / measured_peaks()[0], "traffic": None},
+    }), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "cfg5":
+        run_cfg5(a)
     else:
         run_ours(a)
