@@ -139,3 +139,39 @@ def test_sth_parameter_names_match_reference(golden_dir):
     shifted = [k for k in m101.focuser.state_dict() if k.endswith("conv1.net.weight")]
     assert len(shifted) == 2 + 2 + 12 + 2
     assert m.eval() is None
+
+
+def test_checkpoint_ingest_formats(tmp_path):
+    """Reference checkpoint formats round-trip through adafocus_b200.checkpoint (ACT resume dict; STH resume dict;
+    TSM 'module.base_model.' / 'module.new_fc.' pretrained backbones)."""
+    from adafocus_b200 import checkpoint, synth
+    from adafocus_b200.models.gfv_net import GFV
+    from adafocus_b200.models_sth.gfv_net import GFV as GFV_STH
+    m = GFV(synth.act_args(num_segments=2, num_classes=10))
+    ck = synth.synth_checkpoint_act(m, seed=3)
+    path = tmp_path / "act.pth.tar"
+    checkpoint.save_checkpoint(ck, path)
+    assert not os.path.exists(str(path) + ".tmp")
+    info = checkpoint.load_act_checkpoint(m, str(path))
+    assert info["epoch"] == 0
+    assert torch.equal(m.classifier.fc.weight, ck["fc"]["fc.weight"])
+    assert torch.equal(m.focuser.policy.policy_old.actor[0].weight, ck["policy"]["actor.0.weight"])
+
+    s = GFV_STH(synth.sth_args(num_classes=16))
+    # a TSM-style training checkpoint of the backbones: DataParallel 'module.' prefix, 'new_fc' heads
+    g_sd = {"module.base_model." + k: v.clone() + 1 for k, v in s.glancer.net.state_dict().items()
+            if not k.startswith("classifier.")}
+    g_sd["module.new_fc.weight"] = torch.full_like(s.glancer.net.classifier.weight, 0.5)
+    g_sd["module.new_fc.bias"] = torch.zeros_like(s.glancer.net.classifier.bias)
+    f_sd = {"module." + k: v.clone() + 2 for k, v in s.focuser.net.state_dict().items()}
+    f_sd["module.new_fc.weight"] = torch.full_like(s.classifier.weight, 0.25)
+    f_sd["module.new_fc.bias"] = torch.ones_like(s.classifier.bias)
+    before = s.focuser.net.base_model.conv1.weight.clone()
+    checkpoint.load_sth_pretrained(s, {"state_dict": g_sd}, {"state_dict": f_sd})
+    assert float(s.glancer.net.classifier.weight.mean()) == 0.5
+    assert float(s.classifier.weight.mean()) == 0.25 and float(s.classifier.bias.mean()) == 1.0
+    assert torch.equal(s.focuser.net.base_model.conv1.weight, before + 2)
+    synth.strip_fc_sth(s)
+    ck_s = synth.synth_checkpoint_sth(s, seed=5)
+    checkpoint.load_sth_checkpoint(s, ck_s)
+    assert torch.equal(s.classifier.weight, ck_s["fc"]["weight"])
