@@ -397,6 +397,22 @@ int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* h
   });
 }
 
+int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const float* b_hh, const float* h0, float* hbuf,
+                    void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter, int B, int T, int Hd,
+                    void* stream) {
+  if (ctx == nullptr || xg == nullptr || w_hh_f16 == nullptr || b_hh == nullptr || hbuf == nullptr ||
+      hseq_f16 == nullptr || counter == nullptr)
+    return fail(AF_ERR_INVALID, "af_gru_sequence: null argument");
+  if (Hd % 256 != 0 || Hd > 1024 || Hd / 8 > ctx->sm_count)
+    return fail(AF_ERR_INVALID, "af_gru_sequence: hidden size must be a multiple of 256, <= 1024 and <= 8 * SM count");
+  const __half* w = static_cast<const __half*>(w_hh_f16);
+  __half* hs = static_cast<__half*>(hseq_f16);
+  const int sms = ctx->sm_count;
+  return dispatch(ctx, stream, "af_gru_sequence", [=](cudaStream_t s) {
+    return af::launch_gru_sequence(xg, w, b_hh, h0, hbuf, hs, hseq_stride, h_out, counter, B, T, Hd, sms, s);
+  });
+}
+
 int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,
                    int32_t* action_idx, float* action_yx, int32_t* yx, void* stream) {
   if (logits == nullptr || A < 1 || grid_n < 2 || grid_n * grid_n != A || P > H)

@@ -495,6 +495,128 @@ gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float*
   if (hseq_f32 != nullptr) hseq_f32[static_cast<long long>(b) * hseq_f32_stride + j] = hn;
 }
 
+// ------------------------------------------------------------------------------------------------ GRU sequence
+// Persistent recurrent kernel for small batches: all T steps of a GRU in ONE launch.  CTA c owns hidden units
+// [c*JB, (c+1)*JB): its 3*JB rows of W_hh (fp16) stay in shared memory for the whole sequence.  Per step a warp takes
+// a batch row, holds h_{t-1} (fp32) in registers, forms the 3*JB dot products with warp-shuffle reductions, lanes
+// 0..JB-1 apply the gate math (torch.nn.GRU, gates r,z,n) and publish h_t; a grid-wide barrier (atomic counter,
+// all CTAs co-resident: cooperative launch) separates the steps, so the T-step loop never leaves the device.
+constexpr int kGruJB = 8;
+constexpr int kGruMaxK = 4;   // hidden size <= 1024: h row cached as 4 x 8 floats per lane
+
+__device__ __forceinline__ void gru_grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gru_sequence_kernel(const float* __restrict__ xg, const __half* __restrict__ w_hh, const float* __restrict__ b_hh,
+                    const float* __restrict__ h0, float* __restrict__ hbuf, __half* __restrict__ hseq_f16,
+                    long long hseq_stride, float* __restrict__ h_out, unsigned int* __restrict__ counter, int B, int T,
+                    int Hd) {
+  extern __shared__ __align__(16) uint8_t gru_smem[];
+  __half* s_w = reinterpret_cast<__half*>(gru_smem);                                   // [3][JB][Hd]
+  float* s_b = reinterpret_cast<float*>(gru_smem + sizeof(__half) * 3 * kGruJB * Hd);  // [3][JB]
+  const int unit0 = blockIdx.x * kGruJB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int chunks = Hd >> 3;   // 16-byte chunks per row
+  for (int i = threadIdx.x; i < 3 * kGruJB * chunks; i += blockDim.x) {
+    const int row = i / chunks, ch = i - row * chunks;
+    const int g = row / kGruJB, j = row - g * kGruJB;
+    reinterpret_cast<uint4*>(s_w)[i] =
+        __ldg(reinterpret_cast<const uint4*>(w_hh + (static_cast<long long>(g) * Hd + unit0 + j) * Hd) + ch);
+  }
+  if (threadIdx.x < 3 * kGruJB) {
+    const int g = threadIdx.x / kGruJB, j = threadIdx.x - g * kGruJB;
+    s_b[threadIdx.x] = b_hh[g * Hd + unit0 + j];
+  }
+  // h_{-1}: every CTA initialises its own slice of buffer 0, then the grid synchronises
+  for (int i = threadIdx.x; i < B * kGruJB; i += blockDim.x) {
+    const int b = i / kGruJB, j = i - b * kGruJB;
+    hbuf[static_cast<long long>(b) * Hd + unit0 + j] = h0 ? h0[static_cast<long long>(b) * Hd + unit0 + j] : 0.f;
+  }
+  unsigned int epoch = 1;
+  gru_grid_barrier(counter, epoch * gridDim.x);
+  const int kper = Hd >> 8;   // 8-element groups per lane (Hd / 256)
+  for (int t = 0; t < T; ++t) {
+    const float* hprev = hbuf + static_cast<long long>(t & 1) * B * Hd;
+    float* hnext = hbuf + static_cast<long long>((t + 1) & 1) * B * Hd;
+    for (int b = warp; b < B; b += nwarps) {
+      const float* hb = hprev + static_cast<long long>(b) * Hd;
+      // h_{t-1} of this batch row, 8 consecutive elements per (lane, i); L2-coherent loads (ld.global.cg): the row
+      // was written by other CTAs during this launch and must not be served from a stale L1 line
+      float hv[kGruMaxK][8];
+#pragma unroll
+      for (int i = 0; i < kGruMaxK; ++i) {
+        if (i < kper) {
+          const int k = (i * 32 + lane) * 8;
+          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(hb + k));
+          const float4 a1 = __ldcg(reinterpret_cast<const float4*>(hb + k + 4));
+          hv[i][0] = a0.x; hv[i][1] = a0.y; hv[i][2] = a0.z; hv[i][3] = a0.w;
+          hv[i][4] = a1.x; hv[i][5] = a1.y; hv[i][6] = a1.z; hv[i][7] = a1.w;
+        }
+      }
+      float my_r = 0.f, my_z = 0.f, my_n = 0.f;
+      for (int j = 0; j < kGruJB; ++j) {
+        float ar = 0.f, az = 0.f, an = 0.f;
+#pragma unroll
+        for (int i = 0; i < kGruMaxK; ++i) {
+          if (i < kper) {
+            const int k = (i * 32 + lane) * 8;
+            const uint4 wr = *reinterpret_cast<const uint4*>(s_w + (0 * kGruJB + j) * Hd + k);
+            const uint4 wz = *reinterpret_cast<const uint4*>(s_w + (1 * kGruJB + j) * Hd + k);
+            const uint4 wn = *reinterpret_cast<const uint4*>(s_w + (2 * kGruJB + j) * Hd + k);
+            const __half2* pr = reinterpret_cast<const __half2*>(&wr);
+            const __half2* pz = reinterpret_cast<const __half2*>(&wz);
+            const __half2* pn = reinterpret_cast<const __half2*>(&wn);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fr = __half22float2(pr[q]), fz = __half22float2(pz[q]), fn = __half22float2(pn[q]);
+              ar = fmaf(fr.x, hv[i][2 * q], ar);
+              ar = fmaf(fr.y, hv[i][2 * q + 1], ar);
+              az = fmaf(fz.x, hv[i][2 * q], az);
+              az = fmaf(fz.y, hv[i][2 * q + 1], az);
+              an = fmaf(fn.x, hv[i][2 * q], an);
+              an = fmaf(fn.y, hv[i][2 * q + 1], an);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ar += __shfl_xor_sync(0xffffffffu, ar, o);
+          az += __shfl_xor_sync(0xffffffffu, az, o);
+          an += __shfl_xor_sync(0xffffffffu, an, o);
+        }
+        if (lane == j) {
+          my_r = ar;
+          my_z = az;
+          my_n = an;
+        }
+      }
+      if (lane < kGruJB) {
+        const int unit = unit0 + lane;
+        const float* x = xg + (static_cast<long long>(b) * T + t) * 3 * Hd;
+        const float r = sigmoidf_(x[unit] + my_r + s_b[lane]);
+        const float z = sigmoidf_(x[Hd + unit] + my_z + s_b[kGruJB + lane]);
+        const float nn = tanhf(x[2 * Hd + unit] + r * (my_n + s_b[2 * kGruJB + lane]));
+        const float hn = (1.f - z) * nn + z * __ldcg(hb + unit);
+        hnext[static_cast<long long>(b) * Hd + unit] = hn;
+        hseq_f16[(static_cast<long long>(b) * T + t) * hseq_stride + unit] = __float2half_rn(hn);
+        if (t == T - 1 && h_out != nullptr) h_out[static_cast<long long>(b) * Hd + unit] = hn;
+      }
+    }
+    ++epoch;
+    gru_grid_barrier(counter, epoch * gridDim.x);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ policy heads
 __global__ void __launch_bounds__(kThreads)
 policy_head_kernel(const float* __restrict__ logits, long long logit_stride, int A, int grid_n, int rows, int H,
@@ -730,6 +852,35 @@ cudaError_t launch_gru_gates(const float* xg, long long xg_stride, const float* 
   if (B <= 0) return cudaSuccess;
   return launch_pdl(gru_gates_kernel, dim3(grid_for(static_cast<long long>(B) * Hd)), dim3(kThreads), 0, s, xg, xg_stride,
                     hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd);
+}
+
+cudaError_t launch_gru_sequence(const float* xg, const __half* w_hh, const float* b_hh, const float* h0, float* hbuf,
+                                __half* hseq_f16, long long hseq_stride, float* h_out, unsigned int* counter, int B,
+                                int T, int Hd, int sm_count, cudaStream_t s) {
+  if (B <= 0 || T <= 0) return cudaSuccess;
+  if (Hd % 256 != 0 || Hd / kGruJB > sm_count || Hd > 256 * kGruMaxK) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(__half) * 3 * kGruJB * Hd + sizeof(float) * 3 * kGruJB;
+  static bool attr_done = false;
+  if (!attr_done && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gru_sequence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(Hd / kGruJB);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // guarantees co-residency of all CTAs (grid barrier)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gru_sequence_kernel, xg, w_hh, b_hh, h0, hbuf, hseq_f16, hseq_stride, h_out, counter,
+                            B, T, Hd);
 }
 
 cudaError_t launch_policy_head(const float* logits, long long logit_stride, int A, int grid_n, int rows, int H,

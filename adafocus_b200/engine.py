@@ -337,6 +337,25 @@ class Engine:
         self._count()
         self.keep(xg, hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_f32)
 
+    GRU_SEQ_MAX_BATCH = 8    # measured crossover: from 16 clips on the per-step tcgen05 GEMM path is as fast or faster
+
+    def can_gru_sequence(self, b, hd):
+        return b <= self.GRU_SEQ_MAX_BATCH and hd % 256 == 0 and hd <= 1024 and hd // 8 <= self.ctx.sm_count
+
+    def gru_sequence(self, xg, pc_hh, b, t, hseq16, h0=None, h_out=None):
+        """All T steps of a GRU in one persistent launch. xg (B*T,3H) fp32, pc_hh = PackedConv of W_hh (+ b_hh)."""
+        hd = pc_hh.cin
+        assert pc_hh.w.shape == (3 * hd, hd) and xg.shape == (b * t, 3 * hd)
+        hbuf = self.empty((2, b, hd), torch.float32)
+        counter = self.empty((1,), torch.int32)
+        check(self.lib.af_gru_sequence(self.h, _ptr(xg), _ptr(pc_hh.w), _ptr(pc_hh.bias), _ptr(h0), _ptr(hbuf),
+                                       _ptr(hseq16), hseq16.stride(0), _ptr(h_out), _ptr(counter), b, t, hd,
+                                       self._stream()), "af_gru_sequence")
+        self._count()
+        self.keep(xg, pc_hh.w, pc_hh.bias, h0, hbuf, hseq16, h_out, counter)
+        self.release(hbuf)
+        self.release(counter)
+
     def policy_head(self, logits, action_dim, h, patch, action_idx=None, action_yx=None, yx=None):
         rows = logits.shape[0]
         grid_n = int(round(math.sqrt(action_dim)))

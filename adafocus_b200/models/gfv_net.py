@@ -158,6 +158,14 @@ class GRUHeadRunner:
         """feat16 (B*T, F) fp16 rows b*T+t -> logits fp32 (B*T, logit_stride)."""
         hd = self.hidden
         xg = eng.linear(feat16, self.gru_ih, out_f32=True)
+        if eng.can_gru_sequence(b, hd):
+            # small batch: the whole T-step recurrence is one persistent warp-reduction kernel
+            hseq16 = eng.empty((b * t, hd), torch.float16)
+            eng.gru_sequence(xg, self.gru_hh, b, t, hseq16, h0=h0, h_out=h_out)
+            eng.linear(hseq16, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
+            eng.release(xg)
+            eng.release(hseq16)
+            return
         h = eng.empty((b, hd), torch.float32) if h_out is None else h_out
         if h0 is None:
             eng.fill(h, 0.0)

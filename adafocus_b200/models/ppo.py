@@ -144,21 +144,27 @@ class PolicyRunner:
         action_idx int32 (b*t,) [discrete only], action fp32 (b*t,2))."""
         hd = self.hidden
         xg = self.encode(eng, fmap)
-        h = eng.empty((b, hd), torch.float32)
-        eng.fill(h, 0.0)
-        h16 = eng.f32_to_f16(h)
-        hg = eng.empty((b, 3 * hd), torch.float32)
         hseq16 = eng.empty((b * t, hd), torch.float16)
-        xg3 = xg.view(b, t, 3 * hd)
-        hs3 = hseq16.view(b, t, hd)
-        for step in range(t):
-            eng.linear(h16, self.gru_hh, out=hg, out_f32=True, out_stride=3 * hd)
-            eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h16, hs3[:, step], t * hd)
+        if eng.can_gru_sequence(b, hd):
+            # small batch: the whole T-step recurrence is one persistent warp-reduction kernel
+            eng.gru_sequence(xg, self.gru_hh, b, t, hseq16)
+            tmps = (xg, hseq16)
+        else:
+            h = eng.empty((b, hd), torch.float32)
+            eng.fill(h, 0.0)
+            h16 = eng.f32_to_f16(h)
+            hg = eng.empty((b, 3 * hd), torch.float32)
+            xg3 = xg.view(b, t, 3 * hd)
+            hs3 = hseq16.view(b, t, hd)
+            for step in range(t):
+                eng.linear(h16, self.gru_hh, out=hg, out_f32=True, out_stride=3 * hd)
+                eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h16, hs3[:, step], t * hd)
+            tmps = (xg, h, h16, hg, hseq16)
         yx = eng.empty((b * t, 2), torch.int32)
         idx = None if self.continuous else eng.empty((b * t,), torch.int32)
         ayx = eng.empty((b * t, 2), torch.float32)
         self.head(eng, hseq16, b * t, img_h, patch, idx, ayx, yx)
-        for tmp in (xg, h, h16, hg, hseq16):
+        for tmp in tmps:
             eng.release(tmp)
         return yx, idx, ayx
 

@@ -135,6 +135,16 @@ int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* h
                  void* h_new_f16, void* hseq_f16, int64_t hseq_stride, float* hseq_f32, int64_t hseq_f32_stride,
                  int B, int Hd, void* stream);
 
+/* A whole GRU sequence (all T steps, h0 = zeros when NULL) in ONE persistent cooperative launch, for small batches:
+ * the policy rollout of ACT/models/ppo.py:67-96 / ACT/models/gfv_net.py:110 and the classifier GRU of
+ * ACT/models/gfv_net.py:427-435 without leaving the device between steps.  xg (B*T,3H) fp32 rows b*T+t = W_ih x + b_ih;
+ * w_hh_f16 (3H,H) fp16 row-major; hbuf: 2*B*H floats scratch; counter: one uint32 scratch.  Outputs h_t as fp16 rows
+ * b*T+t of hseq_f16 (row stride hseq_stride) and optionally the final fp32 state h_out (B,H).
+ * Constraints: H % 256 == 0, H <= 1024 and H / 8 <= number of SMs. */
+int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const float* b_hh, const float* h0, float* hbuf,
+                    void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter, int B, int T, int Hd,
+                    void* stream);
+
 /* softmax -> argmax -> standard action table -> patch origin; ACT/models/ppo.py:84,94,
  * ACT/models/gfv_net.py:272-307,345-347, ACT/models/utils.py:42.  grid_n = sqrt(action_dim). */
 int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,

@@ -229,6 +229,34 @@ def test_gru_gates_vs_torch(eng):
     assert torch.equal(h16, h_new.half())
 
 
+@pytest.mark.parametrize("b,t,hd", [(1, 16, 1024), (5, 16, 1024), (8, 3, 1024), (3, 8, 512)])
+def test_gru_sequence_kernel_vs_torch(eng, b, t, hd):
+    """Persistent GRU-sequence kernel (all T steps in one launch) vs torch.nn.GRU on CPU fp32 with the same
+    fp16-rounded W_hh; hidden state stays fp32 inside the kernel -> tolerance 2e-4."""
+    from adafocus_b200.engine import pack_conv
+    torch.manual_seed(b * 100 + t)
+    gru = torch.nn.GRU(64, hd, batch_first=True)
+    with torch.no_grad():
+        gru.weight_hh_l0.copy_(gru.weight_hh_l0.half().float())
+        x = torch.randn(b, t, 64)
+        h0 = torch.randn(1, b, hd) * 0.3
+        ref, hn = gru(x, h0)
+        xg = (x.reshape(b * t, 64) @ gru.weight_ih_l0.t() + gru.bias_ih_l0).contiguous()
+    pc = pack_conv(gru.weight_hh_l0, None, gru.bias_hh_l0, device=DEV, block_n=32)
+    hseq = torch.zeros(b * t, hd, device=DEV, dtype=torch.float16)
+    h_out = torch.zeros(b, hd, device=DEV)
+    assert eng.can_gru_sequence(b, hd)
+    eng.gru_sequence(xg.to(DEV), pc, b, t, hseq, h0=h0[0].to(DEV).contiguous(), h_out=h_out)
+    torch.cuda.synchronize()
+    assert torch.allclose(h_out.cpu(), hn[0], rtol=2e-4, atol=2e-4), float((h_out.cpu() - hn[0]).abs().max())
+    assert torch.allclose(hseq.float().cpu().view(b, t, hd), ref, rtol=2e-3, atol=1e-3)
+    # zero initial state when h0 is omitted
+    eng.gru_sequence(xg.to(DEV), pc, b, t, hseq, h_out=h_out)
+    with torch.no_grad():
+        _, hn0 = gru(x)
+    assert torch.allclose(h_out.cpu(), hn0[0], rtol=2e-4, atol=2e-4)
+
+
 @pytest.mark.parametrize("a,p", [(49, 128), (25, 96), (36, 160), (64, 192), (100, 144)])
 def test_policy_head_argmax_and_coords(eng, a, p):
     from oracle import adafocus_oracle as orc

@@ -178,7 +178,9 @@ def test_full_size_properties():
     big = (big[0].clone(), big[1].clone())
     small = model(input=xd[:8].contiguous(), scan=xd[:8].contiguous(), training=False, backbone_pred=False,
                   one_step=True, gpu=0)
-    assert float((small[1] - big[1][:8]).abs().max()) <= 1e-5          # same kernels, same per-row arithmetic
+    # 8 clips take the persistent GRU kernel (fp32 recurrent state), 64 clips the per-step GEMM path (fp16 copy of the
+    # state feeds the GEMM): same algorithm, fp16-level differences only
+    assert float((small[1] - big[1][:8]).abs().max()) <= 5e-3
     assert torch.equal(small[1].argmax(1), big[1][:8].argmax(1))
     frames = xd.view(64 * 16, 3, 224, 224)
     patches = get_patch(frames, ayx, 128)
