@@ -48,6 +48,8 @@ SIGNATURES = {
     "af_action_to_yx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_int, c_void_p]),
+    "af_stem_conv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),

@@ -11,6 +11,7 @@
 #include "../../include/adafocus_b200.h"
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
+#include "stem_gemm.cuh"
 
 namespace {
 
@@ -236,6 +237,57 @@ int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_d
   return dispatch(ctx, stream, "af_stem_im2col", [=](cudaStream_t s) {
     return af::launch_stem_im2col(frames, yx, yx_div, o, N, H, W, P, KH, KW, stride, pad, Ho, Wo, Kpad, s);
   });
+}
+
+int af_stem_conv_fused(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, const void* w,
+                       const float* scale, const float* bias, void* out, int N, int H, int W, int P, int cout, int KH,
+                       int KW, int stride, int pad, int act, void* stream) {
+  if (ctx == nullptr || frames == nullptr || w == nullptr || bias == nullptr || out == nullptr)
+    return fail(AF_ERR_INVALID, "af_stem_conv_fused: null argument");
+  if (P > H || P > W || N < 1) return fail(AF_ERR_INVALID, "af_stem_conv_fused: bad geometry");
+  af::StemKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames;
+  p.yx = yx;
+  p.yx_div = yx_div < 1 ? 1 : yx_div;
+  p.N = N; p.H = H; p.W = W; p.P = P;
+  p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+  p.Ho = (P + 2 * pad - KH) / stride + 1;
+  p.Wo = (P + 2 * pad - KW) / stride + 1;
+  if (p.Ho < 1 || p.Wo < 1) return fail(AF_ERR_INVALID, "af_stem_conv_fused: empty output");
+  int tn = 1;
+  choose_tile(1, p.Ho, p.Wo, &p.TW, &p.TH, &tn);
+  if (tn != 1) return fail(AF_ERR_INVALID, "af_stem_conv_fused: output smaller than one 128-pixel tile");
+  p.tiles_w = ceil_div(p.Wo, p.TW);
+  p.tiles_h = ceil_div(p.Ho, p.TH);
+  p.KB = ceil_div(KH * KW * 3, 64);
+  p.BN = cout;
+  p.scale = scale;
+  p.bias = bias;
+  p.act = act;
+  if (!af::stem_gemm_supported(p))
+    return fail(AF_ERR_INVALID, "af_stem_conv_fused: unsupported shape (cout multiple of 16 <= 64, K <= 256)");
+  af::StemTensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  {
+    const cuuint64_t kpad = static_cast<cuuint64_t>(p.KB) * 64;
+    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(cout)};
+    const cuuint64_t strides[1] = {kpad * 2};
+    const cuuint32_t bbox[2] = {64, static_cast<cuuint32_t>(cout)};
+    if (!encode_map(ctx, &maps.b, w, 2, dims, strides, bbox, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(cout) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(p.Wo),
+                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * p.Wo, pix_b * p.Wo * p.Ho};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
+    if (!encode_map(ctx, &maps.out, out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  const int sms = ctx->sm_count;
+  return dispatch(ctx, stream, "af_stem_conv_fused",
+                  [=](cudaStream_t s) { return af::launch_stem_gemm(maps, p, sms, s); });
 }
 
 int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {

@@ -3,6 +3,7 @@ tensors.  torch is used for device memory and streams only; every compute launch
 libadafocus_b200.so.  Nothing here falls back to torch ops for the hot path."""
 import ctypes
 import math
+import os
 from ctypes import byref, c_void_p
 
 import torch
@@ -88,7 +89,8 @@ def pack_stem(weight, scale, bias, stride, pad, act, device=None, kpad=None):
     cout, cin, kh, kw = w.shape
     assert cin == 3
     kreal = kh * kw * 3
-    kpad = kpad or round_up(kreal, BLOCK_K)
+    # the im2col rows only need 16-byte granularity: the GEMM's TMA box zero-fills k beyond the row (147 -> 152, not 192)
+    kpad = kpad or round_up(kreal, 8)
     flat = torch.zeros(cout, kpad, dtype=torch.float32, device=device)
     flat[:, :kreal] = w.permute(0, 2, 3, 1).reshape(cout, kreal)
     pc = pack_conv(flat, scale, bias, 1, 0, act, device=device)
@@ -141,6 +143,7 @@ class Engine:
         self.ctx = _lib.Context(self.index)
         self.lib = self.ctx.lib
         self.h = self.ctx.handle
+        self.fused_stem = os.environ.get("AF_NO_FUSED_STEM") is None   # crop + stem conv as one implicit-GEMM kernel
         self.ws = None          # Workspace while recording
         self._keep = None
         self.launch_count = 0   # launches issued eagerly (not recorded)
@@ -237,6 +240,16 @@ class Engine:
         p = patch if patch is not None else h
         ho = (p + 2 * s["pad"] - s["kh"]) // s["stride"] + 1
         wo = (p + 2 * s["pad"] - s["kw"]) // s["stride"] + 1
+        fused_ok = (self.fused_stem and pc.cout % 16 == 0 and pc.cout <= 64 and s["kh"] * s["kw"] * 3 <= 256
+                    and ho * wo >= 128 and s["stride"] <= 2 and s["kh"] <= 7 and s["kw"] <= 7)
+        if fused_ok:
+            out = self.empty((n, ho, wo, pc.cout), torch.float16)
+            check(self.lib.af_stem_conv_fused(self.h, _ptr(frames), _ptr(yx), int(yx_div), _ptr(pc.w), _ptr(pc.scale),
+                                              _ptr(pc.bias), _ptr(out), n, h, w, p, pc.cout, s["kh"], s["kw"],
+                                              s["stride"], s["pad"], pc.act, self._stream()), "af_stem_conv_fused")
+            self._count()
+            self.keep(frames, yx, pc.w, pc.scale, pc.bias, out)
+            return out
         col = self.empty((n * ho * wo, s["kpad"]), torch.float16)
         check(self.lib.af_stem_im2col(self.h, _ptr(frames), _ptr(yx), int(yx_div), _ptr(col), n, h, w, p, s["kh"],
                                       s["kw"], s["stride"], s["pad"], s["kpad"], self._stream()), "af_stem_im2col")

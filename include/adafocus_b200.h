@@ -103,6 +103,15 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
 int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W,
                    int P, int KH, int KW, int stride, int pad, int Kpad, void* stream);
 
+/* Fused get_patch + stem convolution + BN + activation as ONE tcgen05 implicit-GEMM kernel: the patch selected by yx
+ * (ACT/models/utils.py:37-51) goes through Conv2d(3, cout, KHxKW, stride, pad) (ResNet conv1, ACT/models/resnet.py:138)
+ * without the im2col matrix ever reaching HBM -- producer warps build the swizzled A tiles in shared memory from the
+ * fp32 NCHW frames.  w: packed fp16 [cout][ceil(KH*KW*3/64)*64] with k = (r*KW+s)*3 + c (as for af_stem_im2col);
+ * out: NHWC fp16 (N, Ho, Wo, cout).  Needs cout % 16 == 0, cout <= 64, KH*KW*3 <= 256, Ho*Wo >= 128. */
+int af_stem_conv_fused(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, const void* w,
+                       const float* scale, const float* bias, void* out, int N, int H, int W, int P, int cout, int KH,
+                       int KW, int stride, int pad, int act, void* stream);
+
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
  * w27 fp32 [27][32] with k = (r*3+s)*3 + c; scale / bias fp32 [32]. */

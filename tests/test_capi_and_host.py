@@ -61,7 +61,7 @@ def test_pack_conv_layout():
     assert float(pc.w[2:].abs().max()) == 0 and float(pc.w[:, 8:64].abs().max()) == 0
     assert pc.scale[:2].tolist() == [2.0, 3.0] and pc.scale[2:].eq(1).all() and pc.bias[:2].tolist() == [0.5, -0.5]
     ps = pack_stem(w, None, None, stride=2, pad=1, act=2, device="cpu")
-    assert ps.w.shape == (16, 64) and ps.stem["kpad"] == 64
+    assert ps.w.shape == (16, 64) and ps.stem["kpad"] == 32
     assert float(ps.w[1, (1 * 3 + 2) * 3 + 1]) == float(w[1, 1, 1, 2])
     lin = torch.randn(5, 12)
     perm = torch.arange(12).flip(0)
