@@ -210,3 +210,27 @@ def test_stage2_one_step_act_vs_reference_golden(golden_dir):
             scale = max(1.0, float(np.abs(gold["pred"][t]).max()))
             assert np.abs(pred.cpu().numpy() - gold["pred"][t]).max() <= 5e-3 * scale
             assert np.abs(base.cpu().numpy() - gold["baseline_logits"][t]).max() <= 5e-3 * scale
+
+
+@pytest.mark.parametrize("over,batch", [
+    (dict(num_segments=3, patch_size=160, action_dim=25, num_classes=24), 1),                    # one clip, big patch
+    (dict(num_segments=2, patch_size=192, action_dim=64, num_classes=16, with_glancer=False), 2),  # local features only
+    (dict(num_segments=2, patch_size=96, action_dim=49, num_classes=8, glance_size=128), 2),       # down-sampled glance
+])
+def test_other_configurations_vs_oracle(over, batch):
+    """Shapes beyond cfg3: other patch sizes / action grids, with_glancer=False, glance_size != input_size (the caller
+    resizes with nearest interpolation like ACT/main_dist.py:332)."""
+    from oracle import adafocus_oracle as orc
+    args, model, ck, x = _model(over, batch)
+    scan = torch.nn.functional.interpolate(x, (args.glance_size, args.glance_size))
+    ref = orc.act_forward(x, scan, ck, args.patch_size, args.action_dim, with_glancer=args.with_glancer)
+    xd, sd = x.to(DEV), scan.to(DEV)
+    logits, last = model(input=xd, scan=sd if args.glance_size != args.input_size else xd, training=False,
+                         backbone_pred=False, one_step=True, gpu=0)
+    plan = model.last_plan
+    t = args.num_segments
+    assert torch.equal(plan.action_idx.view(batch, t).cpu().long(), ref["actions"])
+    assert np.array_equal(plan.yx.view(batch, t, 2).cpu().numpy(), ref["coords"])
+    scale = max(1.0, float(ref["logits"].abs().max()))
+    assert float((logits.cpu() - ref["logits"]).abs().max()) <= 5e-3 * scale
+    assert torch.equal(last.argmax(1).cpu(), ref["last_out"].argmax(1))
