@@ -35,6 +35,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 struct af_plan {
+  int device = 0;
   std::vector<Launch> launches;
   std::vector<cudaEvent_t> marks;
   int kernel_launches = 0;
@@ -53,6 +54,19 @@ struct af_ctx {
 
 namespace {
 
+// Launches always go to the context's device, whatever the caller's current device is (restored on exit).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) cudaSetDevice(device);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
   if (ctx == nullptr) return fail(AF_ERR_INVALID, std::string(name) + ": null ctx");
   if (ctx->recording) {
@@ -60,6 +74,7 @@ int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
     ctx->current->kernel_launches += 1;
     return AF_OK;
   }
+  DeviceGuard guard(ctx->device);
   cudaError_t e = fn(static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, name);
   return AF_OK;
@@ -153,6 +168,7 @@ int af_plan_begin(af_ctx* ctx) {
   if (ctx == nullptr) return fail(AF_ERR_INVALID, "af_plan_begin: null ctx");
   if (ctx->recording) return fail(AF_ERR_STATE, "af_plan_begin: already recording");
   ctx->current = new af_plan();
+  ctx->current->device = ctx->device;
   ctx->recording = true;
   return AF_OK;
 }
@@ -169,6 +185,7 @@ int af_plan_end(af_ctx* ctx, af_plan** out) {
 int af_plan_run(af_plan* plan, void* stream) {
   if (plan == nullptr) return fail(AF_ERR_INVALID, "af_plan_run: null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DeviceGuard guard(plan->device);
   for (size_t i = 0; i < plan->launches.size(); ++i) {
     cudaError_t e = plan->launches[i](s);
     if (e != cudaSuccess) {
@@ -184,6 +201,7 @@ int af_plan_num_launches(const af_plan* plan) { return plan ? plan->kernel_launc
 
 int af_plan_mark(af_ctx* ctx, int* mark_index) {
   if (ctx == nullptr || !ctx->recording) return fail(AF_ERR_STATE, "af_plan_mark: only valid while recording");
+  DeviceGuard guard(ctx->device);
   cudaEvent_t ev;
   cudaError_t e = cudaEventCreate(&ev);
   if (e != cudaSuccess) return fail_cuda(e, "af_plan_mark: cudaEventCreate");
@@ -504,6 +522,29 @@ int af_consensus_avg(af_ctx* ctx, const float* in, const float* add, float* out,
   if (in == nullptr || out == nullptr || T < 1) return fail(AF_ERR_INVALID, "af_consensus_avg: bad argument");
   return dispatch(ctx, stream, "af_consensus_avg",
                   [=](cudaStream_t s) { return af::launch_consensus_avg(in, add, out, B, T, C, s); });
+}
+
+int af_topk_hits(af_ctx* ctx, const float* logits, int64_t stride, const int64_t* target, int rows, int C, int k0,
+                 int k1, float* hits, void* stream) {
+  if (logits == nullptr || target == nullptr || hits == nullptr || C < 1)
+    return fail(AF_ERR_INVALID, "af_topk_hits: bad argument");
+  const long long* t = reinterpret_cast<const long long*>(target);
+  return dispatch(ctx, stream, "af_topk_hits",
+                  [=](cudaStream_t s) { return af::launch_topk_hits(logits, stride, t, rows, C, k0, k1, hits, s); });
+}
+
+int af_softmax_rows(af_ctx* ctx, const float* logits, int64_t stride, float* probs, int rows, int C, void* stream) {
+  if (logits == nullptr || probs == nullptr || C < 1) return fail(AF_ERR_INVALID, "af_softmax_rows: bad argument");
+  return dispatch(ctx, stream, "af_softmax_rows",
+                  [=](cudaStream_t s) { return af::launch_softmax_rows(logits, stride, probs, rows, C, s); });
+}
+
+int af_class_ap(af_ctx* ctx, const float* probs, const int64_t* labels, int N, int C, int L, float* ap, void* stream) {
+  if (probs == nullptr || labels == nullptr || ap == nullptr || N < 0 || C < 1 || L < 1)
+    return fail(AF_ERR_INVALID, "af_class_ap: bad argument");
+  const long long* l = reinterpret_cast<const long long*>(labels);
+  return dispatch(ctx, stream, "af_class_ap",
+                  [=](cudaStream_t s) { return af::launch_class_ap(probs, l, N, C, L, ap, s); });
 }
 
 int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream) {

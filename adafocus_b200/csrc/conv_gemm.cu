@@ -443,12 +443,15 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   p.epi_bufs = epi_bufs;
   static const int dbg = getenv("AF_CONV_DEBUG") ? atoi(getenv("AF_CONV_DEBUG")) : 0;
   p.debug_flags = dbg;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: remember which devices have been configured
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kConvSmemBudget);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   int grid = total_tiles < sm_count ? total_tiles : sm_count;

@@ -743,6 +743,91 @@ __global__ void consensus_avg_kernel(const float* __restrict__ in, const float* 
   out[i] = s;
 }
 
+// ------------------------------------------------------------------------------------------------ metrics (f-4)
+// top-k hits: rank of the target's logit inside its row (ties: lower index first), one warp per row.
+// ACT/ops/utils.py:35-49 (accuracy): hits[i] counts rows with rank < ks[i].
+__global__ void __launch_bounds__(kThreads)
+topk_hits_kernel(const float* __restrict__ logits, long long stride, const long long* __restrict__ target, int rows,
+                 int C, int k0, int k1, float* __restrict__ hits) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = logits + static_cast<long long>(warp) * stride;
+  const int t = static_cast<int>(target[warp]);
+  if (t < 0 || t >= C) return;
+  const float xt = x[t];
+  int above = 0;
+  for (int j = lane; j < C; j += 32) {
+    const float v = x[j];
+    above += (v > xt) || (v == xt && j < t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  if (lane == 0) {
+    if (above < k0) atomicAdd(hits, 1.f);
+    if (above < k1) atomicAdd(hits + 1, 1.f);
+  }
+}
+
+// row softmax (fp32), one warp per row: the probabilities cal_map ranks (ACT/ops/utils.py:76)
+__global__ void __launch_bounds__(kThreads)
+softmax_rows_kernel(const float* __restrict__ logits, long long stride, float* __restrict__ probs, int rows, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = logits + static_cast<long long>(warp) * stride;
+  float m = -INFINITY;
+  for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int j = lane; j < C; j += 32) s += expf(x[j] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int j = lane; j < C; j += 32) probs[static_cast<long long>(warp) * C + j] = expf(x[j] - m) / s;
+}
+
+// Average precision of one class per block (ACT/ops/utils.py:68-88): for every positive sample i, precision at its
+// rank = (#positives ranked at or above i) / (rank of i); ranks come from counting, not sorting (ties: lower index
+// first, i.e. a stable descending sort).  labels: (N, L) int64, -1 = no label; class k is positive for sample i if any
+// of its L labels equals k.
+__global__ void __launch_bounds__(kThreads)
+class_ap_kernel(const float* __restrict__ probs, const long long* __restrict__ labels, int N, int C, int L,
+                float* __restrict__ ap) {
+  const int k = blockIdx.x;
+  __shared__ float s_sum[kThreads];
+  __shared__ int s_cnt[kThreads];
+  float sum = 0.f;
+  int npos = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    bool pos = false;
+    for (int l = 0; l < L; ++l) pos |= (labels[static_cast<long long>(i) * L + l] == k);
+    if (!pos) continue;
+    ++npos;
+    const float pi = probs[static_cast<long long>(i) * C + k];
+    int rank = 1, tp = 1;
+    for (int j = 0; j < N; ++j) {
+      const float pj = probs[static_cast<long long>(j) * C + k];
+      if ((pj > pi) || (pj == pi && j < i)) {
+        ++rank;
+        bool pj_pos = false;
+        for (int l = 0; l < L; ++l) pj_pos |= (labels[static_cast<long long>(j) * L + l] == k);
+        tp += pj_pos;
+      }
+    }
+    sum += static_cast<float>(tp) / static_cast<float>(rank);
+  }
+  s_sum[threadIdx.x] = sum;
+  s_cnt[threadIdx.x] = npos;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ap[k] = s_sum[0] / fmaxf(static_cast<float>(s_cnt[0]), 1.f);
+}
+
 __global__ void fill_f32_kernel(float* p, float v, long long n) {
   pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -860,12 +945,10 @@ cudaError_t launch_gru_sequence(const float* xg, const __half* w_hh, const float
   if (B <= 0 || T <= 0) return cudaSuccess;
   if (Hd % 256 != 0 || Hd / kGruJB > sm_count || Hd > 256 * kGruMaxK) return cudaErrorInvalidValue;
   const size_t smem = sizeof(__half) * 3 * kGruJB * Hd + sizeof(float) * 3 * kGruJB;
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
+  if (smem > 48 * 1024) {   // per-device attribute; this launch is rare (one per GRU sequence), so set it every time
     cudaError_t e = cudaFuncSetAttribute(gru_sequence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
@@ -919,6 +1002,27 @@ cudaError_t launch_consensus_avg(const float* in, const float* add, float* out, 
   if (B <= 0) return cudaSuccess;
   return launch_pdl(consensus_avg_kernel, dim3(grid_for(static_cast<long long>(B) * C)), dim3(kThreads), 0, s, in, add, out,
                     B, T, C);
+}
+
+cudaError_t launch_topk_hits(const float* logits, long long stride, const long long* target, int rows, int C, int k0,
+                             int k1, float* hits, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  topk_hits_kernel<<<grid_for(static_cast<long long>(rows) * 32), kThreads, 0, s>>>(logits, stride, target, rows, C, k0,
+                                                                                   k1, hits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_rows(const float* logits, long long stride, float* probs, int rows, int C, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  softmax_rows_kernel<<<grid_for(static_cast<long long>(rows) * 32), kThreads, 0, s>>>(logits, stride, probs, rows, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_class_ap(const float* probs, const long long* labels, int N, int C, int L, float* ap,
+                            cudaStream_t s) {
+  if (C <= 0) return cudaSuccess;
+  class_ap_kernel<<<C, kThreads, 0, s>>>(probs, labels, N, C, L, ap);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s) {

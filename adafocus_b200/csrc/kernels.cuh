@@ -79,6 +79,14 @@ cudaError_t launch_tsm_shift_nchw_f32(const float* in, float* out, int NT, int T
 cudaError_t launch_consensus_avg(const float* in, const float* add, float* out, int B, int T, int C,
                                  cudaStream_t s);
 
+// Evaluation metrics on the device: top-k hit counts (ACT/ops/utils.py:35-49), row softmax and
+// per-class average precision (ACT/ops/utils.py:68-88).
+cudaError_t launch_topk_hits(const float* logits, long long stride, const long long* target, int rows, int C, int k0,
+                             int k1, float* hits, cudaStream_t s);
+cudaError_t launch_softmax_rows(const float* logits, long long stride, float* probs, int rows, int C, cudaStream_t s);
+cudaError_t launch_class_ap(const float* probs, const long long* labels, int N, int C, int L, float* ap,
+                            cudaStream_t s);
+
 cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s);
 cudaError_t launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s);
 

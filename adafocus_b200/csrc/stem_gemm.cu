@@ -311,13 +311,15 @@ bool stem_gemm_supported(const StemKernelParams& p) {
 }
 
 cudaError_t launch_stem_gemm(const StemTensorMaps& maps, const StemKernelParams& p, int sm_count, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {};   // function attributes are per device
   const size_t smem = stem_gemm_smem_bytes();
-  if (!attr_set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(stem_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.N;
   int grid = m_tiles < sm_count ? m_tiles : sm_count;

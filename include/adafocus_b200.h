@@ -174,6 +174,15 @@ int af_tsm_shift_nchw_f32(af_ctx* ctx, const float* in, float* out, int NT, int 
 /* ConsensusModule('avg') (+ glancer consensus) -- STH/ops/basic_ops.py:18-27, STH/models/gfv_net.py:170-172. */
 int af_consensus_avg(af_ctx* ctx, const float* in, const float* add, float* out, int B, int T, int C, void* stream);
 
+/* Evaluation metrics on the device, consumers of the path's logits.
+ * af_topk_hits: hits[0] += #rows whose target ranks < k0, hits[1] += ... < k1 -- accuracy(), ACT/ops/utils.py:35-49.
+ * af_softmax_rows + af_class_ap: per-class average precision over N samples with (N, L) int64 labels (-1 = none) --
+ * cal_map(), ACT/ops/utils.py:68-88 (ranks by counting instead of sorting; ties: lower index first). */
+int af_topk_hits(af_ctx* ctx, const float* logits, int64_t stride, const int64_t* target, int rows, int C, int k0,
+                 int k1, float* hits, void* stream);
+int af_softmax_rows(af_ctx* ctx, const float* logits, int64_t stride, float* probs, int rows, int C, void* stream);
+int af_class_ap(af_ctx* ctx, const float* probs, const int64_t* labels, int N, int C, int L, float* ap, void* stream);
+
 int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream);
 int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream);
 

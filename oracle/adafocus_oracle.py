@@ -310,3 +310,40 @@ def act_forward(inp, scan, ck, patch_size=128, action_dim=49, with_glancer=True,
         "patches": torch.stack(patches, 1), "lfeat": torch.stack(lfeats, 1), "features": features,
         "probs": torch.stack(probs_all, 1), "logits": logits, "last_out": last_out,
     }
+
+
+# ------------------------------------------------------------------------------------------------ metrics (f-4)
+def accuracy_topk(output, target, topk=(1,)):
+    """ACT/ops/utils.py:35-49: percentage of rows whose target is among the k largest logits."""
+    output, target = np.asarray(output), np.asarray(target)
+    order = np.argsort(-output, axis=1, kind="stable")
+    res = []
+    for k in topk:
+        res.append(100.0 * np.mean([target[i] in order[i, :k] for i in range(len(target))]))
+    return res
+
+
+def cal_map(output, labels):
+    """ACT/ops/utils.py:51-88: labels re-ranked among the distinct non-negative values (get_multi_hot with
+    assumes_starts_zero=False), softmax over classes, per-class AP = mean over positives of precision at their rank in
+    the descending (stable) order of the class probability; returns (mAP %, AP % per class)."""
+    output = np.asarray(output, dtype=np.float32)
+    labels = np.asarray(labels).reshape(output.shape[0], -1).copy()
+    n, c = output.shape
+    uniq = np.unique(labels[labels >= 0])
+    remap = {int(v): i for i, v in enumerate(uniq)}
+    gt = np.zeros((n, c + 1), dtype=bool)
+    for i in range(n):
+        for l in labels[i]:
+            gt[i, remap[int(l)] if l >= 0 else -1] = True       # -1 lands in the extra last column, dropped below
+    gt = gt[:, :c]
+    z = output - output.max(axis=1, keepdims=True)
+    probs = np.exp(z) / np.exp(z).sum(axis=1, keepdims=True)
+    ap = np.zeros(c, dtype=np.float64)
+    for k in range(c):
+        order = np.argsort(-probs[:, k], kind="stable")
+        truth = gt[order, k]
+        tp = np.cumsum(truth)
+        prec = tp / np.arange(1, n + 1)
+        ap[k] = prec[truth].sum() / max(float(truth.sum()), 1.0)
+    return ap.mean() * 100, ap * 100

@@ -130,6 +130,31 @@ def run_reference_stage2(ref, args, batch, tag, np_seed=7):
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+def metrics_golden():
+    """accuracy() / cal_map() of the reference (ACT/ops/utils.py:35-88) on seeded logits, incl. ties and -1 labels."""
+    import warnings
+    from ops.utils import accuracy, cal_map
+    g = torch.Generator().manual_seed(11)
+    n, c = 257, 12
+    logits = torch.randn(n, c, generator=g)
+    logits[5] = logits[9]                     # tied rows
+    logits[20, 3] = logits[20, 7]             # tie inside a row
+    target = torch.randint(0, c, (n,), generator=g)
+    labels = torch.stack([target, torch.randint(-1, c, (n,), generator=g)], 1)
+    out = {"logits": logits.numpy(), "target": target.numpy(), "labels": labels.numpy()}
+    acc1, acc5 = accuracy(logits, target, topk=(1, 5))
+    out["acc1"], out["acc5"] = acc1.numpy(), acc5.numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m1, ap1 = cal_map(logits, target.view(-1, 1))
+        m2, ap2 = cal_map(logits, labels)
+    out["map_single"], out["ap_single"] = np.array(float(m1)), ap1.numpy()
+    out["map_multi"], out["ap_multi"] = np.array(float(m2)), ap2.numpy()
+    path = os.path.join(HERE, "metrics.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, float(acc1), float(acc5), float(m1), float(m2))
+
+
 def get_patch_kat(ref):
     """Known-answer table for get_patch straight from the reference function (ACT/models/utils.py:37-51)."""
     from models.utils import get_patch
@@ -158,11 +183,15 @@ def get_patch_kat(ref):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref = import_reference_act()
+    if "--metrics-only" in sys.argv:
+        metrics_golden()
+        sys.exit(0)
     if "--stage2-only" in sys.argv:
         run_reference_stage2(ref, synth.act_args(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3,
                              "t4_p96_b3")
         sys.exit(0)
     get_patch_kat(ref)
+    metrics_golden()
     run_reference_stage2(ref, synth.act_args(num_segments=4, patch_size=96, action_dim=36, num_classes=51), 3,
                          "t4_p96_b3")
     # config 3 shape: T=16, P=128, 49 actions, 200 classes; 2 clips

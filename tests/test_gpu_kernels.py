@@ -304,3 +304,18 @@ def test_plan_replay_matches_eager(eng):
     plan.run(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert torch.equal(y2, eager)
+
+
+def test_device_metrics_vs_reference_golden(golden_dir):
+    """On-device accuracy / cal_map (f-4) against the reference functions' outputs on the same logits."""
+    from adafocus_b200 import metrics
+    gold = np.load(os.path.join(golden_dir, "metrics.npz"))
+    logits = torch.from_numpy(gold["logits"]).to(DEV)
+    target = torch.from_numpy(gold["target"]).to(DEV)
+    acc1, acc5 = metrics.accuracy(logits, target, topk=(1, 5))
+    assert abs(float(acc1) - float(gold["acc1"][0])) < 1e-3 and abs(float(acc5) - float(gold["acc5"][0])) < 1e-3
+    m1, ap1 = metrics.cal_map(logits, target.view(-1, 1))
+    m2, ap2 = metrics.cal_map(logits, torch.from_numpy(gold["labels"]).to(DEV))
+    np.testing.assert_allclose(ap1.cpu().numpy(), gold["ap_single"], rtol=1e-3, atol=5e-2)
+    np.testing.assert_allclose(ap2.cpu().numpy(), gold["ap_multi"], rtol=1e-3, atol=5e-2)
+    assert abs(float(m1) - float(gold["map_single"])) < 2e-2 and abs(float(m2) - float(gold["map_multi"])) < 2e-2

@@ -116,3 +116,15 @@ def test_temporal_shift_restatement():
     assert float(y[0, 1]) == 0.0 and torch.equal(y[1, 1], x[0, 1])          # channel 1 comes from t-1, zero at the start
     assert torch.equal(y[:, 2:], x[:, 2:])
     assert float(y[4, 1]) == 0.0 and torch.equal(y[3, 0], torch.zeros(1, 1))   # clips do not leak into each other
+
+
+def test_metrics_restatement_matches_reference(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "metrics.npz"))
+    acc1, acc5 = orc.accuracy_topk(gold["logits"], gold["target"], (1, 5))
+    assert abs(acc1 - float(gold["acc1"][0])) < 1e-4 and abs(acc5 - float(gold["acc5"][0])) < 1e-4
+    m1, ap1 = orc.cal_map(gold["logits"], gold["target"].reshape(-1, 1))
+    m2, ap2 = orc.cal_map(gold["logits"], gold["labels"])
+    # two samples carry identical logits: torch.sort(descending=True) orders ties arbitrarily, the restatement stably
+    np.testing.assert_allclose(ap1, gold["ap_single"], rtol=1e-4, atol=2e-2)
+    np.testing.assert_allclose(ap2, gold["ap_multi"], rtol=1e-4, atol=2e-2)
+    assert abs(m1 - float(gold["map_single"])) < 5e-3 and abs(m2 - float(gold["map_multi"])) < 5e-3
