@@ -385,12 +385,23 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   }
   // fp16 outputs leave through the smem-staged TMA store when 64-channel slices never straddle an n-block
   p.tma_store = (!d->out_f32 && d->cout % 8 == 0 && (p.BN % 64 == 0 || p.n_blocks == 1)) ? 1 : 0;
+  // A residual is added on the tensor core (R * I accumulated into TMEM), which needs the per-channel scale folded
+  // into the weights (scale == NULL); with an explicit scale the slower direct-store epilogue adds it instead.
+  if (d->residual != nullptr) {
+    if (p.tma_store && d->scale == nullptr) p.res_mma = 1;
+    else p.tma_store = 0;
+  }
   if (p.tma_store) {
     const cuuint64_t opix_b = static_cast<cuuint64_t>(d->out_stride) * 2;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
                                 static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(p.N)};
     const cuuint64_t strides[3] = {opix_b, opix_b * p.Wo, opix_b * p.Wo * p.Ho};
     if (!encode_map(ctx, &maps.out, d->out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+    if (p.res_mma) {
+      const cuuint64_t rpix_b = static_cast<cuuint64_t>(d->res_stride) * 2;
+      const cuuint64_t rstrides[3] = {rpix_b, rpix_b * p.Wo, rpix_b * p.Wo * p.Ho};
+      if (!encode_map(ctx, &maps.res, d->residual, 4, dims, rstrides, box, &err)) return fail(AF_ERR_CUDA, err);
+    }
   }
   const int sms = ctx->sm_count;
   return dispatch(ctx, stream, "af_conv2d_nhwc_f16",

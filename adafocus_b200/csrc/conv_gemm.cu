@@ -21,6 +21,7 @@ struct __align__(8) ConvSmemCtrl {
 
 constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
 constexpr int kCtrlBytes = 256;
+constexpr int kIdentBytes = 64 * 128;                         // 64x64 fp16 identity, K-major, 128-B swizzled
 constexpr int kAffineBytes = 2 * 2 * kConvMaxBlockN * 4;       // per group: scale[256] + bias[256] fp32
 constexpr int kEpilogueThreads = 128;                         // per epilogue group (4 warps = 4 TMEM lane quarters)
 constexpr int kEpilogueGroups = 2;                            // group g drains TMEM accumulator stage g
@@ -38,14 +39,15 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// Epilogue math for 32 accumulator columns of one row: y = act(acc * scale + bias (+ residual)) -> fp16, written as
-// four 16-byte chunks into the 128-byte-swizzled staging row.  ACT and RES are compile-time so the hot loop has no
-// per-element branches; ReLU / ReLU6 clamp on packed half2 after the conversion (exact: the clamp bounds 0 and 6 are
-// representable and rounding is monotonic).
-template <int ACT, bool RES>
+// Epilogue math for 32 accumulator columns of one row: y = act(acc * scale + bias) -> fp16, written as four 16-byte
+// chunks into the 128-byte-swizzled staging row.  (A residual, when there is one, is already inside the accumulator:
+// see the identity-matrix MMA in the issuer warp.)  ACT is compile-time so the hot loop has no per-element branches;
+// ReLU / ReLU6 clamp on packed half2 after the conversion (exact: the clamp bounds 0 and 6 are representable and
+// rounding is monotonic).
+template <int ACT>
 __device__ __forceinline__ void epilogue_half_slice(const uint32_t (&v)[32], const float* __restrict__ sc,
-                                                    const float* __restrict__ bi, const uint4* rv, uint8_t* srow,
-                                                    int row, int chunk0) {
+                                                    const float* __restrict__ bi, uint8_t* srow, int row,
+                                                    int chunk0) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 sa = *reinterpret_cast<const float4*>(sc + g * 8), sb = *reinterpret_cast<const float4*>(sc + g * 8 + 4);
@@ -59,15 +61,6 @@ __device__ __forceinline__ void epilogue_half_slice(const uint32_t (&v)[32], con
     x[5] = fmaf(__uint_as_float(v[g * 8 + 5]), sb.y, bb.y);
     x[6] = fmaf(__uint_as_float(v[g * 8 + 6]), sb.z, bb.z);
     x[7] = fmaf(__uint_as_float(v[g * 8 + 7]), sb.w, bb.w);
-    if (RES) {
-      const __half2* rh = reinterpret_cast<const __half2*>(&rv[g]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(rh[j]);
-        x[2 * j] += f.x;
-        x[2 * j + 1] += f.y;
-      }
-    }
     uint4 ov;
     __half2* oh2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
@@ -81,13 +74,11 @@ __device__ __forceinline__ void epilogue_half_slice(const uint32_t (&v)[32], con
   }
 }
 
-template <bool RES>
 __device__ __forceinline__ void epilogue_half_slice_act(int act, const uint32_t (&v)[32], const float* sc,
-                                                        const float* bi, const uint4* rv, uint8_t* srow, int row,
-                                                        int chunk0) {
-  if (act == kActRelu) epilogue_half_slice<kActRelu, RES>(v, sc, bi, rv, srow, row, chunk0);
-  else if (act == kActRelu6) epilogue_half_slice<kActRelu6, RES>(v, sc, bi, rv, srow, row, chunk0);
-  else epilogue_half_slice<kActNone, RES>(v, sc, bi, rv, srow, row, chunk0);
+                                                        const float* bi, uint8_t* srow, int row, int chunk0) {
+  if (act == kActRelu) epilogue_half_slice<kActRelu>(v, sc, bi, srow, row, chunk0);
+  else if (act == kActRelu6) epilogue_half_slice<kActRelu6>(v, sc, bi, srow, row, chunk0);
+  else epilogue_half_slice<kActNone>(v, sc, bi, srow, row, chunk0);
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -100,7 +91,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
   const int stage_b_bytes = p.BN * kConvBlockK * 2;
   const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
-  uint8_t* staging_base = smem + static_cast<size_t>(p.stages) * stage_bytes;      // 2 x 16 KiB, 1024-B aligned
+  // [stages][64x64 identity tile, only with res_mma][epilogue staging][scale/bias][barriers]; all 1024-B aligned
+  uint8_t* ident = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint8_t* staging_base = ident + (p.res_mma ? kIdentBytes : 0);
   float* s_affine = reinterpret_cast<float*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
   ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(reinterpret_cast<uint8_t*>(s_affine) + kAffineBytes);
 
@@ -126,6 +119,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
     if (p.tma_store) tma_prefetch_desc(&maps.out);
+    if (p.res_mma) tma_prefetch_desc(&maps.res);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -135,6 +129,23 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   if (warp == 1) {
     tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
+  }
+  if (p.res_mma && warp >= 2) {
+    // B operand of the residual MMA: I[n][k] = (n == k), 64 rows of 128 B, 16-byte chunk c of row n at (c ^ (n & 7))
+    for (int i = threadIdx.x - 64; i < 64 * 8; i += kEpilogueGroups * kEpilogueThreads) {
+      const int n = i >> 3, c = i & 7;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if ((n >> 3) == c) {
+        const uint32_t one = (n & 1) ? 0x3C000000u : 0x00003C00u;   // fp16 1.0 in the high / low half
+        const int wsel = (n & 7) >> 1;
+        val.x = wsel == 0 ? one : 0u;
+        val.y = wsel == 1 ? one : 0u;
+        val.z = wsel == 2 ? one : 0u;
+        val.w = wsel == 3 ? one : 0u;
+      }
+      *reinterpret_cast<uint4*>(ident + n * 128 + ((c ^ (n & 7)) << 4)) = val;
+    }
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   tc_fence_before();
   __syncthreads();
@@ -185,6 +196,19 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
+        if (p.res_mma) {
+          // the residual tile rides the same pipeline as extra A boxes (64 output channels each)
+          for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
+            mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
+            tma_load_4d(sa, &maps.res, &ctrl->full[stage], nb * p.BN + j * 64, ow0, oh0, n0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -217,6 +241,27 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if (p.res_mma) {
+          // acc[:, j*64 .. j*64+nj) += R_j (128 x 64 fp16) * I (64 x nj): the residual add, exact in fp32
+          const int nb = tile % p.n_blocks;
+          const uint64_t di = make_smem_desc_sw128(smem_u32(ident));
+          for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
+            const int nj = p.BN - j * 64 < 64 ? p.BN - j * 64 : 64;
+            const uint32_t idesc_r = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(nj));
+            mbar_wait_backoff(&ctrl->full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc_sw128(smem_u32(smem + static_cast<size_t>(stage) * stage_bytes));
+#pragma unroll
+            for (int k = 0; k < kConvBlockK / 16; ++k)
+              umma_f16_ss(tmem_d + static_cast<uint32_t>(j * 64), da + static_cast<uint64_t>(k * 2),
+                          di + static_cast<uint64_t>(k * 2), idesc_r, 1u);
+            umma_commit(&ctrl->empty[stage]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         umma_commit(&ctrl->tmem_full[as]);    // accumulator complete -> epilogue
@@ -258,38 +303,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                              static_cast<uint32_t>(as * kConvMaxBlockN);
       if (p.tma_store) {
         // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
-        const bool has_res = (p.residual != nullptr) && valid && !(p.debug_flags & 2);
         const int nslices = (p.BN + 63) >> 6;
-        // residual of the first TWO slices goes in flight now, long before the accumulator is ready; later slices
-        // are prefetched two slices ahead into the slot that was just consumed
-        uint4 rv_a[8], rv_b[8];
-        const __half* res_row = has_res ? p.residual + pix * p.res_stride + co_base : nullptr;
-        // each lane reads its own row: 32-byte loads halve the number of (uncoalesced) requests when alignment allows
-        const bool res256 = has_res && ((reinterpret_cast<uintptr_t>(p.residual) | (p.res_stride * 2)) & 31) == 0 &&
-                            (p.Cout & 15) == 0 && (co_base & 15) == 0;
-        auto load_res = [&](uint4 (&dst)[8], int col0) {
-          if (res256) {
-#pragma unroll
-            for (int g = 0; g < 8; g += 2) {
-              if (co_base + col0 + g * 8 + 16 <= p.Cout) {
-                ldg256_nc(res_row + col0 + g * 8, dst[g], dst[g + 1]);
-              } else {
-                dst[g] = make_uint4(0u, 0u, 0u, 0u);
-                dst[g + 1] = make_uint4(0u, 0u, 0u, 0u);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              dst[g] = (co_base + col0 + g * 8 + 8 <= p.Cout)
-                           ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + g * 8))
-                           : make_uint4(0u, 0u, 0u, 0u);
-          }
-        };
-        if (has_res) {
-          load_res(rv_a, 0);
-          if (nslices > 1) load_res(rv_b, 64);
-        }
         if (nb != loaded_nb) {
           // per-channel scale / bias of this n-block -> smem (zero past BN so stray columns stay finite).  Every
           // thread of the group is past the previous tile's last barrier, i.e. past its last read of these arrays.
@@ -303,7 +317,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         mbar_wait(&ctrl->tmem_full[as], aphase);
         tc_fence_after();
-        auto do_slice = [&](int sl, uint4 (&rvx)[8]) {
+        auto do_slice = [&](int sl) {
           const int c0 = sl * 64;
           // this staging buffer was last read by the store issued two slices ago; thread 0 waited for that store
           // before the previous slice's barrier
@@ -322,14 +336,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               __syncwarp();
               if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
             }
-            if (has_res)
-              epilogue_half_slice_act<true>(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, &rvx[hf * 4], srow,
-                                            row, hf * 4);
-            else
-              epilogue_half_slice_act<false>(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, nullptr, srow,
-                                             row, hf * 4);
+            epilogue_half_slice_act(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, srow, row, hf * 4);
           }
-          if (has_res && sl + 2 < nslices) load_res(rvx, c0 + 128);   // refill the consumed slot two slices ahead
           fence_proxy_async();
           if (et == 0) tma_store_wait_read0();   // the previous slice's store has left the other buffer
           named_barrier_sync(bar_id, kEpilogueThreads);
@@ -339,10 +347,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           }
         };
 #pragma unroll 1
-        for (int sl = 0; sl < nslices; sl += 2) {
-          do_slice(sl, rv_a);
-          if (sl + 1 < nslices) do_slice(sl + 1, rv_b);
-        }
+        for (int sl = 0; sl < nslices; ++sl) do_slice(sl);
       } else {
         // ---- fp32 (or odd-shaped) output: direct global stores, one row per thread
         mbar_wait(&ctrl->tmem_full[as], aphase);
@@ -419,12 +424,12 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int BN, int num_kb, int* stages_out, int* epi_bufs_out) {
-  (void)num_kb;
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int* stages_out, int* epi_bufs_out) {
   const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
   // two epilogue groups x two 16 KiB staging buffers (a TMA store drains while the next slice is produced)
   const int epi_bufs = 2;
-  const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes;
+  const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes +
+                    (res_mma ? kIdentBytes : 0);
   int stages = (kConvSmemBudget - fixed) / stage_bytes;
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   if (stages < 2) stages = 2;
@@ -438,7 +443,7 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   static_assert(sizeof(ConvSmemCtrl) <= kCtrlBytes, "ctrl block too large");
   ConvKernelParams p = p_in;
   int stages = 0, epi_bufs = 1;
-  const size_t smem = conv_gemm_smem_bytes(p.BN, p.KH * p.KW * p.cblks, &stages, &epi_bufs);
+  const size_t smem = conv_gemm_smem_bytes(p.BN, p.res_mma, &stages, &epi_bufs);
   p.stages = stages;
   p.epi_bufs = epi_bufs;
   static const int dbg = getenv("AF_CONV_DEBUG") ? atoi(getenv("AF_CONV_DEBUG")) : 0;

@@ -50,18 +50,20 @@ struct ConvKernelParams {
   int out_f32;
   int act;
   int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
+  int res_mma;                     // 1: residual tile is TMA-loaded (maps.res) and added by an identity-matrix MMA
   int epi_bufs;                    // staging buffers per epilogue group (1 or 2)
-  int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores, 2 = skip residual loads
+  int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores
 };
 
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
   CUtensorMap out;    // output tensor {Cout, Wo, Ho, N}, box {64, TW, TH, TN} (only when tma_store)
+  CUtensorMap res;    // residual tensor, same dims / box as `out` (only when res_mma)
 };
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,
                              cudaStream_t stream);
-size_t conv_gemm_smem_bytes(int BN, int num_kb, int* stages_out, int* epi_bufs_out);
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int* stages_out, int* epi_bufs_out);
 
 }  // namespace af

@@ -52,8 +52,11 @@ def fold_bn(bn_weight, bn_bias, running_mean, running_var, eps):
 
 
 def pack_conv(weight, scale=None, bias=None, stride=1, pad=0, act=AF_ACT_NONE, block_n=None, device=None,
-              cin_perm=None):
+              cin_perm=None, fold_scale=False):
     """weight: (cout, cin, kh, kw) or (cout, cin) fp32 in torch layout -> PackedConv on `device`.
+
+    fold_scale: multiply the per-channel scale into the fp32 weights before the fp16 rounding and pass no scale to
+    the kernel.  Layers that add a residual use it: the kernel then adds the residual on the tensor core.
 
     cin_perm: optional LongTensor; packed input channel j reads torch input channel cin_perm[j] (used to absorb the
     NCHW-flatten vs NHWC-flatten difference of ACT/models/ppo.py:36-37)."""
@@ -65,14 +68,19 @@ def pack_conv(weight, scale=None, bias=None, stride=1, pad=0, act=AF_ACT_NONE, b
     cout, cin, kh, kw = w.shape
     if cin_perm is not None:
         w = w[:, cin_perm.to(device)]
+    if fold_scale and scale is not None:
+        w = w * scale.detach().float().to(device)[:, None, None, None]
+        scale = None
     block_n = block_n or default_block_n(cout)
     cout_pad = round_up(cout, block_n)
     cblk = (cin + BLOCK_K - 1) // BLOCK_K
     wp = torch.zeros(cout_pad, kh * kw, cblk * BLOCK_K, dtype=torch.float16, device=device)
     wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).half()
     wp = wp.reshape(cout_pad, kh * kw * cblk * BLOCK_K).contiguous()
-    sc = torch.ones(cout_pad, dtype=torch.float32, device=device)
+    sc = None
     bi = torch.zeros(cout_pad, dtype=torch.float32, device=device)
+    if scale is not None or not fold_scale:
+        sc = torch.ones(cout_pad, dtype=torch.float32, device=device)
     if scale is not None:
         sc[:cout] = scale.detach().float().to(device)
     if bias is not None:
@@ -207,7 +215,8 @@ class Engine:
         elif out_stride is None:
             out_stride = out.stride(-2)
         d = ConvDesc()
-        d.in_, d.w, d.scale, d.bias = x.data_ptr(), pc.w.data_ptr(), pc.scale.data_ptr(), pc.bias.data_ptr()
+        d.in_, d.w, d.bias = x.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr()
+        d.scale = pc.scale.data_ptr() if pc.scale is not None else None
         d.residual = residual.data_ptr() if residual is not None else None
         d.out = out.data_ptr()
         d.n, d.h, d.w_, d.cin, d.cout = n, h, w, cin, pc.cout

@@ -129,7 +129,7 @@ class MobileNetV2Runner:
             entry["dw_s"], entry["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
             pw, bn = seq[1], seq[2]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-            entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev)
+            entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=entry["res"])
             entry["_proj"] = (pw.weight.detach().float().flatten(1).to(dev), s.to(dev), b.to(dev))
             entry["_exp"] = None
             if blk.expand != 1:

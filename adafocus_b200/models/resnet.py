@@ -121,7 +121,7 @@ class ResNetRunner:
                 e["c2"] = pack_conv(blk.conv2.weight, s, b, stride=blk.conv2.stride[0], pad=1, act=AF_ACT_RELU,
                                     device=dev)
                 s, b = _fold(blk.bn3)
-                e["c3"] = pack_conv(blk.conv3.weight, s, b, act=AF_ACT_RELU, device=dev)   # relu after the add
+                e["c3"] = pack_conv(blk.conv3.weight, s, b, act=AF_ACT_RELU, device=dev, fold_scale=True)   # relu after the add
                 if blk.downsample is not None:
                     s, b = _fold(blk.downsample[1])
                     e["ds"] = pack_conv(blk.downsample[0].weight, s, b, stride=blk.downsample[0].stride[0],

@@ -103,7 +103,7 @@ class SthGlancerRunner(MobileNetV2Runner):
             e["dw_s"], e["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
             pw, bn = seq[3], seq[4]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-            e["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev)
+            e["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=e["res"])
             self.blocks.append(e)
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)

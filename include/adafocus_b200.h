@@ -46,7 +46,9 @@ typedef struct af_plan af_plan; /* a recorded sequence of launches, replayable w
  *        cout_pad = ceil(cout/block_n)*block_n
  *   out: NHWC fp16 or fp32 (n, ho, wo, cout), pixel stride out_stride
  *   y  = act(scale[co]*conv + bias[co] (+ residual)), scale/bias have cout_pad entries; scale may be NULL (= 1,
- *        e.g. when the BatchNorm scale has been folded into the packed weights).
+ *        e.g. when the BatchNorm scale has been folded into the packed weights).  With a residual, scale == NULL is
+ *        the fast path (the residual tile is TMA-loaded and accumulated on the tensor core, exact in fp32); a
+ *        residual together with an explicit scale falls back to a slower epilogue that adds it from registers.
  * A plain GEMM C[M,N] = A[M,K] W[N,K]^T is the case n=1, h=1, w=M, cin=K, kh=kw=1, stride=1, pad=0. */
 typedef struct af_conv_desc {
   const void* in;

@@ -142,6 +142,50 @@ def test_conv_vs_torch_fp32(eng, case):
     assert float(out[..., cout:].abs().max() if cstride > cout else 0.0) == 0.0      # padding columns untouched
 
 
+RES_MMA_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, act  -- residual layers with the scale folded into the weights
+    (2, 16, 16, 64, 256, 1, 1, 0, 1),          # ResNet layer1 conv3
+    (64, 32, 32, 64, 256, 1, 1, 0, 1),         # persistent loop, both TMEM stages
+    (6, 8, 8, 256, 1024, 1, 1, 0, 1),          # four n-blocks, TN = 2
+    (20, 4, 4, 512, 512, 3, 1, 1, 1),          # 3x3 with residual, TN = 8
+    (4, 14, 14, 144, 24, 1, 1, 0, 0),          # MobileNet-V2 projections: Cout 24 / 96 / 160 (BN 32 / 96 / 160)
+    (3, 14, 14, 576, 96, 1, 1, 0, 0),
+    (2, 7, 7, 960, 160, 1, 1, 0, 0),
+    (5, 9, 9, 192, 64, 1, 1, 0, 2),
+]
+
+
+@pytest.mark.parametrize("case", RES_MMA_CASES, ids=[f"r{i}" for i in range(len(RES_MMA_CASES))])
+def test_conv_residual_on_tensor_core(eng, case):
+    """scale == NULL + residual: the residual tile is TMA-loaded and added by an identity-matrix MMA."""
+    from adafocus_b200.engine import pack_conv
+    n, h, w, cin, cout, k, stride, pad, act = case
+    torch.manual_seed(hash(case) % 1000)
+    x = torch.randn(n, h, w, cin, device=DEV).half()
+    wt = torch.randn(cout, cin, k, k, device=DEV) / math.sqrt(cin * k * k)
+    scale = torch.rand(cout, device=DEV) + 0.5
+    bias = torch.randn(cout, device=DEV) * 0.1
+    pc = pack_conv(wt, scale, bias, stride, pad, act, device=DEV, fold_scale=True)
+    assert pc.scale is None
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    # residual with a row stride larger than Cout (a channel slice of a wider tensor)
+    rfull = torch.randn(n, ho, wo, cout + 8, device=DEV).half()
+    r = rfull[..., :cout]
+    out = eng.conv(x, pc, residual=r)
+    torch.cuda.synchronize()
+    wf = (wt * scale.view(-1, 1, 1, 1)).half().float()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wf, None, stride, pad) + bias.view(1, -1, 1, 1)
+    ref = ref + r.float().permute(0, 3, 1, 2)
+    ref = ref.clamp(min=0) if act == 1 else ref.clamp(0, 6) if act == 2 else ref
+    ref = ref.permute(0, 2, 3, 1)
+    got = out.float()
+    assert torch.allclose(got, ref, rtol=4e-3, atol=4e-3), float((got - ref).abs().max())
+    # with zero weights and zero bias the layer must return the residual bit for bit (fp16 -> fp32 -> fp16)
+    pz = pack_conv(torch.zeros_like(wt), None, None, stride, pad, 0, device=DEV, fold_scale=True)
+    out0 = eng.conv(x, pz, residual=r)
+    assert torch.equal(out0, r.contiguous())
+
+
 def test_stem_im2col_conv_vs_torch(eng):
     """Crop fused into the stem staging + 7x7/2 conv as a GEMM == conv2d(get_patch(...))."""
     from adafocus_b200.engine import pack_stem
