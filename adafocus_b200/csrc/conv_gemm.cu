@@ -13,7 +13,7 @@ namespace {
 struct __align__(8) ConvSmemCtrl {
   uint64_t full[kConvMaxStages];
   uint64_t empty[kConvMaxStages];
-  uint64_t tmem_full[2];
+  uint64_t tmem_full[4];   // [stage] or, when single-slice tiles alternate between a stage's two groups, [stage + 2*sub]
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
@@ -22,10 +22,11 @@ struct __align__(8) ConvSmemCtrl {
 constexpr int kStageABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB
 constexpr int kCtrlBytes = 256;
 constexpr int kIdentBytes = 64 * 128;                         // 64x64 fp16 identity, K-major, 128-B swizzled
-constexpr int kAffineBytes = 2 * 2 * kConvMaxBlockN * 4;       // per group: scale[256] + bias[256] fp32
 constexpr int kEpilogueThreads = 128;                         // per epilogue group (4 warps = 4 TMEM lane quarters)
-constexpr int kEpilogueGroups = 2;                            // group g drains TMEM accumulator stage g
-constexpr int kEpilogueBarrier = 1;                           // named barrier ids 1, 2 (one per group)
+constexpr int kEpilogueGroups = 4;                            // groups g and g+2 drain TMEM accumulator stage g
+constexpr int kAffineBytes = kEpilogueGroups * 2 * kConvMaxBlockN * 4;   // per group: scale[256] + bias[256] fp32
+constexpr int kEpilogueBarrier = 1;                           // named barrier ids 1..4 (one per group)
+static_assert(kConvThreads == 64 + kEpilogueGroups * kEpilogueThreads, "thread roles");
 
 // single-thread roles (producer / MMA issuer) back off between probes so they do not steal issue slots from the
 // epilogue warps that share their scheduler
@@ -109,9 +110,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       mbar_init(&ctrl->full[s], 1);
       mbar_init(&ctrl->empty[s], 1);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&ctrl->tmem_full[a], 1);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&ctrl->tmem_full[a], 1);
-      mbar_init(&ctrl->tmem_empty[a], 4);   // one arrive per warp of the epilogue group that owns stage a
+      // one arrive per warp of every epilogue group that reads the stage: both groups of the stage when a tile has
+      // several 64-column slices (they split the slices), one group when it has a single slice (they alternate tiles)
+      mbar_init(&ctrl->tmem_empty[a], (p.tma_store && p.BN <= 64) ? 4 : 8);
     }
     fence_mbar_init();
   }
@@ -215,6 +218,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(p.BN));
+      const bool alternate_tiles = p.tma_store && p.BN <= 64;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -264,28 +268,38 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        umma_commit(&ctrl->tmem_full[as]);    // accumulator complete -> epilogue
+        // accumulator complete -> epilogue.  With single-slice tiles the stage's two groups take alternate tiles and
+        // each waits on its own barrier, so that every waiter sees every phase of the barrier it polls.
+        umma_commit(&ctrl->tmem_full[alternate_tiles ? as + 2 * ((it >> 1) & 1) : as]);
       }
     }
   } else {
-    // ============================ epilogue (2 groups x 4 warps) ============================
-    // Group g only ever handles the tiles whose accumulator lives in TMEM stage g (local tile index it = g, g+2, ..),
-    // so the two groups drain consecutive tiles concurrently, each with its own staging buffer and named barrier.
+    // ============================ epilogue (4 groups x 4 warps) ============================
+    // Groups g and g+2 only ever handle the tiles whose accumulator lives in TMEM stage g & 1 (local tile index
+    // it = g&1, (g&1)+2, ..).  Inside a tile the two groups take alternate 64-column slices; when the tile is a single
+    // slice they take alternate tiles instead.  Every group has its own staging buffer, scale/bias copy and named
+    // barrier, so 16 warps keep the SM's four schedulers busy while the next tile's MMAs run.
     const int group = (warp - 2) >> 2;
+    const int as = group & 1;                 // TMEM accumulator stage this group drains
+    const int sub = group >> 1;               // which of the stage's two groups
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;      // row of the 128-row tile == TMEM lane
     const int et = threadIdx.x - 64 - group * kEpilogueThreads;   // 0..127 inside the group
     const uint32_t bar_id = kEpilogueBarrier + group;
-    uint8_t* group_staging = staging_base + group * 2 * kConvStagingBytes;
+    uint8_t* staging = staging_base + group * kConvStagingBytes;
+    uint8_t* srow = staging + row * 128;
     float* g_scale = s_affine + group * 2 * kConvMaxBlockN;
     float* g_bias = g_scale + kConvMaxBlockN;
-    int slice_ctr = 0;                        // slices stored by this group so far (selects the staging buffer)
     int loaded_nb = -1;                       // n-block whose scale / bias currently sit in smem
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
+    const int nslices = (p.BN + 63) >> 6;
+    const bool alternate_tiles = p.tma_store && nslices == 1;
+    const int sl_first = alternate_tiles ? 0 : sub, sl_step = alternate_tiles ? 1 : 2;
     pdl_wait_prior_grid();
-    for (int it = group; blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += kEpilogueGroups) {
+    for (int it = as; blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += 2) {
+      if (alternate_tiles && ((it >> 1) & 1) != sub) continue;
       const int tile = blockIdx.x + it * gridDim.x;
       const int nb = tile % p.n_blocks;
       const int mt = tile / p.n_blocks;
@@ -296,14 +310,13 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const int ow = ow0 + tw, oh = oh0 + th, n = n0 + tn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
       const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
-      const int as = it & 1;                  // == group
-      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t aphase = alternate_tiles ? (it >> 2) & 1 : (it >> 1) & 1;
+      uint64_t* acc_full = &ctrl->tmem_full[alternate_tiles ? as + 2 * sub : as];
       const int co_base = nb * p.BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * kConvMaxBlockN);
       if (p.tma_store) {
         // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
-        const int nslices = (p.BN + 63) >> 6;
         if (nb != loaded_nb) {
           // per-channel scale / bias of this n-block -> smem (zero past BN so stray columns stay finite).  Every
           // thread of the group is past the previous tile's last barrier, i.e. past its last read of these arrays.
@@ -315,44 +328,42 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           loaded_nb = nb;
           named_barrier_sync(bar_id, kEpilogueThreads);
         }
-        mbar_wait(&ctrl->tmem_full[as], aphase);
+        mbar_wait(acc_full, aphase);
         tc_fence_after();
-        auto do_slice = [&](int sl) {
+#pragma unroll 1
+        for (int sl = sl_first; sl < nslices; sl += sl_step) {
           const int c0 = sl * 64;
-          // this staging buffer was last read by the store issued two slices ago; thread 0 waited for that store
-          // before the previous slice's barrier
-          uint8_t* staging = group_staging + (slice_ctr & 1) * kConvStagingBytes;
-          ++slice_ctr;
-          uint8_t* srow = staging + row * 128;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint32_t v[32];
             __syncwarp();
             tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + hf * 32), v);
             tmem_ld_wait();
-            if (hf == 1 && sl == nslices - 1) {
-              // accumulator fully read: hand the TMEM stage back to the MMA warp
+            if (hf == 1 && sl + sl_step >= nslices) {
+              // this group's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
             }
+            if (hf == 0) {
+              // the group's staging buffer may still be feeding its previous TMA store
+              if (et == 0) tma_store_wait_read0();
+              named_barrier_sync(bar_id, kEpilogueThreads);
+            }
             epilogue_half_slice_act(p.act, v, g_scale + c0 + hf * 32, g_bias + c0 + hf * 32, srow, row, hf * 4);
           }
           fence_proxy_async();
-          if (et == 0) tma_store_wait_read0();   // the previous slice's store has left the other buffer
           named_barrier_sync(bar_id, kEpilogueThreads);
           if (et == 0 && !(p.debug_flags & 1)) {
             tma_store_4d(&maps.out, staging, co_base + c0, ow0, oh0, n0);
             tma_store_commit();
           }
-        };
-#pragma unroll 1
-        for (int sl = 0; sl < nslices; ++sl) do_slice(sl);
+        }
       } else {
         // ---- fp32 (or odd-shaped) output: direct global stores, one row per thread
-        mbar_wait(&ctrl->tmem_full[as], aphase);
+        mbar_wait(acc_full, aphase);
         tc_fence_after();
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        for (int c0 = sub * 16; c0 < p.BN; c0 += 32) {   // the stage's two groups take alternate 16-column chunks
           uint32_t v[16];
           __syncwarp();
           tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c0), v);
@@ -426,8 +437,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 size_t conv_gemm_smem_bytes(int BN, int res_mma, int* stages_out, int* epi_bufs_out) {
   const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
-  // two epilogue groups x two 16 KiB staging buffers (a TMA store drains while the next slice is produced)
-  const int epi_bufs = 2;
+  // one 16 KiB staging buffer per epilogue group (other groups compute while a group's TMA store drains)
+  const int epi_bufs = 1;
   const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes +
                     (res_mma ? kIdentBytes : 0);
   int stages = (kConvSmemBudget - fixed) / stage_bytes;

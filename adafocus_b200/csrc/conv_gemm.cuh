@@ -24,7 +24,7 @@ constexpr int kConvBlockM = 128;
 constexpr int kConvBlockK = 64;          // fp16 elements per k-block = 128 B swizzle span
 constexpr int kConvMaxBlockN = 256;
 constexpr int kConvMaxStages = 8;
-constexpr int kConvThreads = 320;        // warp0: TMA producer, warp1: MMA issuer, warps2-5 / 6-9: epilogue groups
+constexpr int kConvThreads = 576;        // warp0: TMA producer, warp1: MMA issuer, warps 2-17: four epilogue groups
 constexpr int kConvSmemBudget = 227 * 1024;   // max dynamic shared memory per CTA on sm_100
 constexpr int kConvStagingBytes = 128 * 128;  // one 128-row x 64-channel fp16 slice of the output tile
 

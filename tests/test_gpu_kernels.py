@@ -110,6 +110,8 @@ CONV_CASES = [
     (64, 32, 32, 64, 256, 1, 1, 0, 1, False, False, None),      # > 148 tiles: persistent loop + TMEM double buffer
     (32, 16, 16, 128, 128, 3, 1, 1, 1, True, False, 64),
     (5, 18, 18, 128, 128, 3, 2, 1, 1, False, False, None),      # P=144 shapes (36 -> 18 -> 9)
+    (256, 32, 32, 64, 64, 1, 1, 0, 1, False, False, None),      # single-slice tiles, ~14 per CTA: groups alternate tiles
+    (200, 16, 16, 32, 192, 1, 1, 0, 2, False, False, None),     # three slices per tile, ~3 tiles per CTA
 ]
 
 
@@ -152,6 +154,7 @@ RES_MMA_CASES = [
     (3, 14, 14, 576, 96, 1, 1, 0, 0),
     (2, 7, 7, 960, 160, 1, 1, 0, 0),
     (5, 9, 9, 192, 64, 1, 1, 0, 2),
+    (512, 16, 16, 64, 64, 3, 1, 1, 1),         # single-slice tiles with residual, ~7 per CTA
 ]
 
 

@@ -10,6 +10,10 @@ CASES = {
     "conv3_l1": (1024, 32, 32, 64, 256, 1, 1, 0, 1, True),       # fL layer1 conv3 + residual
     "conv2_l3": (1024, 8, 8, 256, 256, 3, 1, 1, 1, False),       # fL layer3 3x3 (MMA-bound)
     "conv1_l1": (1024, 32, 32, 256, 64, 1, 1, 0, 1, False),      # fL layer1 conv1 (read-heavy)
+    "conv2_l1": (1024, 32, 32, 64, 64, 3, 1, 1, 1, False),       # fL layer1 3x3 (L2 operand traffic)
+    "conv3_l2": (1024, 16, 16, 128, 512, 1, 1, 0, 1, True),      # fL layer2 conv3 + residual
+    "conv3_l3": (1024, 8, 8, 256, 1024, 1, 1, 0, 1, True),       # fL layer3 conv3 + residual
+    "expand56": (1024, 56, 56, 24, 144, 1, 1, 0, 2, False),      # fG block 3 expand
 }
 
 def main():
@@ -20,7 +24,7 @@ def main():
         n, h, w, cin, cout, k, stride, pad, act, res = CASES[name]
         x = torch.randn(n, h, w, cin, device=dev).half()
         wt = torch.randn(cout, cin, k, k, device=dev) / math.sqrt(cin * k * k)
-        pc = pack_conv(wt, torch.ones(cout), torch.zeros(cout), stride, pad, act, device=dev)
+        pc = pack_conv(wt, torch.ones(cout), torch.zeros(cout), stride, pad, act, device=dev, fold_scale=res)
         ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
         r = torch.randn(n, ho, wo, cout, device=dev).half() if res else None
         out = torch.empty(n, ho, wo, cout, device=dev, dtype=torch.float16)
