@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -10,6 +11,7 @@
 
 #include "../../include/adafocus_b200.h"
 #include "conv_gemm.cuh"
+#include "dwconv_tma.cuh"
 #include "kernels.cuh"
 #include "stem_gemm.cuh"
 
@@ -81,11 +83,12 @@ int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
 }
 
 bool encode_map(af_ctx* ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box, std::string* err) {
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, std::string* err,
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank),
                                  const_cast<void*>(base), dims, strides_bytes, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -426,6 +429,39 @@ int af_dwconv3x3_nhwc_f16(af_ctx* ctx, const void* in, const float* w9c, const f
   if (C % 8 != 0 || (stride != 1 && stride != 2)) return fail(AF_ERR_INVALID, "af_dwconv3x3_nhwc_f16: bad shape");
   const __half* i = static_cast<const __half*>(in);
   __half* o = static_cast<__half*>(out);
+  static const bool direct_only = getenv("AF_DW_DIRECT") != nullptr;
+  af::DwTmaParams tp;
+  if (ctx != nullptr && !direct_only && af::dwconv_tma_plan(N, H, W, C, stride, &tp)) {
+    // TMA-staged kernel: one 4-D box per tile in, one out (no swizzle: the threads read plain [y][x][c] tiles)
+    tp.w9c = w9c; tp.scale = scale; tp.bias = bias; tp.act = act;
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    const int edge = stride == 1 ? 2 : 1;
+    CUtensorMap in_map, out_map;
+    std::string err;
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(C) * 2;
+    {
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                  static_cast<cuuint64_t>(N)};
+      const cuuint64_t strides[3] = {pix_b, pix_b * W, pix_b * W * H};
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(tp.CB), static_cast<cuuint32_t>(tp.TW * stride + edge),
+                                 static_cast<cuuint32_t>(tp.TH * stride + edge), static_cast<cuuint32_t>(tp.NB)};
+      if (!encode_map(ctx, &in_map, in, 4, dims, strides, box, &err, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return fail(AF_ERR_CUDA, err);
+    }
+    {
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Wo),
+                                  static_cast<cuuint64_t>(Ho), static_cast<cuuint64_t>(N)};
+      const cuuint64_t strides[3] = {pix_b, pix_b * Wo, pix_b * Wo * Ho};
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(tp.CB), static_cast<cuuint32_t>(tp.TW),
+                                 static_cast<cuuint32_t>(tp.TH), static_cast<cuuint32_t>(tp.NB)};
+      if (!encode_map(ctx, &out_map, out, 4, dims, strides, box, &err, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return fail(AF_ERR_CUDA, err);
+    }
+    const int sms = ctx->sm_count;
+    return dispatch(ctx, stream, "af_dwconv3x3_nhwc_f16", [=](cudaStream_t s) {
+      return af::launch_dwconv3x3_tma(in_map, out_map, tp, stride, sms, s);
+    });
+  }
   return dispatch(ctx, stream, "af_dwconv3x3_nhwc_f16", [=](cudaStream_t s) {
     return af::launch_dwconv3x3(i, w9c, scale, bias, o, N, H, W, C, stride, act, s);
   });

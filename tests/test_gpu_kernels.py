@@ -223,10 +223,15 @@ def test_direct_stem_conv3x3s2_vs_torch(eng):
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-@pytest.mark.parametrize("stride,c,hw", [(1, 32, 14), (2, 96, 15), (2, 144, 56), (1, 960, 7)])
-def test_dwconv3x3(eng, stride, c, hw):
+@pytest.mark.parametrize("stride,c,hw,n", [(1, 32, 14, 3), (2, 96, 15, 3), (2, 144, 56, 3), (1, 960, 7, 3),
+                                           (1, 32, 112, 2), (2, 96, 112, 2), (1, 144, 56, 2), (1, 192, 28, 5),
+                                           (2, 192, 28, 5), (1, 384, 14, 5), (1, 576, 14, 3), (2, 576, 14, 7),
+                                           (1, 960, 7, 9), (1, 40, 9, 2), (1, 64, 5, 1), (2, 64, 6, 11)])
+def test_dwconv3x3(eng, stride, c, hw, n):
+    """TMA-staged kernel at every MobileNet-V2 shape (partial tiles, several images per tile, odd sizes) and the
+    direct kernel for channel counts the tiled one does not take (C=40)."""
     torch.manual_seed(c)
-    x = torch.randn(3, hw, hw, c, device=DEV).half()
+    x = torch.randn(n, hw, hw, c, device=DEV).half()
     w = torch.randn(c, 1, 3, 3, device=DEV) / 3
     scale, bias = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.1
     out = eng.dwconv3x3(x, w.reshape(c, 9).t().contiguous(), scale, bias, stride)
