@@ -29,6 +29,16 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class MbconvDesc(ctypes.Structure):
+    """struct af_mbconv_desc"""
+    _fields_ = [
+        ("in_", c_void_p), ("w1", c_void_p), ("bias1", c_void_p), ("dw_w", c_void_p), ("bias2", c_void_p),
+        ("w2", c_void_p), ("bias3", c_void_p), ("residual", c_void_p), ("out", c_void_p),
+        ("n", c_int32), ("h", c_int32), ("w_", c_int32), ("cin", c_int32), ("cexp", c_int32), ("cout", c_int32),
+        ("stride", c_int32), ("res_stride", c_int64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/adafocus_b200.h
 SIGNATURES = {
     "af_version": (c_int, []),
@@ -53,6 +63,8 @@ SIGNATURES = {
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),
+    "af_mbconv_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "af_mbconv_fused": (c_int, [c_void_p, POINTER(MbconvDesc), c_void_p]),
     "af_dwconv3x3_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "af_maxpool3x3s2_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -13,6 +13,7 @@
 #include "conv_gemm.cuh"
 #include "dwconv_tma.cuh"
 #include "kernels.cuh"
+#include "mbconv_fused.cuh"
 #include "stem_gemm.cuh"
 
 namespace {
@@ -409,6 +410,64 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   const int sms = ctx->sm_count;
   return dispatch(ctx, stream, "af_conv2d_nhwc_f16",
                   [=](cudaStream_t s) { return af::launch_conv_gemm(maps, p, sms, s); });
+}
+
+int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride) {
+  af::MbParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cexp = cexp; p.Cout = cout; p.S = stride;
+  return af::mbconv_plan(&p) ? 1 : 0;
+}
+
+int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
+  if (ctx == nullptr || d == nullptr) return fail(AF_ERR_INVALID, "af_mbconv_fused: null argument");
+  if (d->in == nullptr || d->w1 == nullptr || d->bias1 == nullptr || d->dw_w == nullptr || d->bias2 == nullptr ||
+      d->w2 == nullptr || d->bias3 == nullptr || d->out == nullptr)
+    return fail(AF_ERR_INVALID, "af_mbconv_fused: null tensor");
+  af::MbParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;
+  if (!af::mbconv_plan(&p)) return fail(AF_ERR_INVALID, "af_mbconv_fused: unsupported shape");
+  if (d->residual != nullptr && (d->stride != 1 || d->res_stride % 8 != 0 || d->res_stride < d->cout))
+    return fail(AF_ERR_INVALID, "af_mbconv_fused: a residual needs stride 1 and res_stride % 8 == 0");
+  p.bias1 = d->bias1; p.dw_w = d->dw_w; p.bias2 = d->bias2; p.bias3 = d->bias3;
+  p.residual = static_cast<const __half*>(d->residual);
+  p.res_stride = d->res_stride;
+  af::MbTensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cin) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
+                                static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.BW), static_cast<cuuint32_t>(p.BH), 1};
+    if (!encode_map(ctx, &maps.x, d->in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(p.nc) * 64};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, 64};
+    if (!encode_map(ctx, &maps.w1, d->w1, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t kpad = static_cast<cuuint64_t>(p.nc) * 64;
+    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(p.cout_pad)};
+    const cuuint64_t strides[1] = {kpad * 2};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.cout_pad)};
+    if (!encode_map(ctx, &maps.w2, d->w2, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cout) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
+                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * p.Wo, pix_b * p.Wo * p.Ho};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
+    if (!encode_map(ctx, &maps.out, d->out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  const int sms = ctx->sm_count;
+  return dispatch(ctx, stream, "af_mbconv_fused",
+                  [=](cudaStream_t s) { return af::launch_mbconv_fused(maps, p, sms, s); });
 }
 
 int af_stem_conv3x3s2_c32(af_ctx* ctx, const float* frames, const float* w27, const float* scale, const float* bias,

@@ -1,0 +1,427 @@
+// Fused inverted-residual block kernel (see mbconv_fused.cuh for the data flow and the reference call sites).
+#include "mbconv_fused.cuh"
+
+#include <cstdlib>
+
+#include "dw_strip.cuh"
+#include "ptx.cuh"
+
+namespace af {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kEPitch = 144;      // bytes per pixel of the expanded tile E: 64 fp16 + 16 B pad (conflict-free 16-B row writes)
+constexpr int kD2Col = 384;       // TMEM column of the project accumulator (D1 buffers: 2 x Mtiles x 64 <= 384 columns)
+constexpr int kComputeThreads = 256;
+constexpr int kComputeBarrier = 1;
+
+struct __align__(8) MbCtrl {
+  uint64_t x_full[2], x_empty[2];
+  uint64_t w_full;
+  uint64_t d1_full[2], d1_empty[2];
+  uint64_t a2_full[2], a2_empty[2];
+  uint64_t d2_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+
+template <int S>
+__global__ void __launch_bounds__(kMbThreads, 1)
+mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* s_x = smem;
+  uint8_t* s_w1 = smem + p.off_w1;
+  uint8_t* s_w2 = smem + p.off_w2;
+  uint8_t* s_a2 = smem + p.off_a2;
+  uint8_t* s_out = smem + p.off_out;
+  uint8_t* s_e = smem + p.off_e;
+  float* s_f = reinterpret_cast<float*>(smem + p.off_f32);
+  MbCtrl* ctrl = reinterpret_cast<MbCtrl*>(smem + p.off_ctrl);
+  const int CE = p.nc * 64;
+  float* s_dw = s_f;              // [9][CE]
+  float* s_b1 = s_f + 9 * CE;     // [CE]
+  float* s_b2 = s_b1 + CE;        // [CE]
+  float* s_b3 = s_b2 + CE;        // [64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x_buf_bytes = p.Mtiles * 16384;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int n_tiles = tiles_per_img * p.N;
+  const uint32_t w2_chunk = static_cast<uint32_t>(p.cout_pad) * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->x_full[i], 1);
+      mbar_init(&ctrl->x_empty[i], 1);
+      mbar_init(&ctrl->d1_full[i], 1);
+      mbar_init(&ctrl->d1_empty[i], kComputeThreads / 32);
+      mbar_init(&ctrl->a2_full[i], 1);
+      mbar_init(&ctrl->a2_empty[i], 1);
+    }
+    mbar_init(&ctrl->w_full, 1);
+    mbar_init(&ctrl->d2_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.x);
+    tma_prefetch_desc(&maps.w1);
+    tma_prefetch_desc(&maps.w2);
+    tma_prefetch_desc(&maps.out);
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctrl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // launch constants -> shared memory; the A2 operand buffers start as zeros so that channel columns a partial
+    // chunk never writes hold finite values (their weights are zero)
+    const int ct = threadIdx.x - 64;
+    for (int i = ct; i < 2 * 16384 / 16; i += kComputeThreads)
+      reinterpret_cast<uint4*>(s_a2)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = ct; i < 9 * CE; i += kComputeThreads) s_dw[i] = p.dw_w[i];
+    for (int i = ct; i < CE; i += kComputeThreads) {
+      s_b1[i] = p.bias1[i];
+      s_b2[i] = p.bias2[i];
+    }
+    if (ct < 64) s_b3[ct] = ct < p.cout_pad ? p.bias3[ct] : 0.f;
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ============================ TMA producer: weights once, then one input window per tile ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctrl->w_full, static_cast<uint32_t>(p.nc) * (8192u + w2_chunk));
+      for (int c = 0; c < p.nc; ++c) tma_load_2d(s_w1 + c * 8192, &maps.w1, &ctrl->w_full, 0, c * 64);
+      for (int c = 0; c < p.nc; ++c) tma_load_2d(s_w2 + c * w2_chunk, &maps.w2, &ctrl->w_full, c * 64, 0);
+      pdl_wait_prior_grid();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int xb = it % p.XB;
+        const uint32_t ph = static_cast<uint32_t>(it / p.XB) & 1u;
+        wait_backoff(&ctrl->x_empty[xb], ph ^ 1u);
+        const int n = tile / tiles_per_img;
+        const int r = tile - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        mbar_arrive_expect_tx(&ctrl->x_full[xb], static_cast<uint32_t>(p.n_rows) * 128u);
+        tma_load_4d(s_x + xb * x_buf_bytes, &maps.x, &ctrl->x_full[xb], 0, tw_i * p.TW * S - 1, th_i * p.TH * S - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_f16_f32(128, 64);
+      const uint32_t idesc2 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.cout_pad));
+      const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                                      static_cast<int>(gridDim.x)
+                                                : 0;
+      const int G = my_tiles * p.nc;   // channel chunks this CTA goes through, across all its tiles
+      wait_backoff(&ctrl->w_full, 0);
+      tc_fence_after();
+      auto issue_expand = [&](int g) {
+        const int it = g / p.nc, c = g - it * p.nc;
+        const int xb = it % p.XB;
+        if (c == 0) wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
+        wait_backoff(&ctrl->d1_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t xa = smem_u32(s_x + xb * x_buf_bytes);
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_w1 + c * 8192));
+        for (int m = 0; m < p.Mtiles; ++m) {
+          const uint64_t da = make_smem_desc_sw128(xa + static_cast<uint32_t>(m) * 16384u);
+          const uint32_t d = tmem_base + static_cast<uint32_t>((g & 1) * (p.Mtiles * 64) + m * 64);
+          for (int k = 0; k < p.k1steps; ++k)
+            umma_f16_ss(d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc1, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&ctrl->d1_full[g & 1]);
+        if (c == p.nc - 1) umma_commit(&ctrl->x_empty[xb]);   // the tile's input window has been consumed
+      };
+      if (G > 0) issue_expand(0);
+      if (G > 1) issue_expand(1);
+      for (int g = 0; g < G; ++g) {
+        const int it = g / p.nc, c = g - it * p.nc;
+        wait_backoff(&ctrl->a2_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
+        tc_fence_after();
+        const int vc = min(64, p.Cexp - c * 64);
+        const int ks = (vc + 15) >> 4;
+        const uint64_t da = make_smem_desc_sw128(smem_u32(s_a2 + (g & 1) * 16384));
+        const uint64_t db = make_smem_desc_sw128(smem_u32(s_w2 + c * w2_chunk));
+        for (int k = 0; k < ks; ++k)
+          umma_f16_ss(tmem_base + kD2Col, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc2,
+                      (c | k) != 0 ? 1u : 0u);
+        umma_commit(&ctrl->a2_empty[g & 1]);
+        if (c == p.nc - 1) umma_commit(&ctrl->d2_full);
+        if (g + 2 < G) issue_expand(g + 2);
+      }
+    }
+  } else {
+    // ============================ compute warps (8): expand epilogue, depthwise conv, project epilogue ============================
+    const int ct = threadIdx.x - 64;          // 0..255
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int colhalf = (warp - 2) >> 2;      // which 32 of a chunk's 64 columns (expand) / which 16-column groups (project)
+    int by[3], bx[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const int row = m * 128 + quarter * 32 + lane;
+      by[m] = row / p.BW;
+      bx[m] = row - by[m] * p.BW;
+    }
+    const int prow = quarter * 32 + lane;     // output pixel (row of the project accumulator) of this thread
+    const int pth = prow / p.TW, ptw = prow - pth * p.TW;
+    const int pairs = p.TW >> 1;
+    const int q_count = pairs * p.strips;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    pdl_wait_prior_grid();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / tiles_per_img;
+      const int rr = tile - n * tiles_per_img;
+      const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
+      const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
+      bool pvalid[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int iy = iy0 + by[m], ix = ix0 + bx[m];
+        pvalid[m] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      }
+      for (int c = 0; c < p.nc; ++c) {
+        const int g = it * p.nc + c;
+        const int vc = min(64, p.Cexp - c * 64);
+        // ---- expand epilogue: D1 (TMEM) -> +bias, ReLU6, zero outside the image -> E (smem, fp16)
+        mbar_wait(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
+        tc_fence_after();
+        if (colhalf * 32 < vc) {
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            if (m < p.Mtiles && m * 128 + quarter * 32 < p.n_rows) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(tmem_base + lane_sel + static_cast<uint32_t>((g & 1) * (p.Mtiles * 64) + m * 64 + colhalf * 32), v);
+              tmem_ld_wait();
+              const int row = m * 128 + quarter * 32 + lane;
+              if (row < p.n_rows) {
+                uint8_t* erow = s_e + row * kEPitch + colhalf * 64;
+                const float* b1 = s_b1 + c * 64 + colhalf * 32;
+                const bool ok = pvalid[m];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 ba = *reinterpret_cast<const float4*>(b1 + i * 8);
+                  const float4 bb = *reinterpret_cast<const float4*>(b1 + i * 8 + 4);
+                  const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                  uint4 ov;
+                  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    __half2 h = __floats2half2_rn(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
+                                                  __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
+                    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+                    oh2[j] = h;
+                  }
+                  if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
+                  *reinterpret_cast<uint4*>(erow + i * 16) = ov;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->d1_empty[g & 1]);
+        named_barrier_sync(kComputeBarrier, kComputeThreads);   // E complete
+        // ---- depthwise 3x3 over E -> A2 (swizzled K-major operand of the project GEMM)
+        mbar_wait(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
+        {
+          const int n_ch = vc >> 2;             // 4-channel groups of this chunk: 16, 8 or 4
+          const int ch4 = ct & (n_ch - 1);
+          const int q0 = ct / n_ch;
+          const int q_step = kComputeThreads / n_ch;
+          if (q0 < q_count) {
+            const int ce = c * 64 + ch4 * 4;
+            float2 w[9][2], bias[2];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float4 wv = *reinterpret_cast<const float4*>(s_dw + t * CE + ce);
+              w[t][0] = make_float2(wv.x, wv.y);
+              w[t][1] = make_float2(wv.z, wv.w);
+            }
+            const float4 b2 = *reinterpret_cast<const float4*>(s_b2 + ce);
+            bias[0] = make_float2(b2.x, b2.y);
+            bias[1] = make_float2(b2.z, b2.w);
+            uint8_t* a2 = s_a2 + (g & 1) * 16384;
+            for (int q = q0; q < q_count; q += q_step) {
+              const int strip = q / pairs, xp = q - strip * pairs;
+              const uint8_t* in = s_e + ((strip * kMbRO * S) * p.BW + xp * 2 * S) * kEPitch + ch4 * 8;
+              const int prow0 = strip * kMbRO * p.TW + 2 * xp;
+              uint8_t* out0 = a2 + prow0 * 128 + (((ch4 >> 1) ^ (prow0 & 7)) << 4) + (ch4 & 1) * 8;
+              uint8_t* out1 = a2 + (prow0 + 1) * 128 + (((ch4 >> 1) ^ ((prow0 + 1) & 7)) << 4) + (ch4 & 1) * 8;
+              dw_strip<S, kMbRO>(in, kEPitch, p.BW * kEPitch, out0, out1, p.TW * 128, w, bias, 2);
+            }
+          }
+        }
+        fence_proxy_async();                                    // A2 writes -> visible to the tensor core
+        if (c == p.nc - 1 && ct == 0) tma_store_wait_read0();   // the previous tile's store has released the staging tile
+        named_barrier_sync(kComputeBarrier, kComputeThreads);   // A2 complete; nobody reads E any more
+        if (ct == 0) mbar_arrive(&ctrl->a2_full[g & 1]);
+      }
+      // ---- project epilogue: D2 (TMEM) -> +bias (+ residual) -> fp16 -> swizzled staging tile -> TMA store
+      mbar_wait(&ctrl->d2_full, static_cast<uint32_t>(it) & 1u);
+      tc_fence_after();
+      if (quarter * 32 < p.TW * p.TH) {
+        const int oy = th_i * p.TH + pth, ox = tw_i * p.TW + ptw;
+        const bool valid = prow < p.TW * p.TH && oy < p.Ho && ox < p.Wo;
+        const __half* rp = nullptr;
+        if (p.residual != nullptr && valid)
+          rp = p.residual + ((static_cast<long long>(n) * p.Ho + oy) * p.Wo + ox) * p.res_stride;
+        uint8_t* srow = s_out + prow * 128;
+        const int ncg = p.cout_pad >> 4;
+        for (int cg = colhalf; cg < ncg; cg += 2) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_sel + static_cast<uint32_t>(kD2Col + cg * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int co = cg * 16 + h * 8;
+            const float4 ba = *reinterpret_cast<const float4*>(s_b3 + co);
+            const float4 bb = *reinterpret_cast<const float4*>(s_b3 + co + 4);
+            float x[8] = {__uint_as_float(v[h * 8 + 0]) + ba.x, __uint_as_float(v[h * 8 + 1]) + ba.y,
+                          __uint_as_float(v[h * 8 + 2]) + ba.z, __uint_as_float(v[h * 8 + 3]) + ba.w,
+                          __uint_as_float(v[h * 8 + 4]) + bb.x, __uint_as_float(v[h * 8 + 5]) + bb.y,
+                          __uint_as_float(v[h * 8 + 6]) + bb.z, __uint_as_float(v[h * 8 + 7]) + bb.w};
+            if (rp != nullptr && co + 8 <= p.Cout) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + co));
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(rh[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+              }
+            }
+            uint4 ov;
+            __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+            *reinterpret_cast<uint4*>(srow + (((cg * 2 + h) ^ (prow & 7)) << 4)) = ov;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_barrier_sync(kComputeBarrier, kComputeThreads);
+      if (ct == 0) {
+        tma_store_4d(&maps.out, s_out, 0, tw_i * p.TW, th_i * p.TH, n);
+        tma_store_commit();
+      }
+    }
+    if (ct == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool mbconv_plan(MbParams* p) {
+  if (p->S != 1 && p->S != 2) return false;
+  if (p->Cin < 8 || p->Cin > 64 || p->Cin % 8 != 0) return false;
+  if (p->Cout < 8 || p->Cout > 64 || p->Cout % 8 != 0) return false;
+  if (p->Cexp < 16 || p->Cexp % 16 != 0) return false;
+  const int tail = p->Cexp % 64;
+  if (tail == 48) return false;               // chunk widths are 16, 32 or 64 channels
+  if (p->H < 4 || p->W < 4 || p->N < 1) return false;
+  p->Ho = (p->H - 1) / p->S + 1;
+  p->Wo = (p->W - 1) / p->S + 1;
+  p->nc = (p->Cexp + 63) / 64;
+  p->k1steps = (p->Cin + 15) / 16;
+  p->cout_pad = (p->Cout + 15) / 16 * 16;
+  // output tile: 128 pixels (stride 1) or 64 pixels (stride 2: the halo'd input window must fit three 128-row MMA tiles)
+  const int cand1[3][2] = {{16, 8}, {8, 16}, {32, 4}};
+  const int cand2[2][2] = {{8, 8}, {16, 4}};
+  long long best = -1;
+  const int ncand = p->S == 1 ? 3 : 2;
+  for (int i = 0; i < ncand; ++i) {
+    const int tw = p->S == 1 ? cand1[i][0] : cand2[i][0];
+    const int th = p->S == 1 ? cand1[i][1] : cand2[i][1];
+    const long long tiles = 1LL * ((p->Wo + tw - 1) / tw) * ((p->Ho + th - 1) / th);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      p->TW = tw;
+      p->TH = th;
+    }
+  }
+  p->strips = p->TH / kMbRO;
+  const int edge = p->S == 1 ? 2 : 1;
+  p->BW = p->TW * p->S + edge;
+  p->BH = p->TH * p->S + edge;
+  p->n_rows = p->BW * p->BH;
+  p->Mtiles = (p->n_rows + 127) / 128;
+  if (p->Mtiles > 3) return false;
+  p->tiles_w = (p->Wo + p->TW - 1) / p->TW;
+  p->tiles_h = (p->Ho + p->TH - 1) / p->TH;
+  for (int xb = 2; xb >= 1; --xb) {
+    int off = xb * p->Mtiles * 16384;
+    p->off_w1 = off;
+    off += p->nc * 8192;
+    p->off_w2 = off;
+    off += p->nc * p->cout_pad * 128;
+    off = (off + 1023) & ~1023;
+    p->off_a2 = off;
+    off += 2 * 16384;
+    p->off_out = off;
+    off += 16384;
+    p->off_e = off;
+    off += (p->n_rows * kEPitch + 127) & ~127;
+    p->off_f32 = off;
+    off += (11 * p->nc * 64 + 64) * 4;
+    off = (off + 15) & ~15;
+    p->off_ctrl = off;
+    off += 256;
+    p->smem = off;
+    p->XB = xb;
+    if (off <= 227 * 1024) return true;
+  }
+  return false;
+}
+
+cudaError_t launch_mbconv_fused(const MbTensorMaps& maps, const MbParams& p, int sm_count, cudaStream_t stream) {
+  static_assert(sizeof(MbCtrl) <= 256, "ctrl block too large");
+  using Kern = void (*)(const MbTensorMaps, const MbParams);
+  Kern kern = p.S == 1 ? mbconv_fused_kernel<1> : mbconv_fused_kernel<2>;
+  static bool attr_set[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev][p.S - 1]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev][p.S - 1] = true;
+  }
+  const long long n_tiles = 1LL * p.tiles_w * p.tiles_h * p.N;
+  int grid = n_tiles < sm_count ? static_cast<int>(n_tiles) : sm_count;
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kMbThreads);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = getenv("AF_NO_PDL") == nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, maps, p);
+}
+
+}  // namespace af

@@ -9,7 +9,7 @@ from ctypes import byref, c_void_p
 import torch
 
 from . import _lib
-from ._lib import AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6, ConvDesc, check
+from ._lib import AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6, ConvDesc, MbconvDesc, check
 
 BLOCK_K = 64
 
@@ -104,6 +104,39 @@ def pack_stem(weight, scale, bias, stride, pad, act, device=None, kpad=None):
     pc = pack_conv(flat, scale, bias, 1, 0, act, device=device)
     pc.stem = dict(kh=kh, kw=kw, stride=stride, pad=pad, kpad=kpad)
     return pc
+
+
+class PackedMbconv:
+    """An inverted-residual block (expand 1x1 -> depthwise 3x3 -> project 1x1, BatchNorms folded) in the layout of
+    af_mbconv_fused: every BN scale is folded into the weights, the kernel only adds biases."""
+
+    def __init__(self, w1, b1, dw, b2, w2, b3, cin, cexp, cout, stride):
+        self.w1, self.b1, self.dw, self.b2, self.w2, self.b3 = w1, b1, dw, b2, w2, b3
+        self.cin, self.cexp, self.cout, self.stride = cin, cexp, cout, stride
+
+
+def mbconv_supported(n, h, w, cin, cexp, cout, stride):
+    return bool(_lib.load().af_mbconv_fused_supported(int(n), int(h), int(w), int(cin), int(cexp), int(cout),
+                                                      int(stride)))
+
+
+def pack_mbconv(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, device=None):
+    """w_exp (cexp, cin[,1,1]), w_dw (cexp, 1, 3, 3), w_proj (cout, cexp[,1,1]) fp32 in torch layout; (s, b) = folded
+    BatchNorm of each conv.  Returns a PackedMbconv on `device`."""
+    w_exp = w_exp.detach().float().flatten(1)
+    w_proj = w_proj.detach().float().flatten(1)
+    device = device or w_exp.device
+    cexp, cin = w_exp.shape
+    cout = w_proj.shape[0]
+    ce = round_up(cexp, 64)
+    e = pack_conv(w_exp, s1, b1, act=AF_ACT_RELU6, block_n=64, device=device, fold_scale=True)
+    pj = pack_conv(w_proj, s3, b3, act=AF_ACT_NONE, block_n=round_up(cout, 16), device=device, fold_scale=True)
+    assert e.w.shape == (ce, 64) and pj.w.shape == (round_up(cout, 16), ce), (e.w.shape, pj.w.shape)
+    dw = torch.zeros(9, ce, dtype=torch.float32, device=device)
+    dw[:, :cexp] = (w_dw.detach().float().reshape(cexp, 9).to(device) * s2.detach().float().to(device)[:, None]).t()
+    bias2 = torch.zeros(ce, dtype=torch.float32, device=device)
+    bias2[:cexp] = b2.detach().float().to(device)
+    return PackedMbconv(e.w, e.bias, dw.contiguous(), bias2, pj.w, pj.bias, cin, cexp, cout, stride)
 
 
 class Workspace:
@@ -279,6 +312,24 @@ class Engine:
                                              w, act, self._stream()), "af_stem_conv3x3s2_c32")
         self._count()
         self.keep(frames, w27, scale, bias, out)
+        return out
+
+    def mbconv(self, x, pm, residual=None):
+        """Fused inverted-residual block: x NHWC fp16 (n,h,w,cin) contiguous -> (n,ho,wo,cout)."""
+        n, h, w, cin = x.shape
+        assert cin == pm.cin and x.is_contiguous()
+        s = pm.stride
+        ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+        out = self.empty((n, ho, wo, pm.cout), torch.float16)
+        d = MbconvDesc()
+        d.in_, d.w1, d.bias1, d.dw_w, d.bias2 = x.data_ptr(), pm.w1.data_ptr(), pm.b1.data_ptr(), pm.dw.data_ptr(), pm.b2.data_ptr()
+        d.w2, d.bias3, d.out = pm.w2.data_ptr(), pm.b3.data_ptr(), out.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.n, d.h, d.w_, d.cin, d.cexp, d.cout, d.stride = n, h, w, cin, pm.cexp, pm.cout, s
+        d.res_stride = residual.stride(-2) if residual is not None else 0
+        check(self.lib.af_mbconv_fused(self.h, byref(d), self._stream()), "af_mbconv_fused")
+        self._count()
+        self.keep(x, pm.w1, pm.b1, pm.dw, pm.b2, pm.w2, pm.b3, residual, out)
         return out
 
     def dwconv3x3(self, x, w9c, scale, bias, stride, act=AF_ACT_RELU6):

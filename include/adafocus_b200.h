@@ -114,6 +114,32 @@ int af_stem_conv_fused(af_ctx* ctx, const float* frames, const int32_t* yx, int 
                        const float* scale, const float* bias, void* out, int N, int H, int W, int P, int cout, int KH,
                        int KW, int stride, int pad, int act, void* stream);
 
+/* Fused MobileNet-V2 inverted-residual block (ACT/models/mobilenet.py:42-68, InvertedResidual.forward with
+ * expand_ratio != 1): 1x1 expand + BN + ReLU6 -> depthwise 3x3 (stride 1|2, pad 1) + BN + ReLU6 -> 1x1 project + BN
+ * (+ residual) as ONE kernel; the expanded tensor stays in shared memory / TMEM.
+ *   in  : NHWC fp16 (n, h, w, cin) contiguous            out : NHWC fp16 (n, ho, wo, cout) contiguous
+ *   w1  : packed fp16 [ceil(cexp/64)*64][64] (k = ci, BN scale folded in, zero padded)   bias1: fp32 [ceil(cexp/64)*64]
+ *   dw_w: fp32 [9][ceil(cexp/64)*64] with the BN scale folded in (tap-major), zero padded; bias2 likewise
+ *   w2  : packed fp16 [ceil(cout/16)*16][ceil(cexp/64)*64] (BN scale folded in)           bias3: fp32 [ceil(cout/16)*16]
+ *   residual: NHWC fp16 (n, ho, wo, cout) with pixel stride res_stride, or NULL.
+ * af_mbconv_fused_supported is a host-side query (no device work): 1 when the shape is handled (cin, cout <= 64 and
+ * multiples of 8; cexp a multiple of 16 whose last 64-channel chunk holds 16, 32 or 64 channels), else 0. */
+typedef struct af_mbconv_desc {
+  const void* in;
+  const void* w1;
+  const float* bias1;
+  const float* dw_w;
+  const float* bias2;
+  const void* w2;
+  const float* bias3;
+  const void* residual;
+  void* out;
+  int32_t n, h, w_, cin, cexp, cout, stride;
+  int64_t res_stride;
+} af_mbconv_desc;
+int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
+int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream);
+
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
  * w27 fp32 [27][32] with k = (r*3+s)*3 + c; scale / bias fp32 [32]. */

@@ -240,6 +240,43 @@ def test_dwconv3x3(eng, stride, c, hw, n):
     assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("cin,cexp,cout,stride,hw,n,res", [
+    (32, 96, 24, 2, 112, 2, False), (24, 144, 24, 1, 56, 2, True), (24, 144, 32, 2, 56, 3, False),
+    (32, 192, 32, 1, 28, 5, True), (32, 192, 64, 2, 28, 4, False), (16, 96, 24, 2, 30, 3, False),
+    (24, 144, 24, 1, 20, 150, True), (64, 64, 64, 1, 9, 2, True), (8, 16, 8, 1, 7, 1, False),
+    (32, 192, 64, 2, 14, 300, False)])
+def test_mbconv_fused(eng, cin, cexp, cout, stride, hw, n, res):
+    """Fused inverted-residual block (expand -> depthwise -> project) against the three torch convolutions with the
+    fp16 roundings of the unfused pipeline (every MobileNet-V2 block shape the plan fuses, partial tiles, more tiles
+    than SMs so that the persistent loop and both input buffers are exercised)."""
+    from adafocus_b200.engine import mbconv_supported, pack_mbconv
+    assert mbconv_supported(n, hw, hw, cin, cexp, cout, stride)
+    torch.manual_seed(cexp + hw)
+    x = torch.randn(n, hw, hw, cin, device=DEV).half()
+    w1 = torch.randn(cexp, cin, device=DEV) / math.sqrt(cin)
+    wd = torch.randn(cexp, 1, 3, 3, device=DEV) / 3
+    w2 = torch.randn(cout, cexp, device=DEV) / math.sqrt(cexp)
+    s1, b1 = torch.rand(cexp, device=DEV) + 0.5, torch.randn(cexp, device=DEV) * 0.2
+    s2, b2 = torch.rand(cexp, device=DEV) + 0.5, torch.randn(cexp, device=DEV) * 0.2
+    s3, b3 = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV) * 0.2
+    pm = pack_mbconv(w1, s1, b1, wd, s2, b2, w2, s3, b3, stride, device=DEV)
+    out = eng.mbconv(x, pm, residual=x if res else None)
+    torch.cuda.synchronize()
+    xf = x.float().permute(0, 3, 1, 2)
+    # the kernel folds the BN scales into fp16 weights: mirror that rounding
+    w1q = (w1 * s1[:, None]).half().float()
+    w2q = (w2 * s3[:, None]).half().float()
+    e = (F.conv2d(xf, w1q[:, :, None, None]) + b1.view(1, -1, 1, 1)).clamp(0, 6).half().float()
+    d = (F.conv2d(e, wd * s2.view(-1, 1, 1, 1), None, stride, 1, 1, cexp) + b2.view(1, -1, 1, 1)).clamp(0, 6).half().float()
+    ref = F.conv2d(d, w2q[:, :, None, None]) + b3.view(1, -1, 1, 1)
+    if res:
+        ref = ref + xf
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    err = (out.float() - ref).abs().max().item()
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3 * max(1.0, ref.abs().max().item())), err
+
+
 @pytest.mark.parametrize("hw", [64, 72, 9])
 def test_maxpool_bit_exact(eng, hw):
     x = torch.randn(4, hw, hw, 64, device=DEV).half()
