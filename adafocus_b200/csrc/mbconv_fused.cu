@@ -14,15 +14,19 @@ namespace {
 
 constexpr int kEPitch = 144;      // bytes per pixel of the expanded tile E: 64 fp16 + 16 B pad (conflict-free 16-B row writes)
 constexpr int kD2Col = 384;       // TMEM column of the project accumulator (D1 buffers: 2 x Mtiles x 64 <= 384 columns)
-constexpr int kComputeThreads = 256;
-constexpr int kComputeBarrier = 1;
+constexpr int kGroupThreads = 256;   // threads of each compute group (8 warps)
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kFirstGroupWarp = 3;   // warps 0-2: TMA producer, expand MMA issuer, project MMA issuer
+static_assert(kMbThreads == (kFirstGroupWarp + 2 * kGroupWarps) * 32, "thread roles");
+constexpr int kEpilogueBarrier = 1;  // named barrier of the epilogue group (staging tile hand-over)
 
 struct __align__(8) MbCtrl {
   uint64_t x_full[2], x_empty[2];
   uint64_t w_full;
   uint64_t d1_full[2], d1_empty[2];
+  uint64_t e_full[2], e_empty[2];
   uint64_t a2_full[2], a2_empty[2];
-  uint64_t d2_full;
+  uint64_t d2_full[2], d2_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -34,6 +38,7 @@ __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
 template <int S>
 __global__ void __launch_bounds__(kMbThreads, 1)
 mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p) {
+  constexpr int RO = S == 1 ? 4 : 2;   // output rows per depthwise strip (256 strips of work per 64-channel chunk)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* s_x = smem;
@@ -55,18 +60,22 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int n_tiles = tiles_per_img * p.N;
   const uint32_t w2_chunk = static_cast<uint32_t>(p.cout_pad) * 128u;
+  const int d1_cols = p.Mtiles * 64;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->x_full[i], 1);
       mbar_init(&ctrl->x_empty[i], 1);
       mbar_init(&ctrl->d1_full[i], 1);
-      mbar_init(&ctrl->d1_empty[i], kComputeThreads / 32);
-      mbar_init(&ctrl->a2_full[i], 1);
+      mbar_init(&ctrl->d1_empty[i], kGroupWarps);
+      mbar_init(&ctrl->e_full[i], kGroupWarps);
+      mbar_init(&ctrl->e_empty[i], kGroupWarps);
+      mbar_init(&ctrl->a2_full[i], kGroupWarps);
       mbar_init(&ctrl->a2_empty[i], 1);
+      mbar_init(&ctrl->d2_full[i], 1);
+      mbar_init(&ctrl->d2_empty[i], kGroupWarps);
     }
     mbar_init(&ctrl->w_full, 1);
-    mbar_init(&ctrl->d2_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.x);
     tma_prefetch_desc(&maps.w1);
@@ -77,14 +86,14 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
     tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
   }
-  if (warp >= 2) {
+  if (warp >= kFirstGroupWarp) {
     // launch constants -> shared memory; the A2 operand buffers start as zeros so that channel columns a partial
     // chunk never writes hold finite values (their weights are zero)
-    const int ct = threadIdx.x - 64;
-    for (int i = ct; i < 2 * 16384 / 16; i += kComputeThreads)
+    const int ct = threadIdx.x - kFirstGroupWarp * 32;
+    for (int i = ct; i < 2 * 16384 / 16; i += 2 * kGroupThreads)
       reinterpret_cast<uint4*>(s_a2)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = ct; i < 9 * CE; i += kComputeThreads) s_dw[i] = p.dw_w[i];
-    for (int i = ct; i < CE; i += kComputeThreads) {
+    for (int i = ct; i < 9 * CE; i += 2 * kGroupThreads) s_dw[i] = p.dw_w[i];
+    for (int i = ct; i < CE; i += 2 * kGroupThreads) {
       s_b1[i] = p.bias1[i];
       s_b2[i] = p.bias2[i];
     }
@@ -108,7 +117,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int xb = it % p.XB;
         const uint32_t ph = static_cast<uint32_t>(it / p.XB) & 1u;
-        wait_backoff(&ctrl->x_empty[xb], ph ^ 1u);
+        while (!mbar_try_wait(&ctrl->x_empty[xb], ph ^ 1u)) __nanosleep(256);
         const int n = tile / tiles_per_img;
         const int r = tile - n * tiles_per_img;
         const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
@@ -117,18 +126,18 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
+    // ============================ expand MMA issuer: D1[g & 1] = X * W1[chunk]^T as soon as the buffer is free ============================
     if (lane == 0) {
       const uint32_t idesc1 = make_idesc_f16_f32(128, 64);
-      const uint32_t idesc2 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.cout_pad));
-      const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                                      static_cast<int>(gridDim.x)
-                                                : 0;
+      const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
+                               ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                     static_cast<int>(gridDim.x)
+                               : 0;
       const int G = my_tiles * p.nc;   // channel chunks this CTA goes through, across all its tiles
       wait_backoff(&ctrl->w_full, 0);
       tc_fence_after();
-      auto issue_expand = [&](int g) {
-        const int it = g / p.nc, c = g - it * p.nc;
+      int it = 0, c = 0;
+      for (int g = 0; g < G; ++g) {
         const int xb = it % p.XB;
         if (c == 0) wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
         wait_backoff(&ctrl->d1_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
@@ -137,36 +146,58 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         const uint64_t db = make_smem_desc_sw128(smem_u32(s_w1 + c * 8192));
         for (int m = 0; m < p.Mtiles; ++m) {
           const uint64_t da = make_smem_desc_sw128(xa + static_cast<uint32_t>(m) * 16384u);
-          const uint32_t d = tmem_base + static_cast<uint32_t>((g & 1) * (p.Mtiles * 64) + m * 64);
+          const uint32_t d = tmem_base + static_cast<uint32_t>((g & 1) * d1_cols + m * 64);
           for (int k = 0; k < p.k1steps; ++k)
             umma_f16_ss(d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc1, k != 0 ? 1u : 0u);
         }
         umma_commit(&ctrl->d1_full[g & 1]);
         if (c == p.nc - 1) umma_commit(&ctrl->x_empty[xb]);   // the tile's input window has been consumed
-      };
-      if (G > 0) issue_expand(0);
-      if (G > 1) issue_expand(1);
+        if (++c == p.nc) {
+          c = 0;
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================ project MMA issuer: D2[it & 1] += A2[g & 1] * W2[:, chunk]^T ============================
+    if (lane == 0) {
+      const uint32_t idesc2 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.cout_pad));
+      const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
+                               ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                     static_cast<int>(gridDim.x)
+                               : 0;
+      const int G = my_tiles * p.nc;
+      wait_backoff(&ctrl->w_full, 0);
+      tc_fence_after();
+      int it = 0, c = 0;
       for (int g = 0; g < G; ++g) {
-        const int it = g / p.nc, c = g - it * p.nc;
+        if (c == 0) {
+          // the accumulator buffer of this tile was last read by the epilogue of tile it-2
+          wait_backoff(&ctrl->d2_empty[it & 1], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
+        }
         wait_backoff(&ctrl->a2_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
         tc_fence_after();
         const int vc = min(64, p.Cexp - c * 64);
         const int ks = (vc + 15) >> 4;
         const uint64_t da = make_smem_desc_sw128(smem_u32(s_a2 + (g & 1) * 16384));
         const uint64_t db = make_smem_desc_sw128(smem_u32(s_w2 + c * w2_chunk));
+        const uint32_t d2 = tmem_base + static_cast<uint32_t>(kD2Col + (it & 1) * 64);
         for (int k = 0; k < ks; ++k)
-          umma_f16_ss(tmem_base + kD2Col, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc2,
+          umma_f16_ss(d2, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc2,
                       (c | k) != 0 ? 1u : 0u);
         umma_commit(&ctrl->a2_empty[g & 1]);
-        if (c == p.nc - 1) umma_commit(&ctrl->d2_full);
-        if (g + 2 < G) issue_expand(g + 2);
+        if (c == p.nc - 1) umma_commit(&ctrl->d2_full[it & 1]);
+        if (++c == p.nc) {
+          c = 0;
+          ++it;
+        }
       }
     }
-  } else {
-    // ============================ compute warps (8): expand epilogue, depthwise conv, project epilogue ============================
-    const int ct = threadIdx.x - 64;          // 0..255
+  } else if (warp < kFirstGroupWarp + kGroupWarps) {
+    // ============================ epilogue group (8 warps): D1 -> E per chunk, D2 -> output per tile ============================
+    const int et = threadIdx.x - kFirstGroupWarp * 32;   // 0..255
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int colhalf = (warp - 2) >> 2;      // which 32 of a chunk's 64 columns (expand) / which 16-column groups (project)
+    const int colhalf = (warp - kFirstGroupWarp) >> 2;   // which 32 of a chunk's 64 columns (expand) / which 16-column groups (project)
     int by[3], bx[3];
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
@@ -176,103 +207,18 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
     }
     const int prow = quarter * 32 + lane;     // output pixel (row of the project accumulator) of this thread
     const int pth = prow / p.TW, ptw = prow - pth * p.TW;
-    const int pairs = p.TW >> 1;
-    const int q_count = pairs * p.strips;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     pdl_wait_prior_grid();
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+
+    // project epilogue of tile `pit` (this CTA's pit-th tile): D2 (TMEM) -> +bias (+ residual) -> fp16 -> staging -> TMA store
+    auto project_epilogue = [&](int pit, int tile) {
       const int n = tile / tiles_per_img;
       const int rr = tile - n * tiles_per_img;
       const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
-      const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
-      bool pvalid[3];
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const int iy = iy0 + by[m], ix = ix0 + bx[m];
-        pvalid[m] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      }
-      for (int c = 0; c < p.nc; ++c) {
-        const int g = it * p.nc + c;
-        const int vc = min(64, p.Cexp - c * 64);
-        // ---- expand epilogue: D1 (TMEM) -> +bias, ReLU6, zero outside the image -> E (smem, fp16)
-        mbar_wait(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
-        tc_fence_after();
-        if (colhalf * 32 < vc) {
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            if (m < p.Mtiles && m * 128 + quarter * 32 < p.n_rows) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(tmem_base + lane_sel + static_cast<uint32_t>((g & 1) * (p.Mtiles * 64) + m * 64 + colhalf * 32), v);
-              tmem_ld_wait();
-              const int row = m * 128 + quarter * 32 + lane;
-              if (row < p.n_rows) {
-                uint8_t* erow = s_e + row * kEPitch + colhalf * 64;
-                const float* b1 = s_b1 + c * 64 + colhalf * 32;
-                const bool ok = pvalid[m];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 ba = *reinterpret_cast<const float4*>(b1 + i * 8);
-                  const float4 bb = *reinterpret_cast<const float4*>(b1 + i * 8 + 4);
-                  const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                  uint4 ov;
-                  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    __half2 h = __floats2half2_rn(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
-                                                  __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
-                    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
-                    oh2[j] = h;
-                  }
-                  if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
-                  *reinterpret_cast<uint4*>(erow + i * 16) = ov;
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->d1_empty[g & 1]);
-        named_barrier_sync(kComputeBarrier, kComputeThreads);   // E complete
-        // ---- depthwise 3x3 over E -> A2 (swizzled K-major operand of the project GEMM)
-        mbar_wait(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
-        {
-          const int n_ch = vc >> 2;             // 4-channel groups of this chunk: 16, 8 or 4
-          const int ch4 = ct & (n_ch - 1);
-          const int q0 = ct / n_ch;
-          const int q_step = kComputeThreads / n_ch;
-          if (q0 < q_count) {
-            const int ce = c * 64 + ch4 * 4;
-            float2 w[9][2], bias[2];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const float4 wv = *reinterpret_cast<const float4*>(s_dw + t * CE + ce);
-              w[t][0] = make_float2(wv.x, wv.y);
-              w[t][1] = make_float2(wv.z, wv.w);
-            }
-            const float4 b2 = *reinterpret_cast<const float4*>(s_b2 + ce);
-            bias[0] = make_float2(b2.x, b2.y);
-            bias[1] = make_float2(b2.z, b2.w);
-            uint8_t* a2 = s_a2 + (g & 1) * 16384;
-            for (int q = q0; q < q_count; q += q_step) {
-              const int strip = q / pairs, xp = q - strip * pairs;
-              const uint8_t* in = s_e + ((strip * kMbRO * S) * p.BW + xp * 2 * S) * kEPitch + ch4 * 8;
-              const int prow0 = strip * kMbRO * p.TW + 2 * xp;
-              uint8_t* out0 = a2 + prow0 * 128 + (((ch4 >> 1) ^ (prow0 & 7)) << 4) + (ch4 & 1) * 8;
-              uint8_t* out1 = a2 + (prow0 + 1) * 128 + (((ch4 >> 1) ^ ((prow0 + 1) & 7)) << 4) + (ch4 & 1) * 8;
-              dw_strip<S, kMbRO>(in, kEPitch, p.BW * kEPitch, out0, out1, p.TW * 128, w, bias, 2);
-            }
-          }
-        }
-        fence_proxy_async();                                    // A2 writes -> visible to the tensor core
-        if (c == p.nc - 1 && ct == 0) tma_store_wait_read0();   // the previous tile's store has released the staging tile
-        named_barrier_sync(kComputeBarrier, kComputeThreads);   // A2 complete; nobody reads E any more
-        if (ct == 0) mbar_arrive(&ctrl->a2_full[g & 1]);
-      }
-      // ---- project epilogue: D2 (TMEM) -> +bias (+ residual) -> fp16 -> swizzled staging tile -> TMA store
-      mbar_wait(&ctrl->d2_full, static_cast<uint32_t>(it) & 1u);
+      mbar_wait(&ctrl->d2_full[pit & 1], (static_cast<uint32_t>(pit) >> 1) & 1u);
       tc_fence_after();
+      if (et == 0) tma_store_wait_read0();    // the previous tile's store has released the staging tile
+      named_barrier_sync(kEpilogueBarrier, kGroupThreads);
       if (quarter * 32 < p.TW * p.TH) {
         const int oy = th_i * p.TH + pth, ox = tw_i * p.TW + ptw;
         const bool valid = prow < p.TW * p.TH && oy < p.Ho && ox < p.Wo;
@@ -283,7 +229,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         const int ncg = p.cout_pad >> 4;
         for (int cg = colhalf; cg < ncg; cg += 2) {
           uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_sel + static_cast<uint32_t>(kD2Col + cg * 16), v);
+          tmem_ld_32x32b_x16(tmem_base + lane_sel + static_cast<uint32_t>(kD2Col + (pit & 1) * 64 + cg * 16), v);
           tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -313,14 +259,135 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         }
       }
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->d2_empty[pit & 1]);
       fence_proxy_async();
-      named_barrier_sync(kComputeBarrier, kComputeThreads);
-      if (ct == 0) {
+      named_barrier_sync(kEpilogueBarrier, kGroupThreads);
+      if (et == 0) {
         tma_store_4d(&maps.out, s_out, 0, tw_i * p.TW, th_i * p.TH, n);
         tma_store_commit();
       }
+    };
+
+    int it = 0, g = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / tiles_per_img;
+      const int rr = tile - n * tiles_per_img;
+      const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
+      const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
+      bool pvalid[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int iy = iy0 + by[m], ix = ix0 + bx[m];
+        pvalid[m] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      }
+      for (int c = 0; c < p.nc; ++c, ++g) {
+        const int vc = min(64, p.Cexp - c * 64);
+        const int eb = g % p.EB;
+        // ---- expand epilogue: D1 (TMEM) -> +bias, ReLU6, zero outside the image -> E (smem, fp16)
+        mbar_wait(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
+        tc_fence_after();
+        mbar_wait(&ctrl->e_empty[eb], (static_cast<uint32_t>(g / p.EB) & 1u) ^ 1u);
+        if (colhalf * 32 < vc) {
+          uint8_t* e_buf = s_e + eb * p.e_bytes;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            if (m < p.Mtiles && m * 128 + quarter * 32 < p.n_rows) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(tmem_base + lane_sel + static_cast<uint32_t>((g & 1) * d1_cols + m * 64 + colhalf * 32), v);
+              tmem_ld_wait();
+              const int row = m * 128 + quarter * 32 + lane;
+              if (row < p.n_rows) {
+                uint8_t* erow = e_buf + row * kEPitch + colhalf * 64;
+                const float* b1 = s_b1 + c * 64 + colhalf * 32;
+                const bool ok = pvalid[m];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 ba = *reinterpret_cast<const float4*>(b1 + i * 8);
+                  const float4 bb = *reinterpret_cast<const float4*>(b1 + i * 8 + 4);
+                  const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                  uint4 ov;
+                  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    __half2 h = __floats2half2_rn(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
+                                                  __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
+                    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+                    oh2[j] = h;
+                  }
+                  if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
+                  *reinterpret_cast<uint4*>(erow + i * 16) = ov;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ctrl->d1_empty[g & 1]);
+          mbar_arrive(&ctrl->e_full[eb]);
+        }
+        // the previous tile's project epilogue runs one chunk late, so that its accumulator is complete by then
+        if (c == 0 && prev_tile >= 0) project_epilogue(it - 1, prev_tile);
+      }
+      prev_tile = tile;
     }
-    if (ct == 0) tma_store_wait_all();
+    if (prev_tile >= 0) project_epilogue(it - 1, prev_tile);
+    if (et == 0) tma_store_wait_all();
+  } else {
+    // ============================ depthwise group (8 warps): E -> depthwise 3x3 + bias + ReLU6 -> A2 ============================
+    const int dt = threadIdx.x - kFirstGroupWarp * 32 - kGroupThreads;   // 0..255
+    const int pairs = p.TW >> 1;
+    const int q_count = pairs * p.strips;
+    const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
+                             ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                   static_cast<int>(gridDim.x)
+                             : 0;
+    const int G = my_tiles * p.nc;
+    int c = 0;
+    for (int g = 0; g < G; ++g) {
+      const int vc = min(64, p.Cexp - c * 64);
+      const int eb = g % p.EB;
+      const int n_ch = vc >> 2;             // 4-channel groups of this chunk: 16, 8 or 4
+      const int ch4 = dt & (n_ch - 1);
+      const int q0 = dt / n_ch;
+      const int q_step = kGroupThreads / n_ch;
+      const int ce = c * 64 + ch4 * 4;
+      float2 w[9][2], bias[2];
+      if (q0 < q_count) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 wv = *reinterpret_cast<const float4*>(s_dw + t * CE + ce);
+          w[t][0] = make_float2(wv.x, wv.y);
+          w[t][1] = make_float2(wv.z, wv.w);
+        }
+        const float4 b2 = *reinterpret_cast<const float4*>(s_b2 + ce);
+        bias[0] = make_float2(b2.x, b2.y);
+        bias[1] = make_float2(b2.z, b2.w);
+      }
+      mbar_wait(&ctrl->e_full[eb], static_cast<uint32_t>(g / p.EB) & 1u);
+      mbar_wait(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
+      if (q0 < q_count) {
+        const uint8_t* e_buf = s_e + eb * p.e_bytes;
+        uint8_t* a2 = s_a2 + (g & 1) * 16384;
+        for (int q = q0; q < q_count; q += q_step) {
+          const int strip = q / pairs, xp = q - strip * pairs;
+          const uint8_t* in = e_buf + ((strip * RO * S) * p.BW + xp * 2 * S) * kEPitch + ch4 * 8;
+          const int prow0 = strip * RO * p.TW + 2 * xp;
+          uint8_t* out0 = a2 + prow0 * 128 + (((ch4 >> 1) ^ (prow0 & 7)) << 4) + (ch4 & 1) * 8;
+          uint8_t* out1 = a2 + (prow0 + 1) * 128 + (((ch4 >> 1) ^ ((prow0 + 1) & 7)) << 4) + (ch4 & 1) * 8;
+          dw_strip<S, RO>(in, kEPitch, p.BW * kEPitch, out0, out1, p.TW * 128, w, bias, 2);
+        }
+      }
+      fence_proxy_async();                  // A2 writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctrl->e_empty[eb]);
+        mbar_arrive(&ctrl->a2_full[g & 1]);
+      }
+      if (++c == p.nc) c = 0;
+    }
   }
 
   tc_fence_before();
@@ -361,7 +428,7 @@ bool mbconv_plan(MbParams* p) {
       p->TH = th;
     }
   }
-  p->strips = p->TH / kMbRO;
+  p->strips = p->TH / (p->S == 1 ? 4 : 2);
   const int edge = p->S == 1 ? 2 : 1;
   p->BW = p->TW * p->S + edge;
   p->BH = p->TH * p->S + edge;
@@ -370,8 +437,12 @@ bool mbconv_plan(MbParams* p) {
   if (p->Mtiles > 3) return false;
   p->tiles_w = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_h = (p->Ho + p->TH - 1) / p->TH;
-  for (int xb = 2; xb >= 1; --xb) {
-    int off = xb * p->Mtiles * 16384;
+  p->e_bytes = (p->n_rows * kEPitch + 127) & ~127;
+  // preferred: two E buffers (the epilogue group fills one while the depthwise group reads the other) and two input
+  // windows; shrink to what fits in 227 KiB
+  const int try_xb[3] = {2, 1, 1}, try_eb[3] = {2, 2, 1};
+  for (int t = 0; t < 3; ++t) {
+    int off = try_xb[t] * p->Mtiles * 16384;
     p->off_w1 = off;
     off += p->nc * 8192;
     p->off_w2 = off;
@@ -382,14 +453,15 @@ bool mbconv_plan(MbParams* p) {
     p->off_out = off;
     off += 16384;
     p->off_e = off;
-    off += (p->n_rows * kEPitch + 127) & ~127;
+    off += try_eb[t] * p->e_bytes;
     p->off_f32 = off;
     off += (11 * p->nc * 64 + 64) * 4;
     off = (off + 15) & ~15;
     p->off_ctrl = off;
     off += 256;
     p->smem = off;
-    p->XB = xb;
+    p->XB = try_xb[t];
+    p->EB = try_eb[t];
     if (off <= 227 * 1024) return true;
   }
   return false;

@@ -16,15 +16,14 @@
 
 namespace af {
 
-constexpr int kMbThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: compute
-constexpr int kMbRO = 4;          // output rows per depthwise strip
+constexpr int kMbThreads = 608;   // warps 0-2: TMA producer / expand MMA / project MMA, 3-10: epilogues, 11-18: depthwise
 
 struct MbParams {
   int N, H, W, Cin, Cexp, Cout, S, Ho, Wo;
-  int TW, TH, strips;            // output tile (TW % 8 == 0, TH = kMbRO * strips, TW * TH <= 128)
+  int TW, TH, strips;            // output tile (TW % 8 == 0, TW * TH <= 128) and depthwise strips of 4 (2 at stride 2) rows
   int BW, BH, n_rows, Mtiles;    // input halo box, its pixel count and the number of 128-row MMA tiles covering it
   int tiles_w, tiles_h;
-  int XB;                        // input tile buffers (1 or 2)
+  int XB, EB, e_bytes;           // input window buffers / expanded-tile buffers (1 or 2 each), bytes per E buffer
   int nc;                        // 64-channel chunks of the expanded tensor
   int k1steps;                   // ceil(Cin / 16)
   int cout_pad;                  // N of the project MMA (multiple of 16, <= 64)

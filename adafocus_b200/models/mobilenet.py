@@ -4,10 +4,13 @@ Mirror of ACT/models/mobilenet.py (MobileNetV2 :71-152, get_featmap :146-148): t
 parameters under the reference's names (`features.N...`, `classifier.1.*`) so reference checkpoints load unchanged;
 the arithmetic runs in adafocus_b200's CUDA kernels (NHWC fp16, tcgen05 1x1 convs + depthwise 3x3 kernels).
 """
+import os
+
 import torch
 from torch import nn
 
-from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, pack_conv, pack_stem)
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv,
+                      pack_stem)
 
 # (expand t, channels c, repeats n, first stride s) -- the MobileNet-V2 paper's table, as at ACT/models/mobilenet.py:89-98
 _MBV2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
@@ -127,6 +130,7 @@ class MobileNetV2Runner:
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             entry["dw_w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
             entry["dw_s"], entry["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
+            entry["_dw_raw"] = dw.weight.detach().float().to(dev)
             pw, bn = seq[1], seq[2]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=entry["res"])
@@ -149,8 +153,21 @@ class MobileNetV2Runner:
                 bm = se * (we @ bp) + be
                 a["project"] = None
                 nxt["expand"] = pack_conv(wm, se, bm, act=AF_ACT_RELU6, device=dev)
+                nxt["_exp"] = (wm, se, bm)
+        # Blocks whose channel counts fit the fused inverted-residual kernel (expand -> depthwise -> project in one
+        # launch, the expanded tensor never reaches HBM) also get that packing; run() uses it wherever the spatial
+        # size is supported.
+        self.fuse_blocks = os.environ.get("AF_NO_MBCONV_FUSED") is None
         for e in self.blocks:
-            e.pop("_proj"), e.pop("_exp")
+            e["fused"] = None
+            if self.fuse_blocks and e["_exp"] is not None and e["project"] is not None:
+                we, se, be = e["_exp"]
+                wp, sp, bp = e["_proj"]
+                if mbconv_supported(1, 32, 32, we.shape[1], we.shape[0], wp.shape[0], e["stride"]):
+                    e["fused"] = pack_mbconv(we, se, be, e["_dw_raw"], e["dw_s"], e["dw_b"], wp, sp, bp, e["stride"],
+                                             device=dev)
+        for e in self.blocks:
+            e.pop("_proj"), e.pop("_exp"), e.pop("_dw_raw")
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
@@ -181,6 +198,12 @@ class MobileNetV2Runner:
             y = x
             if tsm is not None and e["res"]:
                 y = eng.tsm_shift(y, tsm[0], y.shape[-1] // tsm[1])
+            if e["fused"] is not None and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"]):
+                x = eng.mbconv(y, e["fused"], residual=inp if e["res"] else None)
+                if y is not inp:
+                    eng.release(y)
+                eng.release(inp)
+                continue
             if e["expand"] is not None:
                 h = eng.conv(y, e["expand"])
                 if y is not inp:

@@ -1,9 +1,11 @@
 """TSM-MobileNet-V2 glancer of the Something-Something tree -- mirror of STH/models/mobilenetv2.py (tonylins layout:
 flat `features.N.conv.K` Sequentials, `classifier` is a bare Linear; get_featmap :116-121 returns (map, logits))."""
+import os
+
 import torch
 from torch import nn
 
-from ..engine import AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, pack_conv
+from ..engine import AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv
 from ..models.mobilenet import _MBV2_SETTING, MobileNetV2Runner, _param_key
 
 
@@ -85,6 +87,7 @@ class SthGlancerRunner(MobileNetV2Runner):
         self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
         self.blocks = []
         self.tsm = None
+        fuse = os.environ.get("AF_NO_MBCONV_FUSED") is None
         for blk in f[1:-1]:
             seq = list(blk.conv)
             e = {"res": blk.use_res_connect, "stride": blk.stride, "expand": None, "shift": False}
@@ -94,8 +97,8 @@ class SthGlancerRunner(MobileNetV2Runner):
                     self.tsm = (cv.n_segment, cv.fold_div)
                     e["shift"] = True
                     cv = cv.net
-                s, b = fold_bn(seq[1].weight, seq[1].bias, seq[1].running_mean, seq[1].running_var, seq[1].eps)
-                e["expand"] = pack_conv(cv.weight, s, b, act=AF_ACT_RELU6, device=dev)
+                s1, b1 = fold_bn(seq[1].weight, seq[1].bias, seq[1].running_mean, seq[1].running_var, seq[1].eps)
+                e["expand"] = pack_conv(cv.weight, s1, b1, act=AF_ACT_RELU6, device=dev)
                 seq = seq[3:]
             dw, bn = seq[0], seq[1]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
@@ -104,6 +107,12 @@ class SthGlancerRunner(MobileNetV2Runner):
             pw, bn = seq[3], seq[4]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             e["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=e["res"])
+            e["fused"] = None
+            if (fuse and blk.expand != 1 and
+                    mbconv_supported(1, 32, 32, cv.weight.shape[1], cv.weight.shape[0], pw.weight.shape[0], blk.stride)):
+                # expand -> depthwise -> project as one launch (adafocus_b200/csrc/mbconv_fused.cu)
+                e["fused"] = pack_mbconv(cv.weight, s1, b1, dw.weight, e["dw_s"], e["dw_b"], pw.weight, s, b, blk.stride,
+                                         device=dev)
             self.blocks.append(e)
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
@@ -118,6 +127,12 @@ class SthGlancerRunner(MobileNetV2Runner):
             inp, y = x, x
             if e["shift"]:
                 y = eng.tsm_shift(x, self.tsm[0], x.shape[-1] // self.tsm[1])
+            if e["fused"] is not None and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"]):
+                x = eng.mbconv(y, e["fused"], residual=inp if e["res"] else None)
+                if y is not inp:
+                    eng.release(y)
+                eng.release(inp)
+                continue
             if e["expand"] is not None:
                 h = eng.conv(y, e["expand"])
                 if y is not inp:
