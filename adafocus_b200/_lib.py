@@ -26,6 +26,7 @@ class ConvDesc(ctypes.Structure):
         ("kh", c_int32), ("kw", c_int32), ("stride", c_int32), ("pad", c_int32),
         ("block_n", c_int32), ("act", c_int32), ("out_f32", c_int32),
         ("in_stride", c_int64), ("out_stride", c_int64), ("res_stride", c_int64),
+        ("in_row_stride", c_int64), ("in_img_stride", c_int64),
     ]
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "af_action_to_yx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_int, c_void_p]),
+    "af_stem_s2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p]),
     "af_stem_conv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -249,6 +249,16 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
                   [=](cudaStream_t s) { return af::launch_action_to_yx(action, yx, N, H, P, s); });
 }
 
+int af_stem_s2d(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W, int P,
+                int pad, int Hs, int Ws, void* stream) {
+  if (frames == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_stem_s2d: null tensor");
+  if (P > H || P > W || P < 1 || pad < 0 || Hs < 1 || Ws < 1) return fail(AF_ERR_INVALID, "af_stem_s2d: bad geometry");
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_stem_s2d", [=](cudaStream_t s) {
+    return af::launch_stem_s2d(frames, yx, yx_div, o, N, H, W, P, pad, Hs, Ws, s);
+  });
+}
+
 int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W,
                    int P, int KH, int KW, int stride, int pad, int Kpad, void* stream) {
   if (frames == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_stem_im2col: null tensor");
@@ -319,8 +329,12 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   if (d->block_n < 16 || d->block_n > af::kConvMaxBlockN || d->block_n % 16 != 0)
     return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: block_n must be a multiple of 16 in [16,256]");
   if (d->stride != 1 && d->stride != 2) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: stride must be 1 or 2");
-  if (d->cin % 8 != 0 || d->in_stride % 8 != 0 || d->in_stride < d->cin)
+  const bool windowed = d->in_row_stride != 0 || d->in_img_stride != 0;
+  if (d->cin % 8 != 0 || d->in_stride % 8 != 0 || (!windowed && d->in_stride < d->cin))
     return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: cin and in_stride must be multiples of 8");
+  if (windowed && (d->stride != 1 || d->in_row_stride % 8 != 0 || d->in_img_stride % 8 != 0 ||
+                   d->in_row_stride < 8 || d->in_img_stride < 8))
+    return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: explicit row/image strides need stride 1 and multiples of 8");
   if (d->cout < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: cout < 1");
   if (d->out_stride % 8 != 0 || (d->residual != nullptr && d->res_stride % 8 != 0))
     return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: out_stride / res_stride must be multiples of 8");
@@ -366,7 +380,11 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   if (d->stride == 1) {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
                                 static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
-    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    if (windowed) {
+      strides[1] = static_cast<cuuint64_t>(d->in_row_stride) * 2;
+      strides[2] = static_cast<cuuint64_t>(d->in_img_stride) * 2;
+    }
     if (!encode_map(ctx, &maps.a[0], in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
   } else {
     for (int ph = 0; ph < 2; ++ph) {

@@ -15,6 +15,7 @@ struct __align__(8) ConvSmemCtrl {
   uint64_t empty[kConvMaxStages];
   uint64_t tmem_full[4];   // [stage] or, when single-slice tiles alternate between a stage's two groups, [stage + 2*sub]
   uint64_t tmem_empty[2];
+  uint64_t wfull;          // resident-weights mode: all weight k-blocks have landed
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -91,8 +92,13 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
   const int stage_b_bytes = p.BN * kConvBlockK * 2;
-  const int stage_bytes = kStageABytes + stage_b_bytes;   // multiple of 1024 because BN % 16 == 0 -> BN*128 % 2048 == 0? (BN*128: 16*128=2048) yes
-  // [stages][64x64 identity tile, only with res_mma][epilogue staging][scale/bias][barriers]; all 1024-B aligned
+  // Resident weights (p.wres): a layer with a single n-block and a small filter keeps ALL its weight k-blocks in
+  // shared memory for the life of the CTA; pipeline stages then carry the A operand only, which removes the
+  // per-tile weight re-load (a third of the L2 -> SM traffic of the 64-channel layers) and deepens the A prefetch.
+  const int stage_bytes = kStageABytes + (p.wres ? 0 : stage_b_bytes);   // multiples of 2048 (BN % 16 == 0)
+  // [resident weights][stages][64x64 identity tile, only with res_mma][epilogue staging][scale/bias][barriers]
+  uint8_t* wres = smem;
+  smem += p.wres ? static_cast<size_t>(p.KH * p.KW * p.cblks) * stage_b_bytes : 0;
   uint8_t* ident = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* staging_base = ident + (p.res_mma ? kIdentBytes : 0);
   float* s_affine = reinterpret_cast<float*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
@@ -111,6 +117,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       mbar_init(&ctrl->empty[s], 1);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&ctrl->tmem_full[a], 1);
+    mbar_init(&ctrl->wfull, 1);
     for (int a = 0; a < 2; ++a) {
       // one arrive per warp of every epilogue group that reads the stage: both groups of the stage when a tile has
       // several 64-column slices (they split the slices), one group when it has a single slice (they alternate tiles)
@@ -164,6 +171,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       pdl_wait_prior_grid();
       int stage = 0;
       uint32_t phase = 0;
+      if (p.wres) {
+        mbar_arrive_expect_tx(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, &ctrl->wfull, kb * kConvBlockK, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nb = tile % p.n_blocks;
         const int mt = tile / p.n_blocks;
@@ -191,7 +203,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               uint8_t* sb = sa + kStageABytes;
               mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
               tma_load_4d(sa, &maps.a[map_idx], &ctrl->full[stage], cb * kConvBlockK, cw, ch, n0);
-              tma_load_2d(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
+              if (!p.wres) tma_load_2d(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -222,6 +234,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -232,7 +245,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           mbar_wait_backoff(&ctrl->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + kStageABytes;
+          const uint32_t sb = p.wres ? smem_u32(wres + static_cast<size_t>(kb) * stage_b_bytes) : sa + kStageABytes;
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sb);
 #pragma unroll
@@ -435,18 +448,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int BN, int res_mma, int* stages_out, int* epi_bufs_out) {
-  const int stage_bytes = kStageABytes + BN * kConvBlockK * 2;
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int* stages_out, int* epi_bufs_out) {
+  const int stage_bytes = kStageABytes + (wres_bytes ? 0 : BN * kConvBlockK * 2);
   // one 16 KiB staging buffer per epilogue group (other groups compute while a group's TMA store drains)
   const int epi_bufs = 1;
   const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes +
                     (res_mma ? kIdentBytes : 0);
-  int stages = (kConvSmemBudget - fixed) / stage_bytes;
+  int stages = (kConvSmemBudget - fixed - wres_bytes) / stage_bytes;
   if (stages > kConvMaxStages) stages = kConvMaxStages;
   if (stages < 2) stages = 2;
   if (stages_out) *stages_out = stages;
   if (epi_bufs_out) *epi_bufs_out = epi_bufs;
-  return static_cast<size_t>(stages) * stage_bytes + fixed;
+  return static_cast<size_t>(stages) * stage_bytes + fixed + wres_bytes;
 }
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p_in, int sm_count,
@@ -454,7 +467,11 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   static_assert(sizeof(ConvSmemCtrl) <= kCtrlBytes, "ctrl block too large");
   ConvKernelParams p = p_in;
   int stages = 0, epi_bufs = 1;
-  const size_t smem = conv_gemm_smem_bytes(p.BN, p.res_mma, &stages, &epi_bufs);
+  // resident weights: single n-block and at most 80 KiB of weights (>= 4 A-only stages remain)
+  static const bool no_wres = getenv("AF_NO_WRES") != nullptr;
+  const int wbytes = p.KH * p.KW * p.cblks * p.BN * kConvBlockK * 2;
+  p.wres = (!no_wres && p.n_blocks == 1 && wbytes <= 80 * 1024) ? 1 : 0;
+  const size_t smem = conv_gemm_smem_bytes(p.BN, p.res_mma, p.wres ? wbytes : 0, &stages, &epi_bufs);
   p.stages = stages;
   p.epi_bufs = epi_bufs;
   static const int dbg = getenv("AF_CONV_DEBUG") ? atoi(getenv("AF_CONV_DEBUG")) : 0;

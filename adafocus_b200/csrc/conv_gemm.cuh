@@ -51,6 +51,7 @@ struct ConvKernelParams {
   int act;
   int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
   int res_mma;                     // 1: residual tile is TMA-loaded (maps.res) and added by an identity-matrix MMA
+  int wres;                        // 1: all weight k-blocks stay resident in shared memory (set by the launcher)
   int epi_bufs;                    // staging buffers per epilogue group (1 or 2)
   int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores
 };
@@ -64,6 +65,6 @@ struct ConvTensorMaps {
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,
                              cudaStream_t stream);
-size_t conv_gemm_smem_bytes(int BN, int res_mma, int* stages_out, int* epi_bufs_out);
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int* stages_out, int* epi_bufs_out);
 
 }  // namespace af

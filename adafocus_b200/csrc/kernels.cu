@@ -201,6 +201,55 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ crop + 2x2 space-to-depth
+// A stride-2 KxK convolution over 3 channels equals a stride-1 ceil(K/2) x ceil(K/2) convolution over the 12 channels
+// of the 2x2 space-to-depth image of the zero-padded input.  This kernel cuts the patch at (y0, x0) (get_patch,
+// ACT/models/utils.py:37-51), applies the conv's zero padding, and writes out[n][Y][X][16] fp16 with channel
+// (dy*2+dx)*3 + c = padded[c][2Y+dy][2X+dx] (channels 12-15 zero).  The tensor-core conv then reads it through a TMA
+// view whose "pixel" is 4 consecutive X positions (64 channels, pixel stride 32 B: overlapping windows), so the
+// horizontal taps ride in the channel dimension and the im2col matrix is never written.
+__global__ void __launch_bounds__(kThreads)
+stem_s2d_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, int yx_div,
+                __half* __restrict__ out, int N, int H, int W, int P, int pad, int Hs, int Ws) {
+  pdl_sync();
+  const long long total = static_cast<long long>(N) * Hs * Ws;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % Ws);
+    const long long t = idx / Ws;
+    const int Y = static_cast<int>(t % Hs);
+    const int n = static_cast<int>(t / Hs);
+    int y0 = 0, x0 = 0;
+    if (yx != nullptr) {
+      const int e = n / yx_div;
+      y0 = max(0, min(yx[2 * e], H - P));
+      x0 = max(0, min(yx[2 * e + 1], W - P));
+    }
+    const float* base = frames + static_cast<long long>(n) * 3 * H * W;
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = 2 * Y + dy - pad;
+      const bool row_ok = iy >= 0 && iy < P;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = 2 * X + dx - pad;
+        const bool ok = row_ok && ix >= 0 && ix < P;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[(dy * 2 + dx) * 3 + c] = ok ? __ldg(base + (static_cast<long long>(c) * H + (y0 + iy)) * W + x0 + ix) : 0.f;
+      }
+    }
+    __align__(16) __half2 h[8];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    h[6] = h[7] = __floats2half2_rn(0.f, 0.f);
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ direct 3x3/2 stem
 // MobileNet-V2 features[0] (ACT/models/mobilenet.py:105): 3 -> 32 channels, 3x3, stride 2, pad 1, BN, ReLU6, straight
 // from the fp32 NCHW frame to NHWC fp16.  K = 27 is too thin for a 64-wide MMA k-block, so this layer runs on the
@@ -874,6 +923,14 @@ cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_di
   return launch_pdl<false>(stem_im2col_kernel, dim3(grid), dim3(kThreads), 0, s, frames, yx, yx_div < 1 ? 1 : yx_div, out, N, H, W, P, KH, KW, stride,
                                                pad, Ho, Wo, Kpad);
   return cudaGetLastError();
+}
+
+cudaError_t launch_stem_s2d(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W, int P,
+                            int pad, int Hs, int Ws, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(N) * Hs * Ws;
+  return launch_pdl<false>(stem_s2d_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
+                           yx_div < 1 ? 1 : yx_div, out, N, H, W, P, pad, Hs, Ws);
 }
 
 cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const float* scale, const float* bias,

@@ -103,7 +103,25 @@ def pack_stem(weight, scale, bias, stride, pad, act, device=None, kpad=None):
     flat[:, :kreal] = w.permute(0, 2, 3, 1).reshape(cout, kreal)
     pc = pack_conv(flat, scale, bias, 1, 0, act, device=device)
     pc.stem = dict(kh=kh, kw=kw, stride=stride, pad=pad, kpad=kpad)
+    pc.s2d = None
+    if stride == 2 and kh == kw and kh % 2 == 1 and pad == kh // 2 and (kh + 1) // 2 <= 4:
+        pc.s2d = pack_stem_s2d(w, scale, bias, act, device)
     return pc
+
+
+def pack_stem_s2d(w, scale, bias, act, device):
+    """Stride-2 k x k conv over 3 channels as a stride-1 R x 1 conv (R = (k+1)//2) over the sliding-window view of the
+    2x2 space-to-depth input written by af_stem_s2d: view channel sx*16 + (dy*2+dx)*3 + c at view pixel (Y, X) is
+    padded[c][2Y+dy][2(X+sx)+dx], so tap (r, s) of the original filter lands on vertical tap r//2 and view channel
+    (s//2)*16 + ((r%2)*2 + s%2)*3 + c."""
+    cout, _, k, _ = w.shape
+    R = (k + 1) // 2
+    w64 = torch.zeros(cout, 64, R, 1, dtype=torch.float32, device=device)
+    for r in range(k):
+        for s_ in range(k):
+            ch = (s_ // 2) * 16 + ((r % 2) * 2 + (s_ % 2)) * 3
+            w64[:, ch:ch + 3, r // 2, 0] = w[:, :, r, s_]
+    return pack_conv(w64, scale, bias, 1, 0, act, device=device)
 
 
 class PackedMbconv:
@@ -185,6 +203,7 @@ class Engine:
         self.lib = self.ctx.lib
         self.h = self.ctx.handle
         self.fused_stem = os.environ.get("AF_NO_FUSED_STEM") is None   # crop + stem conv as one implicit-GEMM kernel
+        self.s2d_stem = os.environ.get("AF_NO_S2D_STEM") is None       # crop + space-to-depth, then a windowed R x 1 conv
         self.ws = None          # Workspace while recording
         self._keep = None
         self.launch_count = 0   # launches issued eagerly (not recorded)
@@ -232,8 +251,10 @@ class Engine:
             self.launch_count += 1
 
     # ------------------------------------------------------------------ kernels
-    def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None):
-        """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given]."""
+    def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None,
+             row_stride=0, img_stride=0):
+        """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given; row_stride /
+        img_stride (elements) describe a sliding-window view, see af_conv_desc]."""
         if shape is None:
             n, h, w, cin = x.shape
             in_stride = x.stride(2)
@@ -259,6 +280,7 @@ class Engine:
         d.out_f32 = 1 if out_f32 else 0
         d.in_stride, d.out_stride = in_stride, out_stride
         d.res_stride = residual.stride(-2) if residual is not None else 0
+        d.in_row_stride, d.in_img_stride = row_stride, img_stride
         check(self.lib.af_conv2d_nhwc_f16(self.h, byref(d), self._stream()), "af_conv2d_nhwc_f16")
         self._count()
         self.keep(x, pc.w, pc.scale, pc.bias, out, residual)
@@ -282,6 +304,20 @@ class Engine:
         p = patch if patch is not None else h
         ho = (p + 2 * s["pad"] - s["kh"]) // s["stride"] + 1
         wo = (p + 2 * s["pad"] - s["kw"]) // s["stride"] + 1
+        if self.s2d_stem and getattr(pc, "s2d", None) is not None and p % 2 == 0:
+            q = pc.s2d
+            hs, ws = ho + q.kh - 1, wo + 3
+            # + one pixel row of slack: the window of the last view pixel extends 3 s2d pixels past its row
+            buf = self.empty((n * hs * ws + ws, 16), torch.float16)
+            check(self.lib.af_stem_s2d(self.h, _ptr(frames), _ptr(yx), int(yx_div), _ptr(buf), n, h, w, p, s["pad"],
+                                       hs, ws, self._stream()), "af_stem_s2d")
+            self._count()
+            self.keep(frames, yx, buf)
+            out = self.empty((n, ho, wo, pc.cout), torch.float16)
+            self.conv(buf, q, out=out, out_stride=pc.cout, shape=(n, hs, wo, 64, 16), row_stride=ws * 16,
+                      img_stride=hs * ws * 16)
+            self.release(buf)
+            return out
         fused_ok = (self.fused_stem and pc.cout % 16 == 0 and pc.cout <= 64 and s["kh"] * s["kw"] * 3 <= 256
                     and ho * wo >= 128 and s["stride"] <= 2 and s["kh"] <= 7 and s["kw"] <= 7)
         if fused_ok:

@@ -113,8 +113,8 @@ class MobileNetV2Runner:
             # fp32 [27][32], k = (r*3+s)*3 + c
             self.stem_w = c0.weight.detach().float().permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
             self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
-        else:
-            self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
+        # tensor-core form (space-to-depth + windowed 2x1 conv) -- preferred for even frame sizes
+        self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
         self.blocks = []
         for blk in list(f)[1:-1]:
             seq = list(blk.conv)
@@ -189,7 +189,8 @@ class MobileNetV2Runner:
     def run(self, eng, frames, tsm=None, out_full=None, out_slice=None, n_total=None):
         """frames (N,3,H,W) fp32 contiguous -> (N,h,w,1280) NHWC fp16. tsm=(T, shift_div) applies the temporal shift
         to the input of every residual block's first 1x1 conv (STH/models/gfv_net.py:238-241)."""
-        if self.stem_direct:
+        if self.stem_direct and not (eng.s2d_stem and self.stem.s2d is not None and frames.shape[-1] % 2 == 0
+                                     and frames.shape[-2] == frames.shape[-1]):
             x = eng.stem_conv3x3s2_c32(frames, self.stem_w, self.stem_s, self.stem_b)
         else:
             x = eng.stem(frames, self.stem)

@@ -5,7 +5,8 @@ import os
 import torch
 from torch import nn
 
-from ..engine import AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv,
+                      pack_stem)
 from ..models.mobilenet import _MBV2_SETTING, MobileNetV2Runner, _param_key
 
 
@@ -85,6 +86,7 @@ class SthGlancerRunner(MobileNetV2Runner):
         self.stem_direct = True
         self.stem_w = c0.weight.detach().float().permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
         self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
+        self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
         self.blocks = []
         self.tsm = None
         fuse = os.environ.get("AF_NO_MBCONV_FUSED") is None
@@ -122,7 +124,10 @@ class SthGlancerRunner(MobileNetV2Runner):
         self.logit_stride = (self.num_classes + 7) // 8 * 8
 
     def run(self, eng, frames, tsm=None):
-        x = eng.stem_conv3x3s2_c32(frames, self.stem_w, self.stem_s, self.stem_b)
+        if eng.s2d_stem and self.stem.s2d is not None and frames.shape[-1] % 2 == 0 and frames.shape[-2] == frames.shape[-1]:
+            x = eng.stem(frames, self.stem)
+        else:
+            x = eng.stem_conv3x3s2_c32(frames, self.stem_w, self.stem_s, self.stem_b)
         for e in self.blocks:
             inp, y = x, x
             if e["shift"]:

@@ -64,6 +64,10 @@ typedef struct af_conv_desc {
   int32_t act;     /* af_act */
   int32_t out_f32; /* 0: fp16 output, 1: fp32 output */
   int64_t in_stride, out_stride, res_stride;
+  /* Optional explicit row / image strides of `in` (elements; 0 = dense: w_*in_stride, h*w_*in_stride).  With them
+   * set, in_stride may be smaller than cin: consecutive "pixels" then overlap in memory (a sliding window over a
+   * narrower tensor, e.g. the space-to-depth stem input of af_stem_s2d).  stride-1 convolutions only. */
+  int64_t in_row_stride, in_img_stride;
 } af_conv_desc;
 
 int af_version(void);
@@ -104,6 +108,15 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
  * STH/models/gfv_net.py:141-152,421). */
 int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W,
                    int P, int KH, int KW, int stride, int pad, int Kpad, void* stream);
+
+/* get_patch + conv zero padding + 2x2 space-to-depth + fp32->fp16 for a stride-2 3-channel stem convolution
+ * (ResNet conv1 7x7/2 pad 3, ACT/models/resnet.py:138; MobileNet-V2 features[0] 3x3/2 pad 1,
+ * ACT/models/mobilenet.py:105).  frames (N,3,H,W) fp32 -> out (N,Hs,Ws,16) fp16 with
+ * out[n][Y][X][(dy*2+dx)*3+c] = padded_patch[c][2Y+dy][2X+dx] (zero outside the P x P patch, channels 12-15 zero).
+ * The stride-2 KxK conv is then a stride-1 ceil(K/2) x 1 af_conv2d_nhwc_f16 over the 64-channel sliding-window view
+ * (in_stride = 16, in_row_stride = Ws*16) of this tensor.  yx / yx_div as for af_stem_im2col. */
+int af_stem_s2d(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W, int P,
+                int pad, int Hs, int Ws, void* stream);
 
 /* Fused get_patch + stem convolution + BN + activation as ONE tcgen05 implicit-GEMM kernel: the patch selected by yx
  * (ACT/models/utils.py:37-51) goes through Conv2d(3, cout, KHxKW, stride, pad) (ResNet conv1, ACT/models/resnet.py:138)

@@ -189,22 +189,56 @@ def test_conv_residual_on_tensor_core(eng, case):
     assert torch.equal(out0, r.contiguous())
 
 
-def test_stem_im2col_conv_vs_torch(eng):
-    """Crop fused into the stem staging + 7x7/2 conv as a GEMM == conv2d(get_patch(...))."""
+@pytest.mark.parametrize("mode,p", [("s2d", 128), ("s2d", 96), ("s2d", 144), ("fused", 128), ("im2col", 128)])
+def test_stem_im2col_conv_vs_torch(eng, mode, p):
+    """Crop fused into the stem staging + 7x7/2 conv as a GEMM == conv2d(get_patch(...)), for the three stem paths
+    (space-to-depth + windowed conv, fused producer-warp kernel, im2col matrix + GEMM)."""
     from adafocus_b200.engine import pack_stem
-    from oracle import adafocus_oracle as orc
     torch.manual_seed(4)
-    n, p = 6, 128
+    n = 6
     frames = torch.randn(n, 3, 224, 224, device=DEV)
     yx = torch.tensor([[0, 0], [96, 96], [16, 80], [48, 0], [95, 1], [33, 64]], dtype=torch.int32, device=DEV)
     wt = (torch.randn(64, 3, 7, 7, device=DEV) / math.sqrt(147)).half().float()
     scale, bias = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV) * 0.1
+    yx = yx.clamp(max=224 - p)
     pc = pack_stem(wt, scale, bias, stride=2, pad=3, act=1, device=DEV)
-    out = eng.stem(frames, pc, yx=yx, patch=p)
+    saved = eng.s2d_stem, eng.fused_stem
+    eng.s2d_stem, eng.fused_stem = mode == "s2d", mode != "im2col"
+    try:
+        out = eng.stem(frames, pc, yx=yx, patch=p)
+    finally:
+        eng.s2d_stem, eng.fused_stem = saved
     patches = torch.stack([frames[i, :, y:y + p, x:x + p] for i, (y, x) in enumerate(yx.tolist())])
     ref = F.conv2d(patches.half().float(), wt, None, 2, 3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
     ref = ref.clamp(min=0).permute(0, 2, 3, 1)
-    assert out.shape == (n, 64, 64, 64)
+    assert out.shape == (n, p // 2, p // 2, 64)
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3), float((out.float() - ref).abs().max())
+
+
+def test_stem_s2d_3x3_and_division_crops(eng):
+    """MobileNet-V2 features[0] (3x3/2 pad 1, whole frame) through the space-to-depth path, and one crop origin
+    shared by yx_div consecutive frames (STH: one patch position per video division)."""
+    from adafocus_b200.engine import pack_stem
+    torch.manual_seed(11)
+    for hw in (224, 96):
+        frames = torch.randn(5, 3, hw, hw, device=DEV)
+        wt = (torch.randn(32, 3, 3, 3, device=DEV) / math.sqrt(27)).half().float()
+        scale, bias = torch.rand(32, device=DEV) + 0.5, torch.randn(32, device=DEV) * 0.1
+        pc = pack_stem(wt, scale, bias, stride=2, pad=1, act=2, device=DEV)
+        assert pc.s2d is not None and eng.s2d_stem
+        out = eng.stem(frames, pc)
+        ref = F.conv2d(frames.half().float(), wt, None, 2, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+        ref = ref.clamp(0, 6).permute(0, 2, 3, 1)
+        assert out.shape == ref.shape
+        assert torch.allclose(out.float(), ref, rtol=3e-3, atol=3e-3), float((out.float() - ref).abs().max())
+    frames = torch.randn(6, 3, 224, 224, device=DEV)
+    yx = torch.tensor([[80, 0], [7, 33]], dtype=torch.int32, device=DEV)
+    wt = (torch.randn(64, 3, 7, 7, device=DEV) / math.sqrt(147)).half().float()
+    pc = pack_stem(wt, None, torch.zeros(64, device=DEV), stride=2, pad=3, act=0, device=DEV)
+    out = eng.stem(frames, pc, yx=yx, patch=144, yx_div=3)
+    patches = torch.stack([frames[i, :, yx[i // 3, 0]:yx[i // 3, 0] + 144, yx[i // 3, 1]:yx[i // 3, 1] + 144]
+                           for i in range(6)])
+    ref = F.conv2d(patches.half().float(), wt, None, 2, 3).permute(0, 2, 3, 1)
     assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3), float((out.float() - ref).abs().max())
 
 
