@@ -14,6 +14,7 @@
 #include "dwconv_tma.cuh"
 #include "kernels.cuh"
 #include "mbconv_fused.cuh"
+#include "mbconv_tc.cuh"
 #include "stem_gemm.cuh"
 
 namespace {
@@ -430,11 +431,75 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
                   [=](cudaStream_t s) { return af::launch_conv_gemm(maps, p, sms, s); });
 }
 
+namespace {
+
+// The default is the second-generation kernel (depthwise on the FMA pipes, mbconv_fused.cu).  AF_MBCONV_V3=1 selects
+// the variant with the depthwise on the tensor core (mbconv_tc.cu): correct, but measured 3x slower -- every
+// tcgen05.mma of M=128, K=16 costs ~55 cycles whatever its N (tools/probe/umma_rate_probe.cu), and a depthwise chunk
+// needs 36 of them (profiles/README.md).
+bool use_mb3() {
+  static const bool v = getenv("AF_MBCONV_V3") != nullptr;
+  return v;
+}
+
+bool encode_mb_maps(af_ctx* ctx, const af_mbconv_desc* d, int BW, int BH, int TW, int TH, int Ho, int Wo, int nc,
+                    int cout_pad, af::MbTensorMaps* maps, std::string* err) {
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cin) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
+                                static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(BW), static_cast<cuuint32_t>(BH), 1};
+    if (!encode_map(ctx, &maps->x, d->in, 4, dims, strides, box, err)) return false;
+  }
+  {
+    const cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(nc) * 64};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, 64};
+    if (!encode_map(ctx, &maps->w1, d->w1, 2, dims, strides, box, err)) return false;
+  }
+  {
+    const cuuint64_t kpad = static_cast<cuuint64_t>(nc) * 64;
+    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(cout_pad)};
+    const cuuint64_t strides[1] = {kpad * 2};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(cout_pad)};
+    if (!encode_map(ctx, &maps->w2, d->w2, 2, dims, strides, box, err)) return false;
+  }
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cout) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(Wo),
+                                static_cast<cuuint64_t>(Ho), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * Wo, pix_b * Wo * Ho};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(TH), 1};
+    if (!encode_map(ctx, &maps->out, d->out, 4, dims, strides, box, err)) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
 int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride) {
+  if (use_mb3()) {
+    af::Mb3Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = n; q.H = h; q.W = w; q.Cin = cin; q.Cexp = cexp; q.Cout = cout; q.S = stride;
+    if (af::mbconv3_plan(&q)) return 1;
+  }
   af::MbParams p;
   memset(&p, 0, sizeof(p));
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cexp = cexp; p.Cout = cout; p.S = stride;
   return af::mbconv_plan(&p) ? 1 : 0;
+}
+
+int af_mbconv_fused_plan(int n, int h, int w, int cin, int cexp, int cout, int stride, int32_t* info) {
+  if (info == nullptr) return AF_ERR_INVALID;
+  af::Mb3Params q;
+  memset(&q, 0, sizeof(q));
+  q.N = n; q.H = h; q.W = w; q.Cin = cin; q.Cexp = cexp; q.Cout = cout; q.S = stride;
+  if (!use_mb3() || !af::mbconv3_plan(&q)) return 1;
+  const int32_t v[12] = {q.TW, q.TH, q.BW, q.BH, q.Mtiles, q.e_rows, q.XB, q.EB, q.AB, q.WB, q.nA, q.smem};
+  for (int i = 0; i < 12; ++i) info[i] = v[i];
+  return 0;
 }
 
 int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
@@ -442,48 +507,35 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
   if (d->in == nullptr || d->w1 == nullptr || d->bias1 == nullptr || d->dw_w == nullptr || d->bias2 == nullptr ||
       d->w2 == nullptr || d->bias3 == nullptr || d->out == nullptr)
     return fail(AF_ERR_INVALID, "af_mbconv_fused: null tensor");
+  if (d->residual != nullptr && (d->stride != 1 || d->res_stride % 8 != 0 || d->res_stride < d->cout))
+    return fail(AF_ERR_INVALID, "af_mbconv_fused: a residual needs stride 1 and res_stride % 8 == 0");
+  af::MbTensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  const int sms = ctx->sm_count;
+  if (use_mb3()) {
+    af::Mb3Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = d->n; q.H = d->h; q.W = d->w_; q.Cin = d->cin; q.Cexp = d->cexp; q.Cout = d->cout; q.S = d->stride;
+    if (af::mbconv3_plan(&q)) {
+      q.bias1 = d->bias1; q.dw_w = d->dw_w; q.bias2 = d->bias2; q.bias3 = d->bias3;
+      q.residual = static_cast<const __half*>(d->residual);
+      q.res_stride = d->res_stride;
+      if (!encode_mb_maps(ctx, d, q.BW, q.BH, q.TW, q.TH, q.Ho, q.Wo, q.nc, q.cout_pad, &maps, &err))
+        return fail(AF_ERR_CUDA, err);
+      return dispatch(ctx, stream, "af_mbconv_fused",
+                      [=](cudaStream_t s) { return af::launch_mbconv3(maps, q, sms, s); });
+    }
+  }
   af::MbParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;
   if (!af::mbconv_plan(&p)) return fail(AF_ERR_INVALID, "af_mbconv_fused: unsupported shape");
-  if (d->residual != nullptr && (d->stride != 1 || d->res_stride % 8 != 0 || d->res_stride < d->cout))
-    return fail(AF_ERR_INVALID, "af_mbconv_fused: a residual needs stride 1 and res_stride % 8 == 0");
   p.bias1 = d->bias1; p.dw_w = d->dw_w; p.bias2 = d->bias2; p.bias3 = d->bias3;
   p.residual = static_cast<const __half*>(d->residual);
   p.res_stride = d->res_stride;
-  af::MbTensorMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  std::string err;
-  {
-    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cin) * 2;
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
-                                static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
-    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.BW), static_cast<cuuint32_t>(p.BH), 1};
-    if (!encode_map(ctx, &maps.x, d->in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
-  }
-  {
-    const cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(p.nc) * 64};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, 64};
-    if (!encode_map(ctx, &maps.w1, d->w1, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
-  }
-  {
-    const cuuint64_t kpad = static_cast<cuuint64_t>(p.nc) * 64;
-    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(p.cout_pad)};
-    const cuuint64_t strides[1] = {kpad * 2};
-    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.cout_pad)};
-    if (!encode_map(ctx, &maps.w2, d->w2, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
-  }
-  {
-    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cout) * 2;
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
-                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(d->n)};
-    const cuuint64_t strides[3] = {pix_b, pix_b * p.Wo, pix_b * p.Wo * p.Ho};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
-    if (!encode_map(ctx, &maps.out, d->out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
-  }
-  const int sms = ctx->sm_count;
+  if (!encode_mb_maps(ctx, d, p.BW, p.BH, p.TW, p.TH, p.Ho, p.Wo, p.nc, p.cout_pad, &maps, &err))
+    return fail(AF_ERR_CUDA, err);
   return dispatch(ctx, stream, "af_mbconv_fused",
                   [=](cudaStream_t s) { return af::launch_mbconv_fused(maps, p, sms, s); });
 }
