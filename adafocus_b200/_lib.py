@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libadafocus_b200.so")
+# AF_LIB_PATH: load another build of the same ABI (A/B timing of kernel changes); default is the in-tree library
+LIB_PATH = os.environ.get("AF_LIB_PATH") or os.path.join(HERE, "lib", "libadafocus_b200.so")
 
 AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6 = 0, 1, 2
 
@@ -60,7 +61,7 @@ SIGNATURES = {
     "af_stem_im2col": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_int, c_void_p]),
     "af_stem_s2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                            c_void_p]),
+                            c_int, c_void_p]),
     "af_stem_conv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -251,12 +251,13 @@ int af_action_to_yx(af_ctx* ctx, const float* action, int32_t* yx, int N, int H,
 }
 
 int af_stem_s2d(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W, int P,
-                int pad, int Hs, int Ws, void* stream) {
+                int pad, int Hs, int Ws, int vt, void* stream) {
   if (frames == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_stem_s2d: null tensor");
-  if (P > H || P > W || P < 1 || pad < 0 || Hs < 1 || Ws < 1) return fail(AF_ERR_INVALID, "af_stem_s2d: bad geometry");
+  if (P > H || P > W || P < 1 || pad < 0 || Hs < 1 || Ws < 1 || (vt != 1 && vt != 2))
+    return fail(AF_ERR_INVALID, "af_stem_s2d: bad geometry");
   __half* o = static_cast<__half*>(out);
   return dispatch(ctx, stream, "af_stem_s2d", [=](cudaStream_t s) {
-    return af::launch_stem_s2d(frames, yx, yx_div, o, N, H, W, P, pad, Hs, Ws, s);
+    return af::launch_stem_s2d(frames, yx, yx_div, o, N, H, W, P, pad, Hs, Ws, vt, s);
   });
 }
 
@@ -352,6 +353,32 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   if (p.Ho < 1 || p.Wo < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: empty output");
   p.Cout = d->cout;
   choose_tile(p.N, p.Ho, p.Wo, &p.TW, &p.TH, &p.TN);
+  {
+    // vertical-halo mode (conv_gemm.cuh): stride-1 filters taller than one row whose weights stay resident; the tile
+    // is one image's TW x TH pixels, chosen to minimise the rows loaded per tile (TH + KH - 1 per TH produced)
+    static const bool no_vhalo = getenv("AF_NO_VHALO") != nullptr;
+    const int nb = ceil_div(d->cout, d->block_n), cb = ceil_div(d->cin, af::kConvBlockK);
+    if (!no_vhalo && d->stride == 1 && d->kh > 1 && af::conv_gemm_wres_ok(nb, d->block_n, d->kh, d->kw, cb)) {
+      long long best = -1;
+      int btw = 0, bth = 0;
+      for (int tw = 128; tw >= 8; tw >>= 1) {
+        const int th = 128 / tw;
+        if ((th + d->kh - 1) * tw * 128 > 48 * 1024) continue;
+        const long long cost = 1LL * ceil_div(p.Wo, tw) * ceil_div(p.Ho, th) * (th + d->kh - 1) * tw;
+        if (best < 0 || cost < best) {
+          best = cost;
+          btw = tw;
+          bth = th;
+        }
+      }
+      if (best > 0) {
+        p.vhalo = 1;
+        p.TW = btw;
+        p.TH = bth;
+        p.TN = 1;
+      }
+    }
+  }
   p.tiles_w = ceil_div(p.Wo, p.TW);
   p.tiles_h = ceil_div(p.Ho, p.TH);
   p.tiles_n = ceil_div(p.N, p.TN);
@@ -387,6 +414,11 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
       strides[2] = static_cast<cuuint64_t>(d->in_img_stride) * 2;
     }
     if (!encode_map(ctx, &maps.a[0], in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+    if (p.vhalo) {
+      const cuuint32_t hbox[4] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.TW),
+                                  static_cast<cuuint32_t>(p.TH + p.KH - 1), 1};
+      if (!encode_map(ctx, &maps.ah, in, 4, dims, strides, hbox, &err)) return fail(AF_ERR_CUDA, err);
+    }
   } else {
     for (int ph = 0; ph < 2; ++ph) {
       for (int pw = 0; pw < 2; ++pw) {

@@ -31,8 +31,10 @@ static_assert(kConvThreads == 64 + kEpilogueGroups * kEpilogueThreads, "thread r
 
 // single-thread roles (producer / MMA issuer) back off between probes so they do not steal issue slots from the
 // epilogue warps that share their scheduler
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int ns = 32) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns > 0) __nanosleep(ns);
+  }
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -83,6 +85,7 @@ __device__ __forceinline__ void epilogue_half_slice_act(int act, const uint32_t 
   else epilogue_half_slice<kActNone>(v, sc, bi, srow, row, chunk0);
 }
 
+template <bool VHALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -95,13 +98,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   // Resident weights (p.wres): a layer with a single n-block and a small filter keeps ALL its weight k-blocks in
   // shared memory for the life of the CTA; pipeline stages then carry the A operand only, which removes the
   // per-tile weight re-load (a third of the L2 -> SM traffic of the 64-channel layers) and deepens the A prefetch.
-  const int stage_bytes = kStageABytes + (p.wres ? 0 : stage_b_bytes);   // multiples of 2048 (BN % 16 == 0)
+  // Vertical-halo mode (p.vhalo, resident weights only): a stage holds ONE box of TH + KH - 1 input rows per (kw,
+  // 64-channel slice); the KH vertical taps are row-shifted windows of it -- a UMMA descriptor may start at any
+  // 128-byte row of a swizzled buffer (tools/probe/umma_offset_probe.cu) -- so the tile's L2 -> SM operand traffic
+  // drops from KH*KW to KW*(TH+KH-1)/TH boxes.
+  const int stage_a_bytes = VHALO ? (p.TH + p.KH - 1) * p.TW * 128 : kStageABytes;
+  const int stage_bytes = stage_a_bytes + (p.wres ? 0 : stage_b_bytes);   // multiples of 1024
   // [resident weights][stages][64x64 identity tile, only with res_mma][epilogue staging][scale/bias][barriers]
   uint8_t* wres = smem;
   smem += p.wres ? static_cast<size_t>(p.KH * p.KW * p.cblks) * stage_b_bytes : 0;
   uint8_t* ident = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* staging_base = ident + (p.res_mma ? kIdentBytes : 0);
-  float* s_affine = reinterpret_cast<float*>(staging_base + kEpilogueGroups * p.epi_bufs * kConvStagingBytes);
+  float* s_affine = reinterpret_cast<float*>(staging_base + p.epi_groups * kConvStagingBytes);
   ConvSmemCtrl* ctrl = reinterpret_cast<ConvSmemCtrl*>(reinterpret_cast<uint8_t*>(s_affine) + kAffineBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -121,7 +129,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     for (int a = 0; a < 2; ++a) {
       // one arrive per warp of every epilogue group that reads the stage: both groups of the stage when a tile has
       // several 64-column slices (they split the slices), one group when it has a single slice (they alternate tiles)
-      mbar_init(&ctrl->tmem_empty[a], (p.tma_store && p.BN <= 64) ? 4 : 8);
+      mbar_init(&ctrl->tmem_empty[a], ((p.tma_store && p.BN <= 64) || (VHALO && p.epi_groups == 2)) ? 4 : 8);
     }
     fence_mbar_init();
   }
@@ -130,6 +138,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     tma_prefetch_desc(&maps.b);
     if (p.tma_store) tma_prefetch_desc(&maps.out);
     if (p.res_mma) tma_prefetch_desc(&maps.res);
+    if (VHALO) tma_prefetch_desc(&maps.ah);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -171,6 +180,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       pdl_wait_prior_grid();
       int stage = 0;
       uint32_t phase = 0;
+      const int bo = p.backoff_ns;
       if (p.wres) {
         mbar_arrive_expect_tx(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
@@ -184,7 +194,21 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         const int tn_i = mt / (p.tiles_w * p.tiles_h);
         const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
         int kb = 0;
-        for (int kh = 0; kh < p.KH; ++kh) {
+        if constexpr (VHALO) {
+          for (int kw = 0; kw < p.KW; ++kw) {
+            for (int cb = 0; cb < p.cblks; ++cb) {
+              mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
+              uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+              mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_a_bytes));
+              tma_load_4d(sa, &maps.ah, &ctrl->full[stage], cb * kConvBlockK, ow0 + kw - p.pad, oh0 - p.pad, n0);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+        for (int kh = 0; kh < (VHALO ? 0 : p.KH); ++kh) {
           for (int kw = 0; kw < p.KW; ++kw) {
             int map_idx = 0, ch, cw;
             if (p.stride == 1) {
@@ -198,7 +222,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               map_idx = ph * 2 + pw;
             }
             for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
-              mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1);
+              mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
               uint8_t* sb = sa + kStageABytes;
               mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
@@ -214,7 +238,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         if (p.res_mma) {
           // the residual tile rides the same pipeline as extra A boxes (64 output channels each)
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
-            mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1);
+            mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
             mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
             tma_load_4d(sa, &maps.res, &ctrl->full[stage], nb * p.BN + j * 64, ow0, oh0, n0);
@@ -230,29 +254,53 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(p.BN));
-      const bool alternate_tiles = p.tma_store && p.BN <= 64;
+      const bool alternate_tiles = p.tma_store && p.BN <= 64 && !(VHALO && p.epi_groups == 2);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const int bo = p.backoff_ns;
+      // descriptor low words: stage s of the A ring / k-block kb of the resident weights are fixed offsets apart
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem)), a_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t w_lo0 = smem_desc_lo(smem_u32(wres)), b_step = static_cast<uint32_t>(stage_b_bytes) >> 4;
       if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait_backoff(&ctrl->tmem_empty[as], aphase ^ 1);
+        mbar_wait_backoff(&ctrl->tmem_empty[as], aphase ^ 1, bo);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kConvMaxBlockN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_backoff(&ctrl->full[stage], phase);
+        if constexpr (VHALO) {
+          for (int kw = 0; kw < p.KW; ++kw) {
+            for (int cb = 0; cb < p.cblks; ++cb) {
+              mbar_wait_backoff(&ctrl->full[stage], phase, bo);
+              tc_fence_after();
+              const uint32_t la0 = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+              uint32_t lb = w_lo0 + static_cast<uint32_t>(kw * p.cblks + cb) * b_step;
+              for (int kh = 0; kh < p.KH; ++kh, lb += b_step * static_cast<uint32_t>(p.KW * p.cblks)) {
+                const uint32_t la = la0 + static_cast<uint32_t>(kh * p.TW) * 8u;   // kh rows down: kh * TW * 128 B
+#pragma unroll
+                for (int k = 0; k < kConvBlockK / 16; ++k)
+                  umma_f16_ss_lo(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+                                 (kw | cb | kh | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&ctrl->empty[stage]);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+        for (int kb = 0; kb < (VHALO ? 0 : num_kb); ++kb) {
+          mbar_wait_backoff(&ctrl->full[stage], phase, bo);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = p.wres ? smem_u32(wres + static_cast<size_t>(kb) * stage_b_bytes) : sa + kStageABytes;
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sb);
+          const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+          const uint32_t lb = p.wres ? w_lo0 + static_cast<uint32_t>(kb) * b_step : la + (kStageABytes >> 4);
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
-            umma_f16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss_lo(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
@@ -267,7 +315,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             const int nj = p.BN - j * 64 < 64 ? p.BN - j * 64 : 64;
             const uint32_t idesc_r = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(nj));
-            mbar_wait_backoff(&ctrl->full[stage], phase);
+            mbar_wait_backoff(&ctrl->full[stage], phase, bo);
             tc_fence_after();
             const uint64_t da = make_smem_desc_sw128(smem_u32(smem + static_cast<size_t>(stage) * stage_bytes));
 #pragma unroll
@@ -308,10 +356,13 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     const int th = (row / p.TW) % p.TH;
     const int tn = row / (p.TW * p.TH);
     const int nslices = (p.BN + 63) >> 6;
-    const bool alternate_tiles = p.tma_store && nslices == 1;
-    const int sl_first = alternate_tiles ? 0 : sub, sl_step = alternate_tiles ? 1 : 2;
+    // epi_groups == 2 (MMA-heavy vertical-halo tiles): only groups 0 and 1 work, each draining every tile of its TMEM
+    // stage alone; the staging buffers of groups 2 and 3 are given to the load pipeline instead
+    const bool solo = VHALO && p.epi_groups == 2;
+    const bool alternate_tiles = p.tma_store && nslices == 1 && !solo;
+    const int sl_first = (alternate_tiles || solo) ? 0 : sub, sl_step = (alternate_tiles || solo) ? 1 : 2;
     pdl_wait_prior_grid();
-    for (int it = as; blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += 2) {
+    for (int it = as; !(solo && sub == 1) && blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += 2) {
       if (alternate_tiles && ((it >> 1) & 1) != sub) continue;
       const int tile = blockIdx.x + it * gridDim.x;
       const int nb = tile % p.n_blocks;
@@ -341,7 +392,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           loaded_nb = nb;
           named_barrier_sync(bar_id, kEpilogueThreads);
         }
-        mbar_wait(acc_full, aphase);
+        mbar_wait_backoff(acc_full, aphase, p.epi_backoff_ns);
         tc_fence_after();
 #pragma unroll 1
         for (int sl = sl_first; sl < nslices; sl += sl_step) {
@@ -374,7 +425,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
       } else {
         // ---- fp32 (or odd-shaped) output: direct global stores, one row per thread
-        mbar_wait(acc_full, aphase);
+        mbar_wait_backoff(acc_full, aphase, p.epi_backoff_ns);
         tc_fence_after();
         for (int c0 = sub * 16; c0 < p.BN; c0 += 32) {   // the stage's two groups take alternate 16-column chunks
           uint32_t v[16];
@@ -448,11 +499,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int* stages_out, int* epi_bufs_out) {
-  const int stage_bytes = kStageABytes + (wres_bytes ? 0 : BN * kConvBlockK * 2);
+bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks) {
+  static const bool no_wres = getenv("AF_NO_WRES") != nullptr;
+  const long long wbytes = 1LL * KH * KW * cblks * BN * kConvBlockK * 2;
+  return !no_wres && n_blocks == 1 && wbytes <= 80 * 1024;
+}
+
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int stage_a_bytes, int epi_groups, int* stages_out,
+                            int* epi_bufs_out) {
+  const int stage_bytes = stage_a_bytes + (wres_bytes ? 0 : BN * kConvBlockK * 2);
   // one 16 KiB staging buffer per epilogue group (other groups compute while a group's TMA store drains)
   const int epi_bufs = 1;
-  const int fixed = kEpilogueGroups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes +
+  const int fixed = epi_groups * epi_bufs * kConvStagingBytes + kAffineBytes + kCtrlBytes +
                     (res_mma ? kIdentBytes : 0);
   int stages = (kConvSmemBudget - fixed - wres_bytes) / stage_bytes;
   if (stages > kConvMaxStages) stages = kConvMaxStages;
@@ -468,21 +526,32 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   ConvKernelParams p = p_in;
   int stages = 0, epi_bufs = 1;
   // resident weights: single n-block and at most 80 KiB of weights (>= 4 A-only stages remain)
-  static const bool no_wres = getenv("AF_NO_WRES") != nullptr;
   const int wbytes = p.KH * p.KW * p.cblks * p.BN * kConvBlockK * 2;
-  p.wres = (!no_wres && p.n_blocks == 1 && wbytes <= 80 * 1024) ? 1 : 0;
-  const size_t smem = conv_gemm_smem_bytes(p.BN, p.res_mma, p.wres ? wbytes : 0, &stages, &epi_bufs);
+  p.wres = conv_gemm_wres_ok(p.n_blocks, p.BN, p.KH, p.KW, p.cblks) ? 1 : 0;
+  if (!p.wres) p.vhalo = 0;
+  const int stage_a_bytes = p.vhalo ? (p.TH + p.KH - 1) * p.TW * 128 : kStageABytes;
+  static const bool four_groups = getenv("AF_VHALO_4GROUPS") != nullptr;
+  p.epi_groups = (p.vhalo && p.tma_store && !four_groups) ? 2 : kEpilogueGroups;
+  const size_t smem =
+      conv_gemm_smem_bytes(p.BN, p.res_mma, p.wres ? wbytes : 0, stage_a_bytes, p.epi_groups, &stages, &epi_bufs);
+  if (p.vhalo && (stages < 2 || stage_a_bytes % 1024 != 0)) return cudaErrorInvalidValue;
   p.stages = stages;
   p.epi_bufs = epi_bufs;
   static const int dbg = getenv("AF_CONV_DEBUG") ? atoi(getenv("AF_CONV_DEBUG")) : 0;
   p.debug_flags = dbg;
+  static const int backoff = getenv("AF_CONV_BACKOFF_NS") ? atoi(getenv("AF_CONV_BACKOFF_NS")) : 32;
+  p.backoff_ns = backoff;
+  static const int epi_backoff = getenv("AF_CONV_EPI_BACKOFF_NS") ? atoi(getenv("AF_CONV_EPI_BACKOFF_NS")) : 0;
+  p.epi_backoff_ns = epi_backoff;
   // function attributes are per device: remember which devices have been configured
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kConvSmemBudget);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBudget);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -500,7 +569,8 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   static const bool pdl = getenv("AF_NO_PDL") == nullptr;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel, maps, p);
+  if (p.vhalo) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, maps, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, maps, p);
 }
 
 }  // namespace af

@@ -52,12 +52,17 @@ struct ConvKernelParams {
   int tma_store;                   // 1: fp16 output leaves through smem staging + TMA store (maps.out)
   int res_mma;                     // 1: residual tile is TMA-loaded (maps.res) and added by an identity-matrix MMA
   int wres;                        // 1: all weight k-blocks stay resident in shared memory (set by the launcher)
-  int epi_bufs;                    // staging buffers per epilogue group (1 or 2)
+  int vhalo;                       // 1: one (TH+KH-1)-row input box per (kw, channel slice); vertical taps = row-shifted windows (maps.ah)
+  int epi_bufs;                    // staging buffers per epilogue group (1)
+  int epi_groups;                  // epilogue groups at work (4, or 2 for vertical-halo tiles; set by the launcher)
+  int backoff_ns;                  // sleep between mbarrier probes of the single-thread roles (0 = spin on try_wait)
+  int epi_backoff_ns;              // same for the epilogue warps waiting for an accumulator
   int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores
 };
 
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
+  CUtensorMap ah;     // vhalo: same tensor as a[0], box {64, TW, TH+KH-1, 1}
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
   CUtensorMap out;    // output tensor {Cout, Wo, Ho, N}, box {64, TW, TH, TN} (only when tma_store)
   CUtensorMap res;    // residual tensor, same dims / box as `out` (only when res_mma)
@@ -65,6 +70,8 @@ struct ConvTensorMaps {
 
 cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams& p, int sm_count,
                              cudaStream_t stream);
-size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int* stages_out, int* epi_bufs_out);
+size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int stage_a_bytes, int epi_groups, int* stages_out,
+                            int* epi_bufs_out);
+bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks);
 
 }  // namespace af

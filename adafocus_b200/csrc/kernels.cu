@@ -208,6 +208,10 @@ stem_im2col_kernel(const float* __restrict__ frames, const int32_t* __restrict__
 // (dy*2+dx)*3 + c = padded[c][2Y+dy][2X+dx] (channels 12-15 zero).  The tensor-core conv then reads it through a TMA
 // view whose "pixel" is 4 consecutive X positions (64 channels, pixel stride 32 B: overlapping windows), so the
 // horizontal taps ride in the channel dimension and the im2col matrix is never written.
+// VT = 2 additionally folds the vertical neighbour into the pixel: out[n][Y][X][v*16 + (dy*2+dx)*3 + c] =
+// padded[c][2(Y+v)+dy][2X+dx], 32 channels (64 B) per pixel -- a 3x3/2 stem then needs a window of only two X positions
+// and becomes a single-k-block 1x1 conv over the view (half the operand traffic of the VT = 1 form).
+template <int VT>
 __global__ void __launch_bounds__(kThreads)
 stem_s2d_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, int yx_div,
                 __half* __restrict__ out, int N, int H, int W, int P, int pad, int Hs, int Ws) {
@@ -226,27 +230,31 @@ stem_s2d_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx
       x0 = max(0, min(yx[2 * e + 1], W - P));
     }
     const float* base = frames + static_cast<long long>(n) * 3 * H * W;
-    float v[12];
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * (16 * VT));
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int iy = 2 * Y + dy - pad;
-      const bool row_ok = iy >= 0 && iy < P;
+    for (int v = 0; v < VT; ++v) {
+      float val[12];
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int ix = 2 * X + dx - pad;
-        const bool ok = row_ok && ix >= 0 && ix < P;
+      for (int dy = 0; dy < 2; ++dy) {
+        const int iy = 2 * (Y + v) + dy - pad;
+        const bool row_ok = iy >= 0 && iy < P;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          v[(dy * 2 + dx) * 3 + c] = ok ? __ldg(base + (static_cast<long long>(c) * H + (y0 + iy)) * W + x0 + ix) : 0.f;
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ix = 2 * X + dx - pad;
+          const bool ok = row_ok && ix >= 0 && ix < P;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            val[(dy * 2 + dx) * 3 + c] =
+                ok ? __ldg(base + (static_cast<long long>(c) * H + (y0 + iy)) * W + x0 + ix) : 0.f;
+        }
       }
-    }
-    __align__(16) __half2 h[8];
+      __align__(16) __half2 h[8];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    h[6] = h[7] = __floats2half2_rn(0.f, 0.f);
-    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
-    dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
-    dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+      for (int j = 0; j < 6; ++j) h[j] = __floats2half2_rn(val[2 * j], val[2 * j + 1]);
+      h[6] = h[7] = __floats2half2_rn(0.f, 0.f);
+      dst[2 * v] = *reinterpret_cast<const uint4*>(&h[0]);
+      dst[2 * v + 1] = *reinterpret_cast<const uint4*>(&h[4]);
+    }
   }
 }
 
@@ -926,10 +934,13 @@ cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_di
 }
 
 cudaError_t launch_stem_s2d(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W, int P,
-                            int pad, int Hs, int Ws, cudaStream_t s) {
+                            int pad, int Hs, int Ws, int vt, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const long long total = static_cast<long long>(N) * Hs * Ws;
-  return launch_pdl<false>(stem_s2d_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
+  if (vt == 2)
+    return launch_pdl<false>(stem_s2d_kernel<2>, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
+                             yx_div < 1 ? 1 : yx_div, out, N, H, W, P, pad, Hs, Ws);
+  return launch_pdl<false>(stem_s2d_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
                            yx_div < 1 ? 1 : yx_div, out, N, H, W, P, pad, Hs, Ws);
 }
 

@@ -18,7 +18,7 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
 // out[(n*Ho+oh)*Wo+ow][k], k = (kh*KW+kw)*3 + c (zero for k >= KH*KW*3 and for taps outside the P x P window).
 // yx holds one (y,x) per yx_div consecutive frames.
 cudaError_t launch_stem_s2d(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W, int P,
-                            int pad, int Hs, int Ws, cudaStream_t s);
+                            int pad, int Hs, int Ws, int vt, cudaStream_t s);
 cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W,
                                int P, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, cudaStream_t s);
 

@@ -116,12 +116,15 @@ def pack_stem_s2d(w, scale, bias, act, device):
     (s//2)*16 + ((r%2)*2 + s%2)*3 + c."""
     cout, _, k, _ = w.shape
     R = (k + 1) // 2
-    w64 = torch.zeros(cout, 64, R, 1, dtype=torch.float32, device=device)
+    vt = 2 if R == 2 else 1   # 3x3: fold the two vertical taps into the pixel too -> one k-block, a 1x1 conv
+    w64 = torch.zeros(cout, 64, R // vt, 1, dtype=torch.float32, device=device)
     for r in range(k):
         for s_ in range(k):
-            ch = (s_ // 2) * 16 + ((r % 2) * 2 + (s_ % 2)) * 3
-            w64[:, ch:ch + 3, r // 2, 0] = w[:, :, r, s_]
-    return pack_conv(w64, scale, bias, 1, 0, act, device=device)
+            ch = (s_ // 2) * 16 * vt + ((r // 2) % vt) * 16 + ((r % 2) * 2 + (s_ % 2)) * 3
+            w64[:, ch:ch + 3, (r // 2) // vt, 0] = w[:, :, r, s_]
+    pc = pack_conv(w64, scale, bias, 1, 0, act, device=device)
+    pc.vt = vt
+    return pc
 
 
 class PackedMbconv:
@@ -306,16 +309,17 @@ class Engine:
         wo = (p + 2 * s["pad"] - s["kw"]) // s["stride"] + 1
         if self.s2d_stem and getattr(pc, "s2d", None) is not None and p % 2 == 0:
             q = pc.s2d
-            hs, ws = ho + q.kh - 1, wo + 3
-            # + one pixel row of slack: the window of the last view pixel extends 3 s2d pixels past its row
-            buf = self.empty((n * hs * ws + ws, 16), torch.float16)
+            pe = 16 * q.vt                      # elements per s2d pixel
+            hs, ws = ho + q.kh - 1, wo + 64 // pe - 1
+            # + one pixel row of slack: the window of the last view pixel extends past its row
+            buf = self.empty((n * hs * ws + ws, pe), torch.float16)
             check(self.lib.af_stem_s2d(self.h, _ptr(frames), _ptr(yx), int(yx_div), _ptr(buf), n, h, w, p, s["pad"],
-                                       hs, ws, self._stream()), "af_stem_s2d")
+                                       hs, ws, q.vt, self._stream()), "af_stem_s2d")
             self._count()
             self.keep(frames, yx, buf)
             out = self.empty((n, ho, wo, pc.cout), torch.float16)
-            self.conv(buf, q, out=out, out_stride=pc.cout, shape=(n, hs, wo, 64, 16), row_stride=ws * 16,
-                      img_stride=hs * ws * 16)
+            self.conv(buf, q, out=out, out_stride=pc.cout, shape=(n, hs, wo, 64, pe), row_stride=ws * pe,
+                      img_stride=hs * ws * pe)
             self.release(buf)
             return out
         fused_ok = (self.fused_stem and pc.cout % 16 == 0 and pc.cout <= 64 and s["kh"] * s["kw"] * 3 <= 256

@@ -114,9 +114,11 @@ int af_stem_im2col(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_d
  * ACT/models/mobilenet.py:105).  frames (N,3,H,W) fp32 -> out (N,Hs,Ws,16) fp16 with
  * out[n][Y][X][(dy*2+dx)*3+c] = padded_patch[c][2Y+dy][2X+dx] (zero outside the P x P patch, channels 12-15 zero).
  * The stride-2 KxK conv is then a stride-1 ceil(K/2) x 1 af_conv2d_nhwc_f16 over the 64-channel sliding-window view
- * (in_stride = 16, in_row_stride = Ws*16) of this tensor.  yx / yx_div as for af_stem_im2col. */
+ * (in_stride = 16, in_row_stride = Ws*16) of this tensor.  vt = 2 also folds the vertical neighbour into the pixel
+ * (out (N,Hs,Ws,32), channel v*16 + (dy*2+dx)*3 + c = padded[c][2(Y+v)+dy][2X+dx]): a 3x3/2 stem is then a 1x1 conv
+ * over the two-position window view (in_stride = 32).  yx / yx_div as for af_stem_im2col. */
 int af_stem_s2d(af_ctx* ctx, const float* frames, const int32_t* yx, int yx_div, void* out, int N, int H, int W, int P,
-                int pad, int Hs, int Ws, void* stream);
+                int pad, int Hs, int Ws, int vt, void* stream);
 
 /* Fused get_patch + stem convolution + BN + activation as ONE tcgen05 implicit-GEMM kernel: the patch selected by yx
  * (ACT/models/utils.py:37-51) goes through Conv2d(3, cout, KHxKW, stride, pad) (ResNet conv1, ACT/models/resnet.py:138)

@@ -37,5 +37,35 @@ def main():
     print(f"mobilenet stem direct: {timeit(lambda: eng.stem_conv3x3s2_c32(frames, w27, sc, bi)):.1f} us", flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--pieces" not in sys.argv:
     main()
+
+
+def pieces():
+    """prepass and windowed conv of the two s2d stems timed separately"""
+    from adafocus_b200.engine import _ptr, check
+    dev = torch.device("cuda", 0)
+    eng = get_engine(dev)
+    n = int(os.environ.get("N", 1024))
+    frames = torch.randn(n, 3, 224, 224, device=dev)
+    yx = torch.randint(0, 97, (n, 2), dtype=torch.int32, device=dev)
+    for name, k, pad, cout, patch in (("resnet", 7, 3, 64, 128), ("mobilenet", 3, 1, 32, 224)):
+        wt = torch.randn(cout, 3, k, k, device=dev) / math.sqrt(3 * k * k)
+        pc = pack_stem(wt, torch.ones(cout, device=dev), torch.zeros(cout, device=dev), stride=2, pad=pad, act=1, device=dev)
+        q = pc.s2d
+        pe = 16 * q.vt
+        ho = wo = patch // 2
+        hs, ws = ho + q.kh - 1, wo + 64 // pe - 1
+        buf = torch.zeros(n * hs * ws + ws, pe, device=dev, dtype=torch.float16)
+        out = torch.empty(n, ho, wo, cout, device=dev, dtype=torch.float16)
+        yxp = yx if patch != 224 else None
+        t1 = timeit(lambda: check(eng.lib.af_stem_s2d(eng.h, _ptr(frames), _ptr(yxp), 1, _ptr(buf), n, 224, 224, patch, pad,
+                                                      hs, ws, q.vt, eng._stream()), "s2d"))
+        t2 = timeit(lambda: eng.conv(buf, q, out=out, out_stride=cout, shape=(n, hs, wo, 64, pe), row_stride=ws * pe,
+                                     img_stride=hs * ws * pe))
+        print(f"{name}: prepass {t1:.1f} us ({(frames.numel() * 4 * (patch / 224) ** 2 + buf.numel() * 2) / t1 / 1e6:.2f} TB/s), "
+              f"conv {t2:.1f} us (out {out.numel() * 2 / t2 / 1e6:.2f} TB/s)", flush=True)
+
+
+if __name__ == "__main__" and "--pieces" in sys.argv:
+    pieces()
