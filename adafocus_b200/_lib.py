@@ -92,6 +92,8 @@ SIGNATURES = {
     "af_softmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "af_class_ap": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "af_fill_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
+    "af_frames_u8_to_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                    c_void_p]),
     "af_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

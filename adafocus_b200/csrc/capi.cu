@@ -760,6 +760,19 @@ int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream) {
   return dispatch(ctx, stream, "af_fill_f32", [=](cudaStream_t s) { return af::launch_fill_f32(p, v, n, s); });
 }
 
+int af_frames_u8_to_f32(af_ctx* ctx, const uint8_t* in, float* out, int B, int HW, int C, const float* mean3,
+                        const float* std3, void* stream) {
+  if (in == nullptr || out == nullptr || mean3 == nullptr || std3 == nullptr)
+    return fail(AF_ERR_INVALID, "af_frames_u8_to_f32: null argument");
+  if (B < 0 || HW < 1 || C < 1 || C > 96 || C % 3 != 0)
+    return fail(AF_ERR_INVALID, "af_frames_u8_to_f32: C must be a multiple of 3 in [3, 96]");
+  if (std3[0] == 0.f || std3[1] == 0.f || std3[2] == 0.f) return fail(AF_ERR_INVALID, "af_frames_u8_to_f32: zero std");
+  const float m[3] = {mean3[0], mean3[1], mean3[2]}, sd[3] = {std3[0], std3[1], std3[2]};
+  return dispatch(ctx, stream, "af_frames_u8_to_f32", [=](cudaStream_t s) {
+    return af::launch_u8hwc_to_f32chw_norm(in, out, B, HW, C, m, sd, s);
+  });
+}
+
 int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream) {
   if (in == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_f32_to_f16: null tensor");
   __half* o = static_cast<__half*>(out);

@@ -258,6 +258,48 @@ stem_s2d_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx
   }
 }
 
+// ------------------------------------------------------------------------------------------------ uint8 frame ingest
+// Stack -> ToTorchFormatTensor(div=True) -> GroupNormalize of the reference's loaders (ACT/ops/transforms.py:303-336,
+// 64-77) on the device: in (B, HW, C) uint8 (C = 3T, frame-major RGB, as np.concatenate(axis=2) leaves it) ->
+// out (B, C, HW) fp32 = ((u / 255) - mean[c % 3]) / std[c % 3], every step rounded to fp32 like the torch ops
+// (division, subtraction, division: no FMA contraction is possible).  One block transposes a 128-pixel strip
+// through shared memory: 16-byte coalesced reads, 512-byte coalesced channel rows out.
+constexpr int kIngestPix = 128;
+constexpr int kIngestMaxC = 96;
+__global__ void __launch_bounds__(kThreads)
+u8hwc_to_f32chw_norm_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int HW, int C, float m0, float m1,
+                            float m2, float s0, float s1, float s2) {
+  __shared__ __align__(16) uint8_t tile[kIngestPix * kIngestMaxC + 16];
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kIngestPix;
+  const int npix = min(kIngestPix, HW - p0);
+  const long long src = (static_cast<long long>(b) * HW + p0) * C;
+  const int nbytes = npix * C;
+  if ((src & 15) == 0) {
+    for (int i = threadIdx.x * 16; i < nbytes; i += blockDim.x * 16) {
+      if (i + 16 <= nbytes) {
+        *reinterpret_cast<uint4*>(tile + i) = __ldg(reinterpret_cast<const uint4*>(in + src + i));
+      } else {
+        for (int j = i; j < nbytes; ++j) tile[j] = in[src + j];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) tile[i] = in[src + i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    const int rgb = c % 3;
+    const float m = rgb == 0 ? m0 : (rgb == 1 ? m1 : m2);
+    const float sd = rgb == 0 ? s0 : (rgb == 1 ? s1 : s2);
+    float* dst = out + (static_cast<long long>(b) * C + c) * HW + p0;
+    for (int p = lane; p < npix; p += 32) {
+      const float x = __fdiv_rn(static_cast<float>(tile[p * C + c]), 255.f);
+      dst[p] = __fdiv_rn(__fsub_rn(x, m), sd);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ direct 3x3/2 stem
 // MobileNet-V2 features[0] (ACT/models/mobilenet.py:105): 3 -> 32 channels, 3x3, stride 2, pad 1, BN, ReLU6, straight
 // from the fp32 NCHW frame to NHWC fp16.  K = 27 is too thin for a 64-wide MMA k-block, so this layer runs on the
@@ -1098,6 +1140,16 @@ cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s) {
   return launch_pdl(fill_f32_kernel, dim3(grid_for(n)), dim3(kThreads), 0, s, p, v, n);
   return cudaGetLastError();
 }
+cudaError_t launch_u8hwc_to_f32chw_norm(const uint8_t* in, float* out, int B, int HW, int C, const float* mean3,
+                                        const float* std3, cudaStream_t s) {
+  if (B <= 0 || HW <= 0) return cudaSuccess;
+  if (C < 1 || C > kIngestMaxC || B > 65535) return cudaErrorInvalidValue;
+  dim3 grid((HW + kIngestPix - 1) / kIngestPix, B);
+  u8hwc_to_f32chw_norm_kernel<<<grid, kThreads, 0, s>>>(in, out, HW, C, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                        std3[2]);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   return launch_pdl(f32_to_f16_kernel, dim3(grid_for(n)), dim3(kThreads), 0, s, in, out, n);

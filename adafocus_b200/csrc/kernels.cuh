@@ -17,6 +17,8 @@ cudaError_t launch_action_to_yx(const float* action, int32_t* yx, int N, int H, 
 // Crop + fp32->fp16 + im2col staging of a 3-channel NCHW frame for a KHxKW / stride / pad stem convolution.
 // out[(n*Ho+oh)*Wo+ow][k], k = (kh*KW+kw)*3 + c (zero for k >= KH*KW*3 and for taps outside the P x P window).
 // yx holds one (y,x) per yx_div consecutive frames.
+cudaError_t launch_u8hwc_to_f32chw_norm(const uint8_t* in, float* out, int B, int HW, int C, const float* mean3,
+                                        const float* std3, cudaStream_t s);
 cudaError_t launch_stem_s2d(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W, int P,
                             int pad, int Hs, int Ws, int vt, cudaStream_t s);
 cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W,

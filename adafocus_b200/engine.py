@@ -519,6 +519,22 @@ class Engine:
         self._count()
         self.keep(t)
 
+    def frames_u8_to_f32(self, frames_u8, mean, std, out=None):
+        """Stack -> ToTorchFormatTensor(div=True) -> GroupNormalize (ACT/ops/transforms.py:303-336, 64-77) on the
+        device: frames_u8 (B, H, W, 3T) uint8 -> (B, 3T, H, W) fp32, bit-identical to the torch ops."""
+        b, h, w, c = frames_u8.shape
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.is_cuda
+        if out is None:
+            out = self.empty((b, c, h, w), torch.float32)
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == frames_u8.numel()
+        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+        check(self.lib.af_frames_u8_to_f32(self.h, _ptr(frames_u8), _ptr(out), b, h * w, c, m, sd, self._stream()),
+              "af_frames_u8_to_f32")
+        self._count()
+        self.keep(frames_u8, out)
+        return out
+
     def f32_to_f16(self, x, out=None):
         if out is None:
             out = self.empty(tuple(x.shape), torch.float16)

@@ -5,13 +5,22 @@ ImageNet-normalised, as produced by the reference's DataLoader (ACT/ops/transfor
 host->device, runs the fused stage-3 forward (ACT/main_dist.py:367-371) and copies the per-clip logits back to the
 host.  Two input slots and two CUDA streams overlap the H2D copy of batch i+1 with the compute of batch i; the policy
 loop, the crop and all ~190 layer launches replay natively from one recorded plan per slot.
+
+`input_format="u8_hwc"` moves the last two steps of the reference's transform chain onto the device: the host batches
+are then (B, H, W, 3T) uint8 -- the stacked decoded frames, before ToTorchFormatTensor / GroupNormalize
+(ACT/ops/transforms.py:303-336, 64-77) -- a quarter of the PCIe bytes; `af_frames_u8_to_f32` produces the bit-identical
+fp32 tensor in front of the plan.
 """
 import torch
 
+from .engine import get_engine
+
 
 class StreamingEvaluator:
-    def __init__(self, model, batch, device, slots=2):
+    def __init__(self, model, batch, device, slots=2, input_format="f32"):
+        assert input_format in ("f32", "u8_hwc")
         self.model, self.batch, self.device = model, batch, torch.device(device)
+        self.input_format = input_format
         t, s = model.num_segments, model.input_size
         self.plans = [model.fused_plan(batch, t, s, s, model.glance_size, self.device, True, slot=i)
                       for i in range(slots)]
@@ -22,12 +31,17 @@ class StreamingEvaluator:
         self.num_classes = self.plans[0].num_classes
         self.t = t
         self.out_host = [torch.empty(batch, self.num_classes, dtype=torch.float32).pin_memory() for _ in range(slots)]
-        self.h2d_bytes = batch * 3 * t * s * s * 4
+        self.h2d_bytes = batch * 3 * t * s * s * (4 if input_format == "f32" else 1)
         self.d2h_bytes = batch * self.num_classes * 4
+        self.u8 = None
+        if input_format == "u8_hwc":
+            self.eng = get_engine(self.device)
+            self.u8 = [torch.empty(batch, s, s, 3 * t, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+            self.mean, self.std = list(model.input_mean), list(model.input_std)
 
     def run(self, host_batches, collect=True):
-        """host_batches: iterable of pinned (B,3T,H,W) fp32 CPU tensors.  Returns the list of (B,C) host logits
-        (last time step, the reference's `pred`)."""
+        """host_batches: iterable of pinned (B,3T,H,W) fp32 CPU tensors -- or (B,H,W,3T) uint8 with
+        input_format="u8_hwc".  Returns the list of (B,C) host logits (last time step, the reference's `pred`)."""
         results = []
         n = len(self.plans)
         for s in range(n):
@@ -37,10 +51,12 @@ class StreamingEvaluator:
             plan = self.plans[s]
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(self.consumed[s])        # slot's previous compute has read its input
-                plan.input.copy_(hb, non_blocking=True)
+                (plan.input if self.u8 is None else self.u8[s]).copy_(hb, non_blocking=True)
                 self.copied[s].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self.copied[s])
+                if self.u8 is not None:
+                    self.eng.frames_u8_to_f32(self.u8[s], self.mean, self.std, out=plan.input)
                 plan.run()
                 self.consumed[s].record(self.compute_stream)
                 last = plan.logits.view(self.batch, self.t, -1)[:, -1, : self.num_classes]

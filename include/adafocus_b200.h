@@ -232,6 +232,14 @@ int af_class_ap(af_ctx* ctx, const float* probs, const int64_t* labels, int N, i
 int af_fill_f32(af_ctx* ctx, float* p, float v, int64_t n, void* stream);
 int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream);
 
+/* Frame ingest -- Stack -> ToTorchFormatTensor(div=True) -> GroupNormalize of the reference's loaders
+ * (ACT/ops/transforms.py:303-336, 64-77) on the device, so that clips cross PCIe as bytes:
+ * in (B, HW, C) uint8 with C = 3T channels in frame-major RGB order (what np.concatenate(frames, axis=2) produces)
+ * -> out (B, C, HW) fp32 = ((u / 255) - mean[c % 3]) / std[c % 3], each step rounded to fp32 (bit-identical to the
+ * torch ops).  mean3 / std3 are HOST pointers to three floats. */
+int af_frames_u8_to_f32(af_ctx* ctx, const uint8_t* in, float* out, int B, int HW, int C, const float* mean3,
+                        const float* std3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

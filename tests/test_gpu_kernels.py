@@ -257,6 +257,29 @@ def test_direct_stem_conv3x3s2_vs_torch(eng):
         assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3), float((out.float() - ref).abs().max())
 
 
+def test_frames_u8_ingest_bit_exact(eng):
+    """af_frames_u8_to_f32 == Stack -> ToTorchFormatTensor(div=True) -> GroupNormalize of the reference's loaders
+    (ACT/ops/transforms.py:303-336, 64-77), bit for bit, over every byte value in every channel position."""
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    torch.manual_seed(3)
+    for (b, h, w, c) in ((2, 16, 16, 48), (3, 7, 9, 24), (1, 224, 224, 48), (2, 5, 5, 3)):
+        u = torch.randint(0, 256, (b, h, w, c), dtype=torch.uint8)
+        if u.numel() >= 256 * c:   # every byte value in every channel position
+            u.view(-1, c)[:256] = torch.arange(256, dtype=torch.uint8)[:, None]
+        ref = []
+        for i in range(b):   # the reference chain, one clip at a time, with its own in-place fp32 ops
+            t = u[i].permute(2, 0, 1).contiguous().float().div(255)
+            for ch, m, sd in zip(t, mean * (c // 3), std * (c // 3)):
+                ch.sub_(m).div_(sd)
+            ref.append(t)
+        ref = torch.stack(ref)
+        out = eng.frames_u8_to_f32(u.to(DEV), mean, std)
+        assert out.shape == (b, c, h, w)
+        assert torch.equal(out.cpu(), ref)
+    with pytest.raises(Exception):
+        eng.frames_u8_to_f32(torch.zeros(1, 4, 4, 4, dtype=torch.uint8, device=DEV), mean, std)
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 @pytest.mark.parametrize("stride,c,hw,n", [(1, 32, 14, 3), (2, 96, 15, 3), (2, 144, 56, 3), (1, 960, 7, 3),
                                            (1, 32, 112, 2), (2, 96, 112, 2), (1, 144, 56, 2), (1, 192, 28, 5),

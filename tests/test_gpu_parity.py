@@ -163,6 +163,26 @@ def test_weights_reload_invalidates_packed_copy():
     assert torch.equal(a, c)
 
 
+def test_streaming_evaluator_u8_frames_equal_f32_path(c3):
+    """Clips shipped as stacked uint8 frames (B,H,W,3T) and normalised on the device give exactly the logits of the
+    same clips normalised on the host the reference's way and shipped as fp32 (B,3T,H,W)."""
+    from adafocus_b200.pipeline import StreamingEvaluator
+    model, args = c3["model"], c3["args"]
+    t, s = args.num_segments, args.input_size
+    g = torch.Generator().manual_seed(11)
+    u8 = [torch.randint(0, 256, (2, s, s, 3 * t), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    f32 = []
+    for u in u8:
+        x = u.permute(0, 3, 1, 2).contiguous().float().div(255)
+        for ch in range(3 * t):
+            x[:, ch].sub_(model.input_mean[ch % 3]).div_(model.input_std[ch % 3])
+        f32.append(x.pin_memory())
+    out_f = StreamingEvaluator(model, 2, DEV).run(f32)
+    out_u = StreamingEvaluator(model, 2, DEV, input_format="u8_hwc").run(u8)
+    for a, b in zip(out_f, out_u):
+        assert torch.equal(a, b)
+
+
 def test_full_size_properties():
     """cfg3 at bench size (64 clips): size-independent properties -- per-clip independence (a clip's logits do not
     depend on its batch mates), crop round trip through the public get_patch, determinism."""
