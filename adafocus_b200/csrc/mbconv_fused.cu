@@ -338,7 +338,8 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
   } else {
     // ============================ depthwise group (8 warps): E -> depthwise 3x3 + bias + ReLU6 -> A2 ============================
     const int dt = threadIdx.x - kFirstGroupWarp * 32 - kGroupThreads;   // 0..255
-    const int pairs = p.TW >> 1;
+    const int pairs = p.TW >> 1;                 // TW is 8, 16 or 32: powers of two, so the index splits are shifts
+    const int pairs_log2 = 31 - __clz(pairs);
     const int q_count = pairs * p.strips;
     const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
                              ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -350,9 +351,10 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       const int vc = min(64, p.Cexp - c * 64);
       const int eb = g % p.EB;
       const int n_ch = vc >> 2;             // 4-channel groups of this chunk: 16, 8 or 4
+      const int n_ch_log2 = 31 - __clz(n_ch);
       const int ch4 = dt & (n_ch - 1);
-      const int q0 = dt / n_ch;
-      const int q_step = kGroupThreads / n_ch;
+      const int q0 = dt >> n_ch_log2;
+      const int q_step = kGroupThreads >> n_ch_log2;
       const int ce = c * 64 + ch4 * 4;
       float2 w[9][2], bias[2];
       if (q0 < q_count) {
@@ -372,7 +374,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         const uint8_t* e_buf = s_e + eb * p.e_bytes;
         uint8_t* a2 = s_a2 + (g & 1) * 16384;
         for (int q = q0; q < q_count; q += q_step) {
-          const int strip = q / pairs, xp = q - strip * pairs;
+          const int strip = q >> pairs_log2, xp = q & (pairs - 1);
           const uint8_t* in = e_buf + ((strip * RO * S) * p.BW + xp * 2 * S) * kEPitch + ch4 * 8;
           const int prow0 = strip * RO * p.TW + 2 * xp;
           uint8_t* out0 = a2 + prow0 * 128 + (((ch4 >> 1) ^ (prow0 & 7)) << 4) + (ch4 & 1) * 8;
