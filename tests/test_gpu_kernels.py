@@ -113,6 +113,12 @@ CONV_CASES = [
     (5, 18, 18, 128, 128, 3, 2, 1, 1, False, False, None),      # P=144 shapes (36 -> 18 -> 9)
     (256, 32, 32, 64, 64, 1, 1, 0, 1, False, False, None),      # single-slice tiles, ~14 per CTA: groups alternate tiles
     (200, 16, 16, 32, 192, 1, 1, 0, 2, False, False, None),     # three slices per tile, ~3 tiles per CTA
+    # vertical-halo mode (stride 1, KH > 1, resident weights): row-shifted UMMA descriptors over one (TH+KH-1)-row box
+    (300, 32, 32, 64, 64, 3, 1, 1, 1, False, False, None),      # ~16 tiles per CTA: stage ring wraps, two solo groups
+    (3, 13, 9, 64, 32, 3, 1, 1, 2, False, False, None),         # odd sizes: partial tiles in both directions
+    (2, 20, 20, 16, 16, 5, 1, 2, 0, False, False, None),        # 5x5 filter: five vertical taps per box
+    (4, 12, 40, 128, 16, 3, 1, 1, 1, False, True, None),        # two channel slices, fp32 direct-store epilogue
+    (2, 11, 24, 64, 64, 4, 1, 0, 1, False, False, None),        # even filter height without padding (s2d stem shape)
 ]
 
 
