@@ -14,7 +14,7 @@ struct __align__(8) ConvSmemCtrl {
   uint64_t full[kConvMaxStages];
   uint64_t empty[kConvMaxStages];
   uint64_t tmem_full[4];   // [stage] or, when single-slice tiles alternate between a stage's two groups, [stage + 2*sub]
-  uint64_t tmem_empty[2];
+  uint64_t tmem_empty[4];  // [stage]; single-slice tiles that alternate between four groups use four accumulators: [it & 3]
   uint64_t wfull;          // resident-weights mode: all weight k-blocks have landed
   uint32_t tmem_base;
   uint32_t pad;
@@ -126,7 +126,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     }
     for (int a = 0; a < 4; ++a) mbar_init(&ctrl->tmem_full[a], 1);
     mbar_init(&ctrl->wfull, 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       // one arrive per warp of every epilogue group that reads the stage: both groups of the stage when a tile has
       // several 64-column slices (they split the slices), one group when it has a single slice (they alternate tiles)
       mbar_init(&ctrl->tmem_empty[a], ((p.tma_store && p.BN <= 64) || (VHALO && p.epi_groups == 2)) ? 4 : 8);
@@ -264,11 +264,14 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const uint32_t w_lo0 = smem_desc_lo(smem_u32(wres)), b_step = static_cast<uint32_t>(stage_b_bytes) >> 4;
       if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // accumulator of this tile: two 256-column stages, or -- single-slice tiles handled by four alternating
+        // epilogue groups -- four 128-column ones, so that four tiles are in flight between the MMA and the epilogue
         const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait_backoff(&ctrl->tmem_empty[as], aphase ^ 1, bo);
+        const int ai = alternate_tiles ? (it & 3) : as;
+        const uint32_t aphase = alternate_tiles ? (it >> 2) & 1 : (it >> 1) & 1;
+        mbar_wait_backoff(&ctrl->tmem_empty[ai], aphase ^ 1, bo);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kConvMaxBlockN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(alternate_tiles ? ai * 128 : as * kConvMaxBlockN);
         if constexpr (VHALO) {
           for (int kw = 0; kw < p.KW; ++kw) {
             for (int cb = 0; cb < p.cblks; ++cb) {
@@ -377,8 +380,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const uint32_t aphase = alternate_tiles ? (it >> 2) & 1 : (it >> 1) & 1;
       uint64_t* acc_full = &ctrl->tmem_full[alternate_tiles ? as + 2 * sub : as];
       const int co_base = nb * p.BN;
+      const int ai = alternate_tiles ? as + 2 * sub : as;   // accumulator index (== it & 3 when tiles alternate)
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(as * kConvMaxBlockN);
+                             static_cast<uint32_t>(alternate_tiles ? ai * 128 : as * kConvMaxBlockN);
       if (p.tma_store) {
         // ---- fp16 output: TMEM -> registers -> swizzled smem slice (128 rows x 64 ch) -> TMA store
         if (nb != loaded_nb) {
@@ -407,7 +411,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               // this group's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
+              if (lane == 0) mbar_arrive(&ctrl->tmem_empty[ai]);
             }
             if (hf == 0) {
               // the group's staging buffer may still be feeding its previous TMA store
@@ -483,7 +487,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as]);
+        if (lane == 0) mbar_arrive(&ctrl->tmem_empty[ai]);
       }
     }
     if (p.tma_store && et == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
