@@ -85,6 +85,40 @@ __device__ __forceinline__ void epilogue_half_slice_act(int act, const uint32_t 
   else epilogue_half_slice<kActNone>(v, sc, bi, srow, row, chunk0);
 }
 
+// Tile index -> (n-block, tile column, tile row, image group) as a mixed-radix counter advanced by a fixed step: the
+// persistent loops move by gridDim.x (or 2 * gridDim.x) tiles per iteration, and decoding every tile with four
+// integer divisions costs the single-thread roles ~1k cycles per tile -- more than a one-k-block tile's MMAs.
+struct TileCursor {
+  int nb, tw, th, tn;
+  int d_nb, d_tw, d_th, d_tn;
+  __device__ __forceinline__ void init(int tile, int step, const ConvKernelParams& p) {
+    nb = tile % p.n_blocks;
+    int r = tile / p.n_blocks;
+    tw = r % p.tiles_w;
+    r /= p.tiles_w;
+    th = r % p.tiles_h;
+    tn = r / p.tiles_h;
+    d_nb = step % p.n_blocks;
+    r = step / p.n_blocks;
+    d_tw = r % p.tiles_w;
+    r /= p.tiles_w;
+    d_th = r % p.tiles_h;
+    d_tn = r / p.tiles_h;
+  }
+  __device__ __forceinline__ void advance(const ConvKernelParams& p) {
+    nb += d_nb;
+    int c = nb >= p.n_blocks ? 1 : 0;
+    nb -= c ? p.n_blocks : 0;
+    tw += d_tw + c;
+    c = tw >= p.tiles_w ? 1 : 0;
+    tw -= c ? p.tiles_w : 0;
+    th += d_th + c;
+    c = th >= p.tiles_h ? 1 : 0;
+    th -= c ? p.tiles_h : 0;
+    tn += d_tn + c;
+  }
+};
+
 template <bool VHALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
@@ -186,13 +220,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         for (int kb = 0; kb < num_kb; ++kb)
           tma_load_2d(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, &ctrl->wfull, kb * kConvBlockK, 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nb = tile % p.n_blocks;
-        const int mt = tile / p.n_blocks;
-        const int tw_i = mt % p.tiles_w;
-        const int th_i = (mt / p.tiles_w) % p.tiles_h;
-        const int tn_i = mt / (p.tiles_w * p.tiles_h);
-        const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+      TileCursor cur;
+      cur.init(blockIdx.x, gridDim.x, p);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, cur.advance(p)) {
+        const int nb = cur.nb;
+        const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = cur.tn * p.TN;
         int kb = 0;
         if constexpr (VHALO) {
           for (int kw = 0; kw < p.KW; ++kw) {
@@ -263,7 +295,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem)), a_step = static_cast<uint32_t>(stage_bytes) >> 4;
       const uint32_t w_lo0 = smem_desc_lo(smem_u32(wres)), b_step = static_cast<uint32_t>(stage_b_bytes) >> 4;
       if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int mma_nb = static_cast<int>(blockIdx.x) % p.n_blocks;
+      const int mma_dnb = static_cast<int>(gridDim.x) % p.n_blocks;
+      for (int tile = blockIdx.x; tile < total_tiles;
+           tile += gridDim.x, ++it, mma_nb = mma_nb + mma_dnb >= p.n_blocks ? mma_nb + mma_dnb - p.n_blocks : mma_nb + mma_dnb) {
         // accumulator of this tile: two 256-column stages, or -- single-slice tiles handled by four alternating
         // epilogue groups -- four 128-column ones, so that four tiles are in flight between the MMA and the epilogue
         const int as = it & 1;
@@ -313,7 +348,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         if (p.res_mma) {
           // acc[:, j*64 .. j*64+nj) += R_j (128 x 64 fp16) * I (64 x nj): the residual add, exact in fp32
-          const int nb = tile % p.n_blocks;
+          const int nb = mma_nb;
           const uint64_t di = make_smem_desc_sw128(smem_u32(ident));
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             const int nj = p.BN - j * 64 < 64 ? p.BN - j * 64 : 64;
@@ -365,15 +400,16 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     const bool alternate_tiles = p.tma_store && nslices == 1 && !solo;
     const int sl_first = (alternate_tiles || solo) ? 0 : sub, sl_step = (alternate_tiles || solo) ? 1 : 2;
     pdl_wait_prior_grid();
-    for (int it = as; !(solo && sub == 1) && blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles; it += 2) {
+    TileCursor cur;
+    {
+      const long long first = blockIdx.x + static_cast<long long>(as) * gridDim.x;
+      cur.init(first < total_tiles ? static_cast<int>(first) : 0, 2 * static_cast<int>(gridDim.x), p);
+    }
+    for (int it = as; !(solo && sub == 1) && blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles;
+         it += 2, cur.advance(p)) {
       if (alternate_tiles && ((it >> 1) & 1) != sub) continue;
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int nb = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
-      const int tw_i = mt % p.tiles_w;
-      const int th_i = (mt / p.tiles_w) % p.tiles_h;
-      const int tn_i = mt / (p.tiles_w * p.tiles_h);
-      const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+      const int nb = cur.nb;
+      const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = cur.tn * p.TN;
       const int ow = ow0 + tw, oh = oh0 + th, n = n0 + tn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
       const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
