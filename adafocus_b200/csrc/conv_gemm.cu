@@ -284,7 +284,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    {
+      // the whole warp runs the loop (converged); one elected lane issues each MMA / commit
       const uint32_t idesc = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(p.BN));
       const bool alternate_tiles = p.tma_store && p.BN <= 64 && !(VHALO && p.epi_groups == 2);
       int stage = 0;
@@ -318,10 +319,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                 const uint32_t la = la0 + static_cast<uint32_t>(kh * p.TW) * 8u;   // kh rows down: kh * TW * 128 B
 #pragma unroll
                 for (int k = 0; k < kConvBlockK / 16; ++k)
-                  umma_f16_ss_lo(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+                  umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
                                  (kw | cb | kh | k) != 0 ? 1u : 0u);
               }
-              umma_commit(&ctrl->empty[stage]);
+              umma_commit_elect(&ctrl->empty[stage]);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -337,10 +338,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
-            umma_f16_ss_lo(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+            umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
                            (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
+          umma_commit_elect(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -349,18 +350,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         if (p.res_mma) {
           // acc[:, j*64 .. j*64+nj) += R_j (128 x 64 fp16) * I (64 x nj): the residual add, exact in fp32
           const int nb = mma_nb;
-          const uint64_t di = make_smem_desc_sw128(smem_u32(ident));
+          const uint32_t li = smem_desc_lo(smem_u32(ident));
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             const int nj = p.BN - j * 64 < 64 ? p.BN - j * 64 : 64;
             const uint32_t idesc_r = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(nj));
             mbar_wait_backoff(&ctrl->full[stage], phase, bo);
             tc_fence_after();
-            const uint64_t da = make_smem_desc_sw128(smem_u32(smem + static_cast<size_t>(stage) * stage_bytes));
+            const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
 #pragma unroll
             for (int k = 0; k < kConvBlockK / 16; ++k)
-              umma_f16_ss(tmem_d + static_cast<uint32_t>(j * 64), da + static_cast<uint64_t>(k * 2),
-                          di + static_cast<uint64_t>(k * 2), idesc_r, 1u);
-            umma_commit(&ctrl->empty[stage]);
+              umma_f16_ss_lo_elect(tmem_d + static_cast<uint32_t>(j * 64), la + static_cast<uint32_t>(k * 2),
+                                   li + static_cast<uint32_t>(k * 2), idesc_r, 1u);
+            umma_commit_elect(&ctrl->empty[stage]);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -369,7 +370,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         // accumulator complete -> epilogue.  With single-slice tiles the stage's two groups take alternate tiles and
         // each waits on its own barrier, so that every waiter sees every phase of the barrier it polls.
-        umma_commit(&ctrl->tmem_full[alternate_tiles ? as + 2 * ((it >> 1) & 1) : as]);
+        umma_commit_elect(&ctrl->tmem_full[alternate_tiles ? as + 2 * ((it >> 1) & 1) : as]);
       }
     }
   } else {
@@ -437,13 +438,16 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 #pragma unroll 1
         for (int sl = sl_first; sl < nslices; sl += sl_step) {
           const int c0 = sl * 64;
+          // a slice with at most 32 accumulator columns (BN = 32, or the tail of BN = 96 / 160) is one half-slice
+          const int nhf = (p.BN - c0 > 32) ? 2 : 1;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
+            if (hf >= nhf) break;
             uint32_t v[32];
             __syncwarp();
             tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + hf * 32), v);
             tmem_ld_wait();
-            if (hf == 1 && sl + sl_step >= nslices) {
+            if (hf == nhf - 1 && sl + sl_step >= nslices) {
               // this group's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
