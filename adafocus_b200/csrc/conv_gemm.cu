@@ -210,15 +210,16 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   pdl_launch_dependents();
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    {
+      // converged warp: every lane runs the loop, one elected lane issues each TMA / expect_tx
       pdl_wait_prior_grid();
       int stage = 0;
       uint32_t phase = 0;
       const int bo = p.backoff_ns;
       if (p.wres) {
-        mbar_arrive_expect_tx(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
+        mbar_arrive_expect_tx_elect(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
-          tma_load_2d(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, &ctrl->wfull, kb * kConvBlockK, 0);
+          tma_load_2d_elect(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, &ctrl->wfull, kb * kConvBlockK, 0);
       }
       TileCursor cur;
       cur.init(blockIdx.x, gridDim.x, p);
@@ -231,8 +232,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             for (int cb = 0; cb < p.cblks; ++cb) {
               mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-              mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_a_bytes));
-              tma_load_4d(sa, &maps.ah, &ctrl->full[stage], cb * kConvBlockK, ow0 + kw - p.pad, oh0 - p.pad, n0);
+              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_a_bytes));
+              tma_load_4d_elect(sa, &maps.ah, &ctrl->full[stage], cb * kConvBlockK, ow0 + kw - p.pad, oh0 - p.pad, n0);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -257,9 +258,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
               uint8_t* sb = sa + kStageABytes;
-              mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
-              tma_load_4d(sa, &maps.a[map_idx], &ctrl->full[stage], cb * kConvBlockK, cw, ch, n0);
-              if (!p.wres) tma_load_2d(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
+              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+              tma_load_4d_elect(sa, &maps.a[map_idx], &ctrl->full[stage], cb * kConvBlockK, cw, ch, n0);
+              if (!p.wres) tma_load_2d_elect(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -272,8 +273,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-            mbar_arrive_expect_tx(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
-            tma_load_4d(sa, &maps.res, &ctrl->full[stage], nb * p.BN + j * 64, ow0, oh0, n0);
+            mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
+            tma_load_4d_elect(sa, &maps.res, &ctrl->full[stage], nb * p.BN + j * 64, ow0, oh0, n0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
