@@ -108,10 +108,10 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
 
   if (warp == 0) {
     // ============================ TMA producer: weights once, then one input window per tile ============================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&ctrl->w_full, static_cast<uint32_t>(p.nc) * (8192u + w2_chunk));
-      for (int c = 0; c < p.nc; ++c) tma_load_2d(s_w1 + c * 8192, &maps.w1, &ctrl->w_full, 0, c * 64);
-      for (int c = 0; c < p.nc; ++c) tma_load_2d(s_w2 + c * w2_chunk, &maps.w2, &ctrl->w_full, c * 64, 0);
+    {   // converged warp: all lanes run the loop, one elected lane issues (ptx.cuh, *_elect)
+      mbar_arrive_expect_tx_elect(&ctrl->w_full, static_cast<uint32_t>(p.nc) * (8192u + w2_chunk));
+      for (int c = 0; c < p.nc; ++c) tma_load_2d_elect(s_w1 + c * 8192, &maps.w1, &ctrl->w_full, 0, c * 64);
+      for (int c = 0; c < p.nc; ++c) tma_load_2d_elect(s_w2 + c * w2_chunk, &maps.w2, &ctrl->w_full, c * 64, 0);
       pdl_wait_prior_grid();
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -121,13 +121,13 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         const int n = tile / tiles_per_img;
         const int r = tile - n * tiles_per_img;
         const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
-        mbar_arrive_expect_tx(&ctrl->x_full[xb], static_cast<uint32_t>(p.n_rows) * 128u);
-        tma_load_4d(s_x + xb * x_buf_bytes, &maps.x, &ctrl->x_full[xb], 0, tw_i * p.TW * S - 1, th_i * p.TH * S - 1, n);
+        mbar_arrive_expect_tx_elect(&ctrl->x_full[xb], static_cast<uint32_t>(p.n_rows) * 128u);
+        tma_load_4d_elect(s_x + xb * x_buf_bytes, &maps.x, &ctrl->x_full[xb], 0, tw_i * p.TW * S - 1, th_i * p.TH * S - 1, n);
       }
     }
   } else if (warp == 1) {
     // ============================ expand MMA issuer: D1[g & 1] = X * W1[chunk]^T as soon as the buffer is free ============================
-    if (lane == 0) {
+    {   // converged warp: all lanes run the loop, one elected lane issues (ptx.cuh, *_elect)
       const uint32_t idesc1 = make_idesc_f16_f32(128, 64);
       const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
                                ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -142,16 +142,17 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         if (c == 0) wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
         wait_backoff(&ctrl->d1_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t xa = smem_u32(s_x + xb * x_buf_bytes);
-        const uint64_t db = make_smem_desc_sw128(smem_u32(s_w1 + c * 8192));
+        const uint32_t la0 = smem_desc_lo(smem_u32(s_x + xb * x_buf_bytes));
+        const uint32_t lb = smem_desc_lo(smem_u32(s_w1 + c * 8192));
         for (int m = 0; m < p.Mtiles; ++m) {
-          const uint64_t da = make_smem_desc_sw128(xa + static_cast<uint32_t>(m) * 16384u);
+          const uint32_t la = la0 + static_cast<uint32_t>(m) * (16384u >> 4);
           const uint32_t d = tmem_base + static_cast<uint32_t>((g & 1) * d1_cols + m * 64);
           for (int k = 0; k < p.k1steps; ++k)
-            umma_f16_ss(d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc1, k != 0 ? 1u : 0u);
+            umma_f16_ss_lo_elect(d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc1,
+                                 k != 0 ? 1u : 0u);
         }
-        umma_commit(&ctrl->d1_full[g & 1]);
-        if (c == p.nc - 1) umma_commit(&ctrl->x_empty[xb]);   // the tile's input window has been consumed
+        umma_commit_elect(&ctrl->d1_full[g & 1]);
+        if (c == p.nc - 1) umma_commit_elect(&ctrl->x_empty[xb]);   // the tile's input window has been consumed
         if (++c == p.nc) {
           c = 0;
           ++it;
@@ -160,7 +161,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
     }
   } else if (warp == 2) {
     // ============================ project MMA issuer: D2[it & 1] += A2[g & 1] * W2[:, chunk]^T ============================
-    if (lane == 0) {
+    {   // converged warp: all lanes run the loop, one elected lane issues (ptx.cuh, *_elect)
       const uint32_t idesc2 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.cout_pad));
       const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles
                                ? (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -179,14 +180,14 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         tc_fence_after();
         const int vc = min(64, p.Cexp - c * 64);
         const int ks = (vc + 15) >> 4;
-        const uint64_t da = make_smem_desc_sw128(smem_u32(s_a2 + (g & 1) * 16384));
-        const uint64_t db = make_smem_desc_sw128(smem_u32(s_w2 + c * w2_chunk));
+        const uint32_t la = smem_desc_lo(smem_u32(s_a2 + (g & 1) * 16384));
+        const uint32_t lb = smem_desc_lo(smem_u32(s_w2 + c * w2_chunk));
         const uint32_t d2 = tmem_base + static_cast<uint32_t>(kD2Col + (it & 1) * 64);
         for (int k = 0; k < ks; ++k)
-          umma_f16_ss(d2, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc2,
-                      (c | k) != 0 ? 1u : 0u);
-        umma_commit(&ctrl->a2_empty[g & 1]);
-        if (c == p.nc - 1) umma_commit(&ctrl->d2_full[it & 1]);
+          umma_f16_ss_lo_elect(d2, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc2,
+                               (c | k) != 0 ? 1u : 0u);
+        umma_commit_elect(&ctrl->a2_empty[g & 1]);
+        if (c == p.nc - 1) umma_commit_elect(&ctrl->d2_full[it & 1]);
         if (++c == p.nc) {
           c = 0;
           ++it;
