@@ -77,6 +77,10 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
   const int opix_b = p.CB * 2, orow_b = p.TW * opix_b, oimg_b = p.TH * orow_b;
   const int pairs = p.TW >> 1;
   const int q_count = pairs * p.strips * p.NB;
+  // work item q = (nb * strips + strip) * pairs + xp, visited as q0, q0 + q_step, ..: a mixed-radix counter, so the
+  // tile loop has no integer divisions
+  const int xp0 = q0 % pairs, strip0 = (q0 / pairs) % p.strips, nb0 = q0 / (pairs * p.strips);
+  const int dxp = q_step % pairs, dstrip = (q_step / pairs) % p.strips, dnb = q_step / (pairs * p.strips);
 
   auto issue_load = [&](int sp, int buf) {
     const int tw_i = sp % p.tiles_w;
@@ -98,14 +102,18 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     mbar_wait(&ctrl->full[buf], (it >> 1) & 1);
     const uint8_t* tin = s_in + buf * p.in_bytes + chunk * 8;
     uint8_t* tout = s_out + buf * p.out_bytes + chunk * 8;
+    int xp = xp0, strip = strip0, nb = nb0;
     for (int q = q0; q < q_count; q += q_step) {
-      const int xp = q % pairs;
-      const int t2 = q / pairs;
-      const int strip = t2 % p.strips;
-      const int nb = t2 / p.strips;
       dw_strip<S, RO>(tin + nb * img_b + (strip * RO * S) * row_b + (xp * 2 * S) * pix_b, pix_b, row_b,
                       tout + nb * oimg_b + (strip * RO) * orow_b + (xp * 2) * opix_b,
                       tout + nb * oimg_b + (strip * RO) * orow_b + (xp * 2 + 1) * opix_b, orow_b, w, bias, p.act);
+      xp += dxp;
+      int carry = xp >= pairs ? 1 : 0;
+      xp -= carry ? pairs : 0;
+      strip += dstrip + carry;
+      carry = strip >= p.strips ? 1 : 0;
+      strip -= carry ? p.strips : 0;
+      nb += dnb + carry;
     }
     fence_proxy_async();
     __syncthreads();   // every read of s_in[buf] and every write of s_out[buf] is done

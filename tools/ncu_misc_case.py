@@ -23,7 +23,8 @@ def main():
     n = 1024
     for w in which:
         if w.startswith("dw"):
-            c, hw, s = {"dw32": (32, 112, 1), "dw144": (144, 56, 1), "dw96s2": (96, 112, 2)}[w]
+            c, hw, s = {"dw32": (32, 112, 1), "dw144": (144, 56, 1), "dw96s2": (96, 112, 2), "dw384": (384, 14, 1),
+                        "dw576": (576, 14, 1), "dw576s2": (576, 14, 2), "dw960": (960, 7, 1)}[w]
             x = torch.randn(n, hw, hw, c, device=dev).half()
             w9 = torch.randn(9, c, device=dev)
             sc, bi = torch.ones(c, device=dev), torch.zeros(c, device=dev)
