@@ -465,37 +465,40 @@ dwconv3x3_kernel(const __half* __restrict__ in, const float* __restrict__ w9c, c
 __global__ void __launch_bounds__(kThreads)
 maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int Ho,
                     int Wo) {
+  // grid (x: output-column pairs x 8-channel groups, y: output row, z: image); a thread produces two adjacent output
+  // pixels of one 8-channel group from a 3 x 5 input window (the middle column feeds both): 15 loads for 2 outputs,
+  // 32-bit index math only
   pdl_sync();
   const int c8n = C >> 3;
-  const long long total = static_cast<long long>(N) * Ho * Wo * c8n;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % c8n);
-  long long pix = idx / c8n;
-  const int ow = static_cast<int>(pix % Wo);
-  const int oh = static_cast<int>((pix / Wo) % Ho);
-  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ((Wo + 1) >> 1) * c8n) return;
+  const int c8 = idx % c8n;
+  const int ow0 = (idx / c8n) * 2;
+  const int oh = blockIdx.y, n = blockIdx.z;
   const __half2 ninf = __float2half2_rn(-65504.f);
-  __half2 m[4] = {ninf, ninf, ninf, ninf};
+  __align__(16) __half2 m0[4] = {ninf, ninf, ninf, ninf};
+  __align__(16) __half2 m1[4] = {ninf, ninf, ninf, ninf};
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int iy = oh * 2 + kh - 1;
     if (iy < 0 || iy >= H) continue;
+    const __half* rowp = in + (static_cast<long long>(n) * H + iy) * W * C + c8 * 8;
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int ix = ow * 2 + kw - 1;
+    for (int j = 0; j < 5; ++j) {
+      const int ix = ow0 * 2 - 1 + j;
       if (ix < 0 || ix >= W) continue;
-      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c8 * 8));
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(ix) * C));
       const __half2* xh = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], xh[j]);
+      for (int q = 0; q < 4; ++q) {
+        if (j <= 2) m0[q] = __hmax2(m0[q], xh[q]);
+        if (j >= 2) m1[q] = __hmax2(m1[q], xh[q]);
+      }
     }
   }
-  uint4 ov;
-  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) oh2[j] = m[j];
-  *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = ov;
+  __half* op = out + ((static_cast<long long>(n) * Ho + oh) * Wo + ow0) * C + c8 * 8;
+  *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(m0);
+  if (ow0 + 1 < Wo) *reinterpret_cast<uint4*>(op + C) = *reinterpret_cast<const uint4*>(m1);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1013,8 +1016,11 @@ cudaError_t launch_dwconv3x3(const __half* in, const float* w9c, const float* sc
 cudaError_t launch_maxpool3x3s2(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
-  return launch_pdl<false>(maxpool3x3s2_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out, N, H, W, C, Ho, Wo);
+  if (N > 65535 || Ho > 65535) return cudaErrorInvalidValue;
+  const int per_row = ((Wo + 1) / 2) * (C / 8);
+  const int threads = per_row >= kThreads ? kThreads : (per_row + 31) / 32 * 32;
+  dim3 grid((per_row + threads - 1) / threads, Ho, N);
+  return launch_pdl<false>(maxpool3x3s2_kernel, grid, dim3(threads), 0, s, in, out, N, H, W, C, Ho, Wo);
   return cudaGetLastError();
 }
 
