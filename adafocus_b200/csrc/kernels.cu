@@ -215,14 +215,13 @@ template <int VT>
 __global__ void __launch_bounds__(kThreads)
 stem_s2d_kernel(const float* __restrict__ frames, const int32_t* __restrict__ yx, int yx_div,
                 __half* __restrict__ out, int N, int H, int W, int P, int pad, int Hs, int Ws) {
+  // block = 32 x 8 pixels of one image (grid: x tiles, y tiles, image): no integer divisions
   pdl_sync();
-  const long long total = static_cast<long long>(N) * Hs * Ws;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int X = static_cast<int>(idx % Ws);
-    const long long t = idx / Ws;
-    const int Y = static_cast<int>(t % Hs);
-    const int n = static_cast<int>(t / Hs);
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (X < Ws && Y < Hs) {
+    const long long idx = (static_cast<long long>(n) * Hs + Y) * Ws + X;
     int y0 = 0, x0 = 0;
     if (yx != nullptr) {
       const int e = n / yx_div;
@@ -981,12 +980,13 @@ cudaError_t launch_stem_im2col(const float* frames, const int32_t* yx, int yx_di
 cudaError_t launch_stem_s2d(const float* frames, const int32_t* yx, int yx_div, __half* out, int N, int H, int W, int P,
                             int pad, int Hs, int Ws, int vt, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  const long long total = static_cast<long long>(N) * Hs * Ws;
+  if (N > 65535) return cudaErrorInvalidValue;
+  const dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, N);
   if (vt == 2)
-    return launch_pdl<false>(stem_s2d_kernel<2>, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
-                             yx_div < 1 ? 1 : yx_div, out, N, H, W, P, pad, Hs, Ws);
-  return launch_pdl<false>(stem_s2d_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, s, frames, yx,
-                           yx_div < 1 ? 1 : yx_div, out, N, H, W, P, pad, Hs, Ws);
+    return launch_pdl<false>(stem_s2d_kernel<2>, grid, dim3(kThreads), 0, s, frames, yx, yx_div < 1 ? 1 : yx_div, out,
+                             N, H, W, P, pad, Hs, Ws);
+  return launch_pdl<false>(stem_s2d_kernel<1>, grid, dim3(kThreads), 0, s, frames, yx, yx_div < 1 ? 1 : yx_div, out, N,
+                           H, W, P, pad, Hs, Ws);
 }
 
 cudaError_t launch_stem_conv3x3s2(const float* frames, const float* w27, const float* scale, const float* bias,
