@@ -119,6 +119,10 @@ CONV_CASES = [
     (2, 20, 20, 16, 16, 5, 1, 2, 0, False, False, None),        # 5x5 filter: five vertical taps per box
     (4, 12, 40, 128, 16, 3, 1, 1, 1, False, True, None),        # two channel slices, fp32 direct-store epilogue
     (2, 11, 24, 64, 64, 4, 1, 0, 1, False, False, None),        # even filter height without padding (s2d stem shape)
+    # weight-stationary mode (several n-blocks, >= 2 tiles per SM): a CTA keeps its n-block's weights in smem
+    (150, 16, 16, 128, 512, 1, 1, 0, 1, False, False, None),    # two n-blocks
+    (80, 32, 32, 256, 512, 1, 2, 0, 0, False, False, None),     # stride-2 downsample
+    (40, 14, 14, 96, 576, 1, 1, 0, 2, False, False, None),      # three n-blocks of 192, Cin padded to 128
 ]
 
 
@@ -162,6 +166,7 @@ RES_MMA_CASES = [
     (2, 7, 7, 960, 160, 1, 1, 0, 0),
     (5, 9, 9, 192, 64, 1, 1, 0, 2),
     (512, 16, 16, 64, 64, 3, 1, 1, 1),         # single-slice tiles with residual, ~7 per CTA
+    (160, 8, 8, 256, 1024, 1, 1, 0, 1),        # weight-stationary (four n-blocks) + residual tiles in the A ring
 ]
 
 
