@@ -69,6 +69,36 @@ def test_pack_conv_layout():
     assert torch.equal(pl.w[:5, :12], lin[:, perm].half())
 
 
+@pytest.mark.parametrize("k,pad,p,cout", [(7, 3, 32, 64), (3, 1, 24, 32), (5, 2, 20, 16)])
+def test_stem_space_to_depth_packing_equals_strided_conv(k, pad, p, cout):
+    """Host-side half of the tensor-core stems: the weights pack_stem_s2d produces, applied as a stride-1 R x 1 conv
+    over the sliding-window view of the 2x2 space-to-depth image (emulated here with torch ops exactly as
+    af_stem_s2d lays it out), equal the stride-2 k x k convolution (ACT/models/resnet.py:138, mobilenet.py:105)."""
+    import torch.nn.functional as F
+    from adafocus_b200.engine import pack_stem
+    torch.manual_seed(k)
+    w = torch.randn(cout, 3, k, k)
+    x = torch.randn(2, 3, p, p)
+    q = pack_stem(w, None, None, 2, pad, 0, device="cpu").s2d
+    assert q is not None and q.cin == 64 and q.kw == 1 and q.kh * q.vt == (k + 1) // 2
+    ref = F.conv2d(x, w, stride=2, padding=pad)
+    ho = ref.shape[2]
+    pe, win = 16 * q.vt, 64 // (16 * q.vt)            # channels per s2d pixel, X positions per view pixel
+    hs, ws = ho + q.kh - 1, ho + win - 1
+    xp = torch.zeros(2, 3, 2 * (hs + q.vt), 2 * (ws + 1))
+    xp[:, :, pad:pad + p, pad:pad + p] = x
+    s2d = torch.zeros(2, hs, ws, pe)
+    for v in range(q.vt):
+        for dy in range(2):
+            for dx in range(2):
+                for c in range(3):
+                    s2d[..., v * 16 + (dy * 2 + dx) * 3 + c] = xp[:, c, dy + 2 * v::2, dx::2][:, :hs, :ws]
+    view = torch.cat([s2d[:, :, sx:sx + ho, :] for sx in range(win)], dim=3)          # (2, hs, ho, 64)
+    wq = q.w.float().reshape(-1, q.kh, 64)[:cout]
+    out = sum(torch.einsum("nhwc,oc->nohw", view[:, r:r + ho], wq[:, r]) for r in range(q.kh))
+    assert float((out - ref).abs().max()) <= 2e-2 * float(ref.abs().max())            # fp16 weight rounding only
+
+
 def test_standard_action_table_matches_reference_literals():
     from adafocus_b200.models.gfv_net import standard_action_table
     t49 = standard_action_table(49)
