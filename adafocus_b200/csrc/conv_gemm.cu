@@ -69,8 +69,15 @@ __device__ __forceinline__ void epilogue_half_slice(const uint32_t (&v)[32], con
     __half2* oh2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-      if (ACT != kActNone) h = __hmax2(h, __float2half2_rn(0.f));
+      __half2 h;
+      if (ACT != kActNone) {
+        // ReLU folded into the conversion (cvt.rn.relu.f16x2.f32; first source operand = upper half)
+        uint32_t d;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x[2 * j + 1]), "f"(x[2 * j]));
+        h = *reinterpret_cast<__half2*>(&d);
+      } else {
+        h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      }
       if (ACT == kActRelu6) h = __hmin2(h, __float2half2_rn(6.f));
       oh2[j] = h;
     }

@@ -22,6 +22,14 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
+// fp32 pair -> packed fp16 with the ReLU folded into the conversion (cvt.rn.relu.f16x2.f32: negative results become
+// +0), one instruction instead of a conversion and a max.  The first PTX source operand is the UPPER half.
+__device__ __forceinline__ __half2 floats2half2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&d);
+}
+
 // One thread's share of a tile: 4 channels x 2 output columns x RO output rows.
 //   in  : top-left input pixel of the thread's window (its 4 channels), pixel pitch pix_b bytes, row pitch row_b bytes
 //   out0 / out1 : where the thread's left / right output pixel of row 0 goes (row pitch orow_b); two pointers so that
@@ -62,17 +70,18 @@ __device__ __forceinline__ void dw_strip(const uint8_t* __restrict__ in, int pix
         // output row o is complete
 #pragma unroll
         for (int px = 0; px < 2; ++px) {
-          __half2 h0 = __floats2half2_rn(acc[o][px][0].x, acc[o][px][0].y);
-          __half2 h1 = __floats2half2_rn(acc[o][px][1].x, acc[o][px][1].y);
+          __half2 h0, h1;
           if (act != 0) {
-            const __half2 z = __float2half2_rn(0.f);
-            h0 = __hmax2(h0, z);
-            h1 = __hmax2(h1, z);
+            h0 = floats2half2_relu(acc[o][px][0].x, acc[o][px][0].y);
+            h1 = floats2half2_relu(acc[o][px][1].x, acc[o][px][1].y);
             if (act == 2) {
               const __half2 six = __float2half2_rn(6.f);
               h0 = __hmin2(h0, six);
               h1 = __hmin2(h1, six);
             }
+          } else {
+            h0 = __floats2half2_rn(acc[o][px][0].x, acc[o][px][0].y);
+            h1 = __floats2half2_rn(acc[o][px][1].x, acc[o][px][1].y);
           }
           uint2 ov;
           ov.x = *reinterpret_cast<const uint32_t*>(&h0);

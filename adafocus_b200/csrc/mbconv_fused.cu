@@ -311,10 +311,9 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
                   __half2* oh2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    __half2 h = __floats2half2_rn(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
-                                                  __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
-                    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
-                    oh2[j] = h;
+                    const __half2 h = floats2half2_relu(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
+                                                        __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
+                    oh2[j] = __hmin2(h, __float2half2_rn(6.f));
                   }
                   if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
                   *reinterpret_cast<uint4*>(erow + i * 16) = ov;
