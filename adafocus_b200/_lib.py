@@ -37,7 +37,7 @@ class MbconvDesc(ctypes.Structure):
         ("in_", c_void_p), ("w1", c_void_p), ("bias1", c_void_p), ("dw_w", c_void_p), ("bias2", c_void_p),
         ("w2", c_void_p), ("bias3", c_void_p), ("residual", c_void_p), ("out", c_void_p),
         ("n", c_int32), ("h", c_int32), ("w_", c_int32), ("cin", c_int32), ("cexp", c_int32), ("cout", c_int32),
-        ("stride", c_int32), ("res_stride", c_int64),
+        ("stride", c_int32), ("res_stride", c_int64), ("bias1_in_w1", c_int32),
     ]
 
 

@@ -563,6 +563,12 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
   memset(&p, 0, sizeof(p));
   p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;
   if (!af::mbconv_plan(&p)) return fail(AF_ERR_INVALID, "af_mbconv_fused: unsupported shape");
+  p.bias_col = -1;
+  if (d->bias1_in_w1) {
+    if (d->cin + 2 > 64) return fail(AF_ERR_INVALID, "af_mbconv_fused: bias1_in_w1 needs cin + 2 <= 64");
+    p.bias_col = d->cin;
+    p.k1steps = (d->cin + 2 + 15) / 16;
+  }
   p.bias1 = d->bias1; p.dw_w = d->dw_w; p.bias2 = d->bias2; p.bias3 = d->bias3;
   p.residual = static_cast<const __half*>(d->residual);
   p.res_stride = d->res_stride;

@@ -136,10 +136,42 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       const int G = my_tiles * p.nc;   // channel chunks this CTA goes through, across all its tiles
       wait_backoff(&ctrl->w_full, 0);
       tc_fence_after();
+      // bias-in-MMA: lane l owns halo rows l, l+32, ..; their (by, bx) inside the halo box never change
+      int one_by[12], one_bx[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const int r = lane + 32 * j;
+        one_by[j] = r / p.BW;
+        one_bx[j] = r - one_by[j] * p.BW;
+      }
       int it = 0, c = 0;
       for (int g = 0; g < G; ++g) {
         const int xb = it % p.XB;
-        if (c == 0) wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
+        if (c == 0) {
+          wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
+          if (p.bias_col >= 0) {
+            // plant the constant-1 channel pair in every in-image pixel of the freshly landed window (TMA zero-filled
+            // the channels past Cin and the pixels outside the image): X * [W1 | bias_hi | bias_lo]^T then yields
+            // x W1^T + bias inside the image and exactly 0 outside it
+            const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int n = tile / tiles_per_img;
+            const int rr = tile - n * tiles_per_img;
+            const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
+            const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
+            uint8_t* xt = s_x + xb * x_buf_bytes;
+            const uint32_t chunk = static_cast<uint32_t>(p.bias_col >> 3), sub = static_cast<uint32_t>(p.bias_col & 7) * 2u;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              const int r = lane + 32 * j;
+              const int iy = iy0 + one_by[j], ix = ix0 + one_bx[j];
+              if (r < p.n_rows && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                *reinterpret_cast<uint32_t*>(xt + r * 128 + ((chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4) + sub) =
+                    0x3C003C00u;   // fp16 (1.0, 1.0)
+            }
+            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+          }
+        }
         wait_backoff(&ctrl->d1_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t la0 = smem_desc_lo(smem_u32(s_x + xb * x_buf_bytes));
@@ -301,22 +333,36 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
               if (row < p.n_rows) {
                 uint8_t* erow = e_buf + row * kEPitch + colhalf * 64;
                 const float* b1 = s_b1 + c * 64 + colhalf * 32;
-                const bool ok = pvalid[m];
+                if (p.bias_col >= 0) {
+                  // bias and the zero padding already came out of the MMA: ReLU6 + convert only
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 ba = *reinterpret_cast<const float4*>(b1 + i * 8);
-                  const float4 bb = *reinterpret_cast<const float4*>(b1 + i * 8 + 4);
-                  const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                  uint4 ov;
-                  __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+                  for (int i = 0; i < 4; ++i) {
+                    uint4 ov;
+                    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const __half2 h = floats2half2_relu(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
-                                                        __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
-                    oh2[j] = __hmin2(h, __float2half2_rn(6.f));
+                    for (int j = 0; j < 4; ++j)
+                      oh2[j] = __hmin2(floats2half2_relu(__uint_as_float(v[i * 8 + 2 * j]), __uint_as_float(v[i * 8 + 2 * j + 1])),
+                                       __float2half2_rn(6.f));
+                    *reinterpret_cast<uint4*>(erow + i * 16) = ov;
                   }
-                  if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
-                  *reinterpret_cast<uint4*>(erow + i * 16) = ov;
+                } else {
+                  const bool ok = pvalid[m];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 ba = *reinterpret_cast<const float4*>(b1 + i * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(b1 + i * 8 + 4);
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    uint4 ov;
+                    __half2* oh2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const __half2 h = floats2half2_relu(__uint_as_float(v[i * 8 + 2 * j]) + bv[2 * j],
+                                                          __uint_as_float(v[i * 8 + 2 * j + 1]) + bv[2 * j + 1]);
+                      oh2[j] = __hmin2(h, __float2half2_rn(6.f));
+                    }
+                    if (!ok) ov = make_uint4(0u, 0u, 0u, 0u);   // depthwise zero padding lives in the expanded domain
+                    *reinterpret_cast<uint4*>(erow + i * 16) = ov;
+                  }
                 }
               }
             }

@@ -25,7 +25,9 @@ struct MbParams {
   int tiles_w, tiles_h;
   int XB, EB, e_bytes;           // input window buffers / expanded-tile buffers (1 or 2 each), bytes per E buffer
   int nc;                        // 64-channel chunks of the expanded tensor
-  int k1steps;                   // ceil(Cin / 16)
+  int k1steps;                   // ceil(Cin / 16), or ceil((Cin + 2) / 16) with the bias columns
+  int bias_col;                  // >= 0: input channel pair (bias_col, bias_col+1) carries the constant 1 that multiplies the
+                                 // bias columns of w1 (af_mbconv_desc.bias1_in_w1); -1: bias added in the epilogue
   int cout_pad;                  // N of the project MMA (multiple of 16, <= 64)
   const float* bias1;            // [nc*64] expand bias (BN folded, zero padded)
   const float* dw_w;             // [9][nc*64] depthwise weights with the BN scale folded in, zero padded

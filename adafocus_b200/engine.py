@@ -131,9 +131,10 @@ class PackedMbconv:
     """An inverted-residual block (expand 1x1 -> depthwise 3x3 -> project 1x1, BatchNorms folded) in the layout of
     af_mbconv_fused: every BN scale is folded into the weights, the kernel only adds biases."""
 
-    def __init__(self, w1, b1, dw, b2, w2, b3, cin, cexp, cout, stride):
+    def __init__(self, w1, b1, dw, b2, w2, b3, cin, cexp, cout, stride, bias1_in_w1=False):
         self.w1, self.b1, self.dw, self.b2, self.w2, self.b3 = w1, b1, dw, b2, w2, b3
         self.cin, self.cexp, self.cout, self.stride = cin, cexp, cout, stride
+        self.bias1_in_w1 = bias1_in_w1
 
 
 def mbconv_supported(n, h, w, cin, cexp, cout, stride):
@@ -157,7 +158,14 @@ def pack_mbconv(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, device=None
     dw[:, :cexp] = (w_dw.detach().float().reshape(cexp, 9).to(device) * s2.detach().float().to(device)[:, None]).t()
     bias2 = torch.zeros(ce, dtype=torch.float32, device=device)
     bias2[:cexp] = b2.detach().float().to(device)
-    return PackedMbconv(e.w, e.bias, dw.contiguous(), bias2, pj.w, pj.bias, cin, cexp, cout, stride)
+    # expand bias as two extra K columns (fp16 hi + lo parts) multiplied by a constant-1 channel pair the kernel adds
+    # to the input tile: the bias add and the zeroing outside the image leave the epilogue (include/adafocus_b200.h)
+    bias_in_w1 = cin + 2 <= 64 and os.environ.get("AF_MB_NO_BIAS_MMA") is None
+    if bias_in_w1:
+        hi = e.bias.half()
+        e.w[:, cin] = hi
+        e.w[:, cin + 1] = (e.bias - hi.float()).half()
+    return PackedMbconv(e.w, e.bias, dw.contiguous(), bias2, pj.w, pj.bias, cin, cexp, cout, stride, bias_in_w1)
 
 
 class Workspace:
@@ -367,6 +375,7 @@ class Engine:
         d.residual = residual.data_ptr() if residual is not None else None
         d.n, d.h, d.w_, d.cin, d.cexp, d.cout, d.stride = n, h, w, cin, pm.cexp, pm.cout, s
         d.res_stride = residual.stride(-2) if residual is not None else 0
+        d.bias1_in_w1 = 1 if pm.bias1_in_w1 else 0
         check(self.lib.af_mbconv_fused(self.h, byref(d), self._stream()), "af_mbconv_fused")
         self._count()
         self.keep(x, pm.w1, pm.b1, pm.dw, pm.b2, pm.w2, pm.b3, residual, out)

@@ -151,6 +151,11 @@ typedef struct af_mbconv_desc {
   void* out;
   int32_t n, h, w_, cin, cexp, cout, stride;
   int64_t res_stride;
+  /* 1: the expand bias rides in the weights -- w1[:, cin] = fp16(bias1), w1[:, cin + 1] = fp16(bias1 - fp16(bias1)),
+   * needs cin + 2 <= 64; the kernel then plants a 1.0 pair in those two channels of every in-image pixel of the input
+   * tile, so the bias (to ~22 bits) and the zero padding of the expanded tensor both come out of the MMA and the
+   * expand epilogue is a pure ReLU6 + convert.  bias1 is ignored. */
+  int32_t bias1_in_w1;
 } af_mbconv_desc;
 int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream);
