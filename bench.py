@@ -329,7 +329,7 @@ def run_ours(a):
     roofline = {
         "bound": "tensor", "achieved": fl_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": fl_tflops / tf_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum over the 56 fL launches of one step at 64 clips/GPU
-        # (profiles/r1_v12_launches_dram_b64.csv, launches 74-129 of a replay); scaled linearly with the number of patches
+        # (profiles/r1_v15_launches_dram_b64.csv, launches 74-129 of a replay); scaled linearly with the number of patches
         "traffic": 16.71e9 * (b * t) / 1024.0,
         "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM), all fL launches of one step",
         "how": f"{b * t} patches x {FL_GFLOP_PER_PATCH} GFLOP (ResNet-50 trunk @128^2) / fL stage time {fl_ms:.3f} ms "
