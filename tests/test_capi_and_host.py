@@ -99,6 +99,29 @@ def test_stem_space_to_depth_packing_equals_strided_conv(k, pad, p, cout):
     assert float((out - ref).abs().max()) <= 2e-2 * float(ref.abs().max())            # fp16 weight rounding only
 
 
+def test_fused_block_packing_carries_the_expand_bias_in_two_weight_columns():
+    """pack_mbconv: BN scales folded into fp16 weights; with cin + 2 <= 64 the expand bias is stored as an fp16
+    high part + fp16 remainder in weight columns cin and cin + 1 (they multiply the constant-1 channel pair the kernel
+    plants in the input tile), reproducing the fp32 bias to ~2^-22."""
+    from adafocus_b200.engine import pack_mbconv
+    torch.manual_seed(5)
+    cin, cexp, cout = 24, 144, 32
+    w1, wd, w2 = torch.randn(cexp, cin), torch.randn(cexp, 1, 3, 3), torch.randn(cout, cexp)
+    s1, b1 = torch.rand(cexp) + 0.5, torch.randn(cexp)
+    s2, b2 = torch.rand(cexp) + 0.5, torch.randn(cexp)
+    s3, b3 = torch.rand(cout) + 0.5, torch.randn(cout)
+    pm = pack_mbconv(w1, s1, b1, wd, s2, b2, w2, s3, b3, 1, device="cpu")
+    assert pm.bias1_in_w1 and pm.w1.shape == (192, 64) and pm.w1.dtype == torch.float16
+    assert torch.equal(pm.w1[:cexp, :cin], (w1 * s1[:, None]).half())
+    rebuilt = pm.w1[:cexp, cin].float() + pm.w1[:cexp, cin + 1].float()
+    assert float((rebuilt - b1).abs().max()) <= 2 ** -20 * float(b1.abs().max())
+    assert float(pm.w1[cexp:].abs().max()) == 0 and float(pm.w1[:, cin + 2:].abs().max()) == 0
+    assert torch.allclose(pm.dw[:, :cexp].t().reshape(cexp, 1, 3, 3), wd * s2.view(-1, 1, 1, 1))
+    wide = pack_mbconv(torch.randn(384, 64), torch.ones(384), torch.zeros(384), torch.randn(384, 1, 3, 3), torch.ones(384),
+                       torch.zeros(384), torch.randn(64, 384), torch.ones(64), torch.zeros(64), 1, device="cpu")
+    assert not wide.bias1_in_w1          # no spare K columns at cin = 64: bias stays in the epilogue
+
+
 def test_standard_action_table_matches_reference_literals():
     from adafocus_b200.models.gfv_net import standard_action_table
     t49 = standard_action_table(49)
