@@ -7,7 +7,7 @@ from torch import nn
 
 from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv,
                       pack_stem)
-from ..models.mobilenet import _MBV2_SETTING, MobileNetV2Runner, _param_key
+from ..models.mobilenet import _FUSE_MIN_HW, _MBV2_SETTING, MobileNetV2Runner, _param_key
 
 
 def conv_bn(inp, oup, stride):
@@ -132,7 +132,8 @@ class SthGlancerRunner(MobileNetV2Runner):
             inp, y = x, x
             if e["shift"]:
                 y = eng.tsm_shift(x, self.tsm[0], x.shape[-1] // self.tsm[1])
-            if e["fused"] is not None and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"]):
+            if (e["fused"] is not None and y.shape[1] >= _FUSE_MIN_HW
+                    and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"])):
                 x = eng.mbconv(y, e["fused"], residual=inp if e["res"] else None)
                 if y is not inp:
                     eng.release(y)
