@@ -41,6 +41,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct af_plan {
   int device = 0;
   std::vector<Launch> launches;
+  std::vector<char> is_mark;       // launches[i] is a timing-mark event record (skipped under stream capture)
   std::vector<cudaEvent_t> marks;
   int kernel_launches = 0;
   ~af_plan() {
@@ -75,6 +76,7 @@ int dispatch(af_ctx* ctx, void* stream, const char* name, Launch fn) {
   if (ctx == nullptr) return fail(AF_ERR_INVALID, std::string(name) + ": null ctx");
   if (ctx->recording) {
     ctx->current->launches.push_back(std::move(fn));
+    ctx->current->is_mark.push_back(0);
     ctx->current->kernel_launches += 1;
     return AF_OK;
   }
@@ -191,7 +193,12 @@ int af_plan_run(af_plan* plan, void* stream) {
   if (plan == nullptr) return fail(AF_ERR_INVALID, "af_plan_run: null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(plan->device);
+  // Replays are CUDA-graph capturable (cudaStreamBeginCapture ... af_plan_run ... EndCapture): the kernel launches
+  // (PDL edges included) become graph nodes; the timing marks are left out of a captured replay.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
   for (size_t i = 0; i < plan->launches.size(); ++i) {
+    if (cap != cudaStreamCaptureStatusNone && plan->is_mark[i]) continue;
     cudaError_t e = plan->launches[i](s);
     if (e != cudaSuccess) {
       char buf[64];
@@ -214,6 +221,7 @@ int af_plan_mark(af_ctx* ctx, int* mark_index) {
   plan->marks.push_back(ev);
   if (mark_index != nullptr) *mark_index = static_cast<int>(plan->marks.size()) - 1;
   plan->launches.push_back([ev](cudaStream_t s) { return cudaEventRecord(ev, s); });
+  plan->is_mark.push_back(1);
   return AF_OK;
 }
 

@@ -241,6 +241,7 @@ class _FusedPlan:
     def __init__(self, model, b, t, h, w, g, device, share_scan):
         eng = get_engine(device)
         self.eng, self.b, self.t = eng, b, t
+        self.graph = None
         p = model.patch_size
         self.input = torch.empty(b, 3 * t, h, w, dtype=torch.float32, device=device)
         self.scan = self.input if share_scan else torch.empty(b, 3 * t, g, g, dtype=torch.float32, device=device)
@@ -275,7 +276,27 @@ class _FusedPlan:
                      _param_key(model.focuser.policy.policy_old), _param_key(model.classifier))
 
     def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return
         self.plan.run(torch.cuda.current_stream(self.input.device).cuda_stream)
+
+    def capture_graph(self):
+        """Capture one replay of the plan into a CUDA graph (small batches are launch-bound: ~170 launches of a few
+        microseconds each).  Later run() calls replay the graph; stage_ms() is unavailable for graph replays (the
+        timing marks are not captured)."""
+        dev = self.input.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.plan.run(side.cuda_stream)          # warm-up outside capture (function attributes, lazy init)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.plan.run(torch.cuda.current_stream(dev).cuda_stream)
+        self.graph = g
+        return g
 
     def stage_ms(self):
         """Device time of each stage in the last completed replay (call after a synchronize)."""

@@ -83,7 +83,7 @@ int af_ctx_sm_count(const af_ctx* ctx);
  * (ACT/models/gfv_net.py:95-133) run without returning to Python. */
 int af_plan_begin(af_ctx* ctx);
 int af_plan_end(af_ctx* ctx, af_plan** out);
-int af_plan_run(af_plan* plan, void* stream);
+int af_plan_run(af_plan* plan, void* stream); /* CUDA-graph capturable; timing marks are skipped under capture */
 int af_plan_num_launches(const af_plan* plan); /* kernel launches per replay (marks excluded) */
 /* Timing marks: while recording, af_plan_mark inserts a CUDA event record at this point of the sequence; after a
  * replay has completed, af_plan_mark_elapsed_ms gives the device time between two marks of that replay. */

@@ -183,6 +183,25 @@ def test_streaming_evaluator_u8_frames_equal_f32_path(c3):
         assert torch.equal(a, b)
 
 
+def test_plan_replay_is_cuda_graph_capturable(c3):
+    """af_plan_run under stream capture: the ~170 launches of a forward (PDL edges included) become one CUDA graph whose
+    replay writes bit-identical logits."""
+    model, args = c3["model"], c3["args"]
+    plan = model.fused_plan(2, args.num_segments, args.input_size, args.input_size, model.glance_size, DEV, True, slot=7)
+    plan.input.copy_(c3["xd"])
+    plan.run()
+    torch.cuda.synchronize()
+    ref = plan.logits.clone()
+    assert float((ref[:, : args.num_classes].cpu() - c3["ref"]["logits"]).abs().max()) <= 5e-3 * max(
+        1.0, float(c3["ref"]["logits"].abs().max()))
+    plan.capture_graph()
+    for _ in range(2):
+        plan.logits.zero_()
+        plan.run()
+        torch.cuda.synchronize()
+        assert torch.equal(plan.logits, ref)
+
+
 def test_full_size_properties():
     """cfg3 at bench size (64 clips): size-independent properties -- per-clip independence (a clip's logits do not
     depend on its batch mates), crop round trip through the public get_patch, determinism."""
