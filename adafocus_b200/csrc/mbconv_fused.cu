@@ -115,8 +115,8 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       pdl_wait_prior_grid();
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int xb = it % p.XB;
-        const uint32_t ph = static_cast<uint32_t>(it / p.XB) & 1u;
+        const int xb = it & (p.XB - 1);   // XB is 1 or 2
+        const uint32_t ph = static_cast<uint32_t>(it >> (p.XB - 1)) & 1u;
         while (!mbar_try_wait(&ctrl->x_empty[xb], ph ^ 1u)) __nanosleep(256);
         const int n = tile / tiles_per_img;
         const int r = tile - n * tiles_per_img;
@@ -146,9 +146,9 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       }
       int it = 0, c = 0;
       for (int g = 0; g < G; ++g) {
-        const int xb = it % p.XB;
+        const int xb = it & (p.XB - 1);   // XB is 1 or 2
         if (c == 0) {
-          wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it / p.XB) & 1u);
+          wait_backoff(&ctrl->x_full[xb], static_cast<uint32_t>(it >> (p.XB - 1)) & 1u);
           if (p.bias_col >= 0) {
             // plant the constant-1 channel pair in every in-image pixel of the freshly landed window (TMA zero-filled
             // the channels past Cin and the pixels outside the image): X * [W1 | bias_hi | bias_lo]^T then yields
@@ -316,11 +316,11 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       }
       for (int c = 0; c < p.nc; ++c, ++g) {
         const int vc = min(64, p.Cexp - c * 64);
-        const int eb = g % p.EB;
+        const int eb = g & (p.EB - 1);   // EB is 1 or 2
         // ---- expand epilogue: D1 (TMEM) -> +bias, ReLU6, zero outside the image -> E (smem, fp16)
         mbar_wait(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
         tc_fence_after();
-        mbar_wait(&ctrl->e_empty[eb], (static_cast<uint32_t>(g / p.EB) & 1u) ^ 1u);
+        mbar_wait(&ctrl->e_empty[eb], (static_cast<uint32_t>(g >> (p.EB - 1)) & 1u) ^ 1u);
         if (colhalf * 32 < vc) {
           uint8_t* e_buf = s_e + eb * p.e_bytes;
 #pragma unroll
@@ -395,7 +395,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
     int c = 0;
     for (int g = 0; g < G; ++g) {
       const int vc = min(64, p.Cexp - c * 64);
-      const int eb = g % p.EB;
+      const int eb = g & (p.EB - 1);   // EB is 1 or 2
       const int n_ch = vc >> 2;             // 4-channel groups of this chunk: 16, 8 or 4
       const int n_ch_log2 = 31 - __clz(n_ch);
       const int ch4 = dt & (n_ch - 1);
@@ -414,7 +414,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         bias[0] = make_float2(b2.x, b2.y);
         bias[1] = make_float2(b2.z, b2.w);
       }
-      mbar_wait(&ctrl->e_full[eb], static_cast<uint32_t>(g / p.EB) & 1u);
+      mbar_wait(&ctrl->e_full[eb], static_cast<uint32_t>(g >> (p.EB - 1)) & 1u);
       mbar_wait(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
       if (q0 < q_count) {
         const uint8_t* e_buf = s_e + eb * p.e_bytes;
