@@ -31,6 +31,31 @@ struct __align__(8) MbCtrl {
   uint32_t pad;
 };
 
+// tile index -> (tile column, tile row, image) as a mixed-radix counter advanced by gridDim.x per persistent-loop
+// iteration (no per-tile integer divisions, cf. TileCursor in conv_gemm.cu)
+struct MbCursor {
+  int tw, th, n, d_tw, d_th, d_n;
+  __device__ __forceinline__ void init(int tile, int step, const MbParams& p) {
+    tw = tile % p.tiles_w;
+    int r = tile / p.tiles_w;
+    th = r % p.tiles_h;
+    n = r / p.tiles_h;
+    d_tw = step % p.tiles_w;
+    r = step / p.tiles_w;
+    d_th = r % p.tiles_h;
+    d_n = r / p.tiles_h;
+  }
+  __device__ __forceinline__ void advance(const MbParams& p) {
+    tw += d_tw;
+    int c = tw >= p.tiles_w ? 1 : 0;
+    tw -= c ? p.tiles_w : 0;
+    th += d_th + c;
+    c = th >= p.tiles_h ? 1 : 0;
+    th -= c ? p.tiles_h : 0;
+    n += d_n + c;
+  }
+};
+
 __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
@@ -114,13 +139,13 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       for (int c = 0; c < p.nc; ++c) tma_load_2d_elect(s_w2 + c * w2_chunk, &maps.w2, &ctrl->w_full, c * 64, 0);
       pdl_wait_prior_grid();
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      MbCursor cur;
+      cur.init(blockIdx.x, gridDim.x, p);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it, cur.advance(p)) {
         const int xb = it & (p.XB - 1);   // XB is 1 or 2
         const uint32_t ph = static_cast<uint32_t>(it >> (p.XB - 1)) & 1u;
         while (!mbar_try_wait(&ctrl->x_empty[xb], ph ^ 1u)) __nanosleep(256);
-        const int n = tile / tiles_per_img;
-        const int r = tile - n * tiles_per_img;
-        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        const int n = cur.n, th_i = cur.th, tw_i = cur.tw;
         mbar_arrive_expect_tx_elect(&ctrl->x_full[xb], static_cast<uint32_t>(p.n_rows) * 128u);
         tma_load_4d_elect(s_x + xb * x_buf_bytes, &maps.x, &ctrl->x_full[xb], 0, tw_i * p.TW * S - 1, th_i * p.TH * S - 1, n);
       }
@@ -145,6 +170,8 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         one_bx[j] = r - one_by[j] * p.BW;
       }
       int it = 0, c = 0;
+      MbCursor cur;
+      cur.init(blockIdx.x, gridDim.x, p);
       for (int g = 0; g < G; ++g) {
         const int xb = it & (p.XB - 1);   // XB is 1 or 2
         if (c == 0) {
@@ -153,11 +180,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
             // plant the constant-1 channel pair in every in-image pixel of the freshly landed window (TMA zero-filled
             // the channels past Cin and the pixels outside the image): X * [W1 | bias_hi | bias_lo]^T then yields
             // x W1^T + bias inside the image and exactly 0 outside it
-            const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-            const int n = tile / tiles_per_img;
-            const int rr = tile - n * tiles_per_img;
-            const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
-            const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
+            const int iy0 = cur.th * p.TH * S - 1, ix0 = cur.tw * p.TW * S - 1;
             uint8_t* xt = s_x + xb * x_buf_bytes;
             const uint32_t chunk = static_cast<uint32_t>(p.bias_col >> 3), sub = static_cast<uint32_t>(p.bias_col & 7) * 2u;
 #pragma unroll
@@ -188,6 +211,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         if (++c == p.nc) {
           c = 0;
           ++it;
+          cur.advance(p);
         }
       }
     }
@@ -244,10 +268,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
     pdl_wait_prior_grid();
 
     // project epilogue of tile `pit` (this CTA's pit-th tile): D2 (TMEM) -> +bias (+ residual) -> fp16 -> staging -> TMA store
-    auto project_epilogue = [&](int pit, int tile) {
-      const int n = tile / tiles_per_img;
-      const int rr = tile - n * tiles_per_img;
-      const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
+    auto project_epilogue = [&](int pit, int n, int th_i, int tw_i) {
       mbar_wait(&ctrl->d2_full[pit & 1], (static_cast<uint32_t>(pit) >> 1) & 1u);
       tc_fence_after();
       if (et == 0) tma_store_wait_read0();    // the previous tile's store has released the staging tile
@@ -302,11 +323,11 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
       }
     };
 
-    int it = 0, g = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int n = tile / tiles_per_img;
-      const int rr = tile - n * tiles_per_img;
-      const int th_i = rr / p.tiles_w, tw_i = rr - th_i * p.tiles_w;
+    int it = 0, g = 0, prev_tile = -1, prev_n = 0, prev_th = 0, prev_tw = 0;
+    MbCursor cur;
+    cur.init(blockIdx.x, gridDim.x, p);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it, cur.advance(p)) {
+      const int n = cur.n, th_i = cur.th, tw_i = cur.tw;
       const int iy0 = th_i * p.TH * S - 1, ix0 = tw_i * p.TW * S - 1;
       bool pvalid[3];
 #pragma unroll
@@ -375,11 +396,14 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
           mbar_arrive(&ctrl->e_full[eb]);
         }
         // the previous tile's project epilogue runs one chunk late, so that its accumulator is complete by then
-        if (c == 0 && prev_tile >= 0) project_epilogue(it - 1, prev_tile);
+        if (c == 0 && prev_tile >= 0) project_epilogue(it - 1, prev_n, prev_th, prev_tw);
       }
       prev_tile = tile;
+      prev_n = n;
+      prev_th = th_i;
+      prev_tw = tw_i;
     }
-    if (prev_tile >= 0) project_epilogue(it - 1, prev_tile);
+    if (prev_tile >= 0) project_epilogue(it - 1, prev_n, prev_th, prev_tw);
     if (et == 0) tma_store_wait_all();
   } else {
     // ============================ depthwise group (8 warps): E -> depthwise 3x3 + bias + ReLU6 -> A2 ============================
