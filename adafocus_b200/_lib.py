@@ -78,9 +78,10 @@ SIGNATURES = {
     "af_nhwc_f16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "af_nchw_f32_to_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "af_gru_gates": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                             c_void_p, c_int64, c_int, c_int, c_void_p]),
+                             c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "af_split3_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "af_gru_sequence": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                c_void_p, c_int, c_int, c_int, c_void_p]),
+                                c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "af_policy_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "af_policy_head_continuous": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -56,3 +56,16 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+def source_hash():
+    """sha256 over the CUDA sources + headers the library is built from: identifies a build in profiles/traffic.json."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(SOURCES) + sorted(HEADERS):
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            h.update(name.encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]

@@ -678,20 +678,20 @@ int af_nchw_f32_to_nhwc_f16(af_ctx* ctx, const float* in, void* out, int N, int 
 
 int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* hg, const float* h_prev, float* h_new,
                  void* h_new_f16, void* hseq_f16, int64_t hseq_stride, float* hseq_f32, int64_t hseq_f32_stride, int B,
-                 int Hd, void* stream) {
+                 int Hd, int split, void* stream) {
   if (xg == nullptr || hg == nullptr || h_prev == nullptr || h_new == nullptr)
     return fail(AF_ERR_INVALID, "af_gru_gates: null tensor");
   __half* a = static_cast<__half*>(h_new_f16);
   __half* b = static_cast<__half*>(hseq_f16);
   return dispatch(ctx, stream, "af_gru_gates", [=](cudaStream_t s) {
     return af::launch_gru_gates(xg, xg_stride, hg, h_prev, h_new, a, b, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd,
-                                s);
+                                split, s);
   });
 }
 
 int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const float* b_hh, const float* h0, float* hbuf,
                     void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter, int B, int T, int Hd,
-                    void* stream) {
+                    int split, void* stream) {
   if (ctx == nullptr || xg == nullptr || w_hh_f16 == nullptr || b_hh == nullptr || hbuf == nullptr ||
       hseq_f16 == nullptr || counter == nullptr)
     return fail(AF_ERR_INVALID, "af_gru_sequence: null argument");
@@ -701,7 +701,7 @@ int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const fl
   __half* hs = static_cast<__half*>(hseq_f16);
   const int sms = ctx->sm_count;
   return dispatch(ctx, stream, "af_gru_sequence", [=](cudaStream_t s) {
-    return af::launch_gru_sequence(xg, w, b_hh, h0, hbuf, hs, hseq_stride, h_out, counter, B, T, Hd, sms, s);
+    return af::launch_gru_sequence(xg, w, b_hh, h0, hbuf, hs, hseq_stride, h_out, counter, B, T, Hd, sms, split, s);
   });
 }
 
@@ -785,6 +785,13 @@ int af_frames_u8_to_f32(af_ctx* ctx, const uint8_t* in, float* out, int B, int H
   return dispatch(ctx, stream, "af_frames_u8_to_f32", [=](cudaStream_t s) {
     return af::launch_u8hwc_to_f32chw_norm(in, out, B, HW, C, m, sd, s);
   });
+}
+
+int af_split3_f16(af_ctx* ctx, const float* in, int64_t in_stride, void* out, int rows, int cols, void* stream) {
+  if (in == nullptr || out == nullptr || in_stride < cols) return fail(AF_ERR_INVALID, "af_split3_f16: bad argument");
+  __half* o = static_cast<__half*>(out);
+  return dispatch(ctx, stream, "af_split3_f16",
+                  [=](cudaStream_t s) { return af::launch_split3_f16(in, in_stride, o, rows, cols, s); });
 }
 
 int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream) {

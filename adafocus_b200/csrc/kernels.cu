@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreads)
 gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float* __restrict__ hg,
                  const float* __restrict__ h_prev, float* __restrict__ h_new, __half* __restrict__ h_new_f16,
                  __half* __restrict__ hseq_f16, long long hseq_stride, float* __restrict__ hseq_f32,
-                 long long hseq_f32_stride, int B, int Hd) {
+                 long long hseq_f32_stride, int B, int Hd, int split) {
   pdl_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(B) * Hd) return;
@@ -591,8 +591,26 @@ gru_gates_kernel(const float* __restrict__ xg, long long xg_stride, const float*
   const float hp = h_prev[idx];
   const float hn = (1.f - z) * nn + z * hp;
   h_new[idx] = hn;
-  if (h_new_f16 != nullptr) h_new_f16[idx] = __float2half_rn(hn);
-  if (hseq_f16 != nullptr) hseq_f16[static_cast<long long>(b) * hseq_stride + j] = __float2half_rn(hn);
+  const __half hi = __float2half_rn(hn);
+  if (split) {
+    // split-precision operand rows [hi | lo | hi] (3*Hd wide): the next GEMM multiplies them with [W_hi | W_hi | W_lo]
+    const __half lo = __float2half_rn(hn - __half2float(hi));
+    if (h_new_f16 != nullptr) {
+      __half* o = h_new_f16 + static_cast<long long>(b) * 3 * Hd + j;
+      o[0] = hi;
+      o[Hd] = lo;
+      o[2 * Hd] = hi;
+    }
+    if (hseq_f16 != nullptr) {
+      __half* o = hseq_f16 + static_cast<long long>(b) * hseq_stride + j;
+      o[0] = hi;
+      o[Hd] = lo;
+      o[2 * Hd] = hi;
+    }
+  } else {
+    if (h_new_f16 != nullptr) h_new_f16[idx] = hi;
+    if (hseq_f16 != nullptr) hseq_f16[static_cast<long long>(b) * hseq_stride + j] = hi;
+  }
   if (hseq_f32 != nullptr) hseq_f32[static_cast<long long>(b) * hseq_f32_stride + j] = hn;
 }
 
@@ -617,22 +635,29 @@ __device__ __forceinline__ void gru_grid_barrier(unsigned int* counter, unsigned
   __syncthreads();
 }
 
+// SPLIT: w_hh rows are [W_hi | W_hi | W_lo] (3*Hd wide, the split-precision packing of the classifier head); the lo
+// parts are kept in shared memory as well and h_t is emitted as [hi | lo | hi] rows for the following GEMM.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gru_sequence_kernel(const float* __restrict__ xg, const __half* __restrict__ w_hh, const float* __restrict__ b_hh,
                     const float* __restrict__ h0, float* __restrict__ hbuf, __half* __restrict__ hseq_f16,
                     long long hseq_stride, float* __restrict__ h_out, unsigned int* __restrict__ counter, int B, int T,
                     int Hd) {
   extern __shared__ __align__(16) uint8_t gru_smem[];
-  __half* s_w = reinterpret_cast<__half*>(gru_smem);                                   // [3][JB][Hd]
-  float* s_b = reinterpret_cast<float*>(gru_smem + sizeof(__half) * 3 * kGruJB * Hd);  // [3][JB]
+  constexpr int kParts = SPLIT ? 2 : 1;
+  __half* s_w = reinterpret_cast<__half*>(gru_smem);                                   // [parts][3][JB][Hd]
+  float* s_b = reinterpret_cast<float*>(gru_smem + sizeof(__half) * kParts * 3 * kGruJB * Hd);  // [3][JB]
+  const long long w_stride = SPLIT ? 3ll * Hd : Hd;
   const int unit0 = blockIdx.x * kGruJB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = Hd >> 3;   // 16-byte chunks per row
   for (int i = threadIdx.x; i < 3 * kGruJB * chunks; i += blockDim.x) {
     const int row = i / chunks, ch = i - row * chunks;
     const int g = row / kGruJB, j = row - g * kGruJB;
-    reinterpret_cast<uint4*>(s_w)[i] =
-        __ldg(reinterpret_cast<const uint4*>(w_hh + (static_cast<long long>(g) * Hd + unit0 + j) * Hd) + ch);
+    const __half* src = w_hh + (static_cast<long long>(g) * Hd + unit0 + j) * w_stride;
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(src) + ch);
+    if (SPLIT)
+      reinterpret_cast<uint4*>(s_w + 3 * kGruJB * Hd)[i] = __ldg(reinterpret_cast<const uint4*>(src + 2 * Hd) + ch);
   }
   if (threadIdx.x < 3 * kGruJB) {
     const int g = threadIdx.x / kGruJB, j = threadIdx.x - g * kGruJB;
@@ -677,9 +702,22 @@ gru_sequence_kernel(const float* __restrict__ xg, const __half* __restrict__ w_h
             const __half2* pr = reinterpret_cast<const __half2*>(&wr);
             const __half2* pz = reinterpret_cast<const __half2*>(&wz);
             const __half2* pn = reinterpret_cast<const __half2*>(&wn);
+            uint4 lr, lz, ln;
+            if (SPLIT) {
+              const __half* s_lo = s_w + 3 * kGruJB * Hd;
+              lr = *reinterpret_cast<const uint4*>(s_lo + (0 * kGruJB + j) * Hd + k);
+              lz = *reinterpret_cast<const uint4*>(s_lo + (1 * kGruJB + j) * Hd + k);
+              ln = *reinterpret_cast<const uint4*>(s_lo + (2 * kGruJB + j) * Hd + k);
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float2 fr = __half22float2(pr[q]), fz = __half22float2(pz[q]), fn = __half22float2(pn[q]);
+              float2 fr = __half22float2(pr[q]), fz = __half22float2(pz[q]), fn = __half22float2(pn[q]);
+              if (SPLIT) {
+                const float2 gr = __half22float2(reinterpret_cast<const __half2*>(&lr)[q]);
+                const float2 gz = __half22float2(reinterpret_cast<const __half2*>(&lz)[q]);
+                const float2 gn = __half22float2(reinterpret_cast<const __half2*>(&ln)[q]);
+                fr.x += gr.x; fr.y += gr.y; fz.x += gz.x; fz.y += gz.y; fn.x += gn.x; fn.y += gn.y;
+              }
               ar = fmaf(fr.x, hv[i][2 * q], ar);
               ar = fmaf(fr.y, hv[i][2 * q + 1], ar);
               az = fmaf(fz.x, hv[i][2 * q], az);
@@ -709,7 +747,13 @@ gru_sequence_kernel(const float* __restrict__ xg, const __half* __restrict__ w_h
         const float nn = tanhf(x[2 * Hd + unit] + r * (my_n + s_b[2 * kGruJB + lane]));
         const float hn = (1.f - z) * nn + z * __ldcg(hb + unit);
         hnext[static_cast<long long>(b) * Hd + unit] = hn;
-        hseq_f16[(static_cast<long long>(b) * T + t) * hseq_stride + unit] = __float2half_rn(hn);
+        __half* hs = hseq_f16 + (static_cast<long long>(b) * T + t) * hseq_stride + unit;
+        const __half hi = __float2half_rn(hn);
+        hs[0] = hi;
+        if (SPLIT) {
+          hs[Hd] = __float2half_rn(hn - __half2float(hi));
+          hs[2 * Hd] = hi;
+        }
         if (t == T - 1 && h_out != nullptr) h_out[static_cast<long long>(b) * Hd + unit] = hn;
       }
     }
@@ -934,6 +978,23 @@ __global__ void fill_f32_kernel(float* p, float v, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// fp32 rows -> split-precision fp16 operand rows [hi | lo | hi] (3*cols wide): x = hi + lo to ~22 bits; a GEMM against
+// weights packed as [W_hi | W_hi | W_lo] then accumulates x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32 on the tensor core
+// (the W_lo x_lo term, 2^-22 relative, is dropped).  Used by the classifier head (ACT/models/gfv_net.py:427-435).
+__global__ void split3_f16_kernel(const float* __restrict__ in, long long in_stride, __half* __restrict__ out, int rows,
+                                  int cols) {
+  pdl_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int c = static_cast<int>(i % cols);
+  const long long r = i / cols;
+  const float v = in[r * in_stride + c];
+  const __half hi = __float2half_rn(v);
+  __half* o = out + r * 3 * cols + c;
+  o[0] = hi;
+  o[cols] = __float2half_rn(v - __half2float(hi));
+  o[2 * cols] = hi;
+}
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
   pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1049,21 +1110,27 @@ cudaError_t launch_nchw_f32_to_nhwc_f16(const float* in, __half* out, int N, int
 
 cudaError_t launch_gru_gates(const float* xg, long long xg_stride, const float* hg, const float* h_prev,
                              float* h_new, __half* h_new_f16, __half* hseq_f16, long long hseq_stride,
-                             float* hseq_f32, long long hseq_f32_stride, int B, int Hd, cudaStream_t s) {
+                             float* hseq_f32, long long hseq_f32_stride, int B, int Hd, int split, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   return launch_pdl(gru_gates_kernel, dim3(grid_for(static_cast<long long>(B) * Hd)), dim3(kThreads), 0, s, xg, xg_stride,
-                    hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd);
+                    hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_stride, hseq_f32, hseq_f32_stride, B, Hd, split);
+}
+
+cudaError_t launch_split3_f16(const float* in, long long in_stride, __half* out, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  return launch_pdl(split3_f16_kernel, dim3(grid_for(static_cast<long long>(rows) * cols)), dim3(kThreads), 0, s, in,
+                    in_stride, out, rows, cols);
 }
 
 cudaError_t launch_gru_sequence(const float* xg, const __half* w_hh, const float* b_hh, const float* h0, float* hbuf,
                                 __half* hseq_f16, long long hseq_stride, float* h_out, unsigned int* counter, int B,
-                                int T, int Hd, int sm_count, cudaStream_t s) {
+                                int T, int Hd, int sm_count, int split, cudaStream_t s) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   if (Hd % 256 != 0 || Hd / kGruJB > sm_count || Hd > 256 * kGruMaxK) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(__half) * 3 * kGruJB * Hd + sizeof(float) * 3 * kGruJB;
+  const size_t smem = sizeof(__half) * (split ? 2 : 1) * 3 * kGruJB * Hd + sizeof(float) * 3 * kGruJB;
+  auto* kern = split ? gru_sequence_kernel<true> : gru_sequence_kernel<false>;
   if (smem > 48 * 1024) {   // per-device attribute; this launch is rare (one per GRU sequence), so set it every time
-    cudaError_t e = cudaFuncSetAttribute(gru_sequence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
@@ -1078,8 +1145,7 @@ cudaError_t launch_gru_sequence(const float* xg, const __half* w_hh, const float
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gru_sequence_kernel, xg, w_hh, b_hh, h0, hbuf, hseq_f16, hseq_stride, h_out, counter,
-                            B, T, Hd);
+  return cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hh, h0, hbuf, hseq_f16, hseq_stride, h_out, counter, B, T, Hd);
 }
 
 cudaError_t launch_policy_head(const float* logits, long long logit_stride, int A, int grid_n, int rows, int H,

@@ -53,14 +53,15 @@ cudaError_t launch_nchw_f32_to_nhwc_f16(const float* in, __half* out, int N, int
 // xg: [B,3H] row stride xg_stride (includes b_ih), hg: [B,3H] contiguous (includes b_hh).
 cudaError_t launch_gru_gates(const float* xg, long long xg_stride, const float* hg, const float* h_prev,
                              float* h_new, __half* h_new_f16, __half* hseq_f16, long long hseq_stride,
-                             float* hseq_f32, long long hseq_f32_stride, int B, int Hd, cudaStream_t s);
+                             float* hseq_f32, long long hseq_f32_stride, int B, int Hd, int split, cudaStream_t s);
+cudaError_t launch_split3_f16(const float* in, long long in_stride, __half* out, int rows, int cols, cudaStream_t s);
 
 // Whole GRU sequence in one persistent launch (small batches): xg [B*T,3H] fp32 rows b*T+t (W_ih x + b_ih), w_hh fp16
 // [3H][H], b_hh fp32 [3H], h0 [B,H] or null (zeros); hbuf = 2*B*H floats of scratch, counter = one zero-initialised
 // uint32 (reset by the launcher).  Writes h_t as fp16 rows b*T+t of hseq_f16 and the final state to h_out (optional).
 cudaError_t launch_gru_sequence(const float* xg, const __half* w_hh, const float* b_hh, const float* h0, float* hbuf,
                                 __half* hseq_f16, long long hseq_stride, float* h_out, unsigned int* counter, int B,
-                                int T, int Hd, int sm_count, cudaStream_t s);
+                                int T, int Hd, int sm_count, int split, cudaStream_t s);
 
 // softmax over A logits, argmax (first maximum), action table lookup, floor(a*(H-P)) -> int32 (y,x).
 // ACT/models/ppo.py:84,94 + ACT/models/gfv_net.py:345-347 + ACT/models/utils.py:42.

@@ -44,10 +44,17 @@ class PackedConv:
         self.stride, self.pad, self.block_n, self.act = stride, pad, block_n, act
 
 
+def host(t):
+    """fp32 HOST copy of a parameter / buffer (one D2H memcpy).  All weight packing below is host arithmetic followed
+    by one H2D copy per packed tensor: repacking a model issues no device kernels at all (round 1 spent ~1000 small
+    torch launches per model here, which also hid the product kernels from launch-capped profilers)."""
+    return None if t is None else t.detach().to(dtype=torch.float32, device="cpu")
+
+
 def fold_bn(bn_weight, bn_bias, running_mean, running_var, eps):
-    """BatchNorm2d in eval mode as y = x*scale + bias (fp32)."""
-    scale = bn_weight.float() / torch.sqrt(running_var.float() + eps)
-    bias = bn_bias.float() - running_mean.float() * scale
+    """BatchNorm2d in eval mode as y = x*scale + bias (fp32, host tensors)."""
+    scale = host(bn_weight) / torch.sqrt(host(running_var) + eps)
+    bias = host(bn_bias) - host(running_mean) * scale
     return scale, bias
 
 
@@ -60,46 +67,59 @@ def pack_conv(weight, scale=None, bias=None, stride=1, pad=0, act=AF_ACT_NONE, b
 
     cin_perm: optional LongTensor; packed input channel j reads torch input channel cin_perm[j] (used to absorb the
     NCHW-flatten vs NHWC-flatten difference of ACT/models/ppo.py:36-37)."""
-    w = weight.detach().float()
+    device = device or weight.device
+    w = host(weight)
     if w.dim() == 2:
         w = w[:, :, None, None]
-    device = device or w.device
-    w = w.to(device)
     cout, cin, kh, kw = w.shape
     if cin_perm is not None:
-        w = w[:, cin_perm.to(device)]
+        w = w[:, cin_perm.cpu()]
     if fold_scale and scale is not None:
-        w = w * scale.detach().float().to(device)[:, None, None, None]
+        w = w * host(scale)[:, None, None, None]
         scale = None
     block_n = block_n or default_block_n(cout)
     cout_pad = round_up(cout, block_n)
     cblk = (cin + BLOCK_K - 1) // BLOCK_K
-    wp = torch.zeros(cout_pad, kh * kw, cblk * BLOCK_K, dtype=torch.float16, device=device)
+    wp = torch.zeros(cout_pad, kh * kw, cblk * BLOCK_K, dtype=torch.float16)
     wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).half()
     wp = wp.reshape(cout_pad, kh * kw * cblk * BLOCK_K).contiguous()
     sc = None
-    bi = torch.zeros(cout_pad, dtype=torch.float32, device=device)
+    bi = torch.zeros(cout_pad, dtype=torch.float32)
     if scale is not None or not fold_scale:
-        sc = torch.ones(cout_pad, dtype=torch.float32, device=device)
+        sc = torch.ones(cout_pad, dtype=torch.float32)
     if scale is not None:
-        sc[:cout] = scale.detach().float().to(device)
+        sc[:cout] = host(scale)
     if bias is not None:
-        bi[:cout] = bias.detach().float().to(device)
-    return PackedConv(wp, sc, bi, cin, cout, kh, kw, stride, pad, block_n, act)
+        bi[:cout] = host(bias)
+    return PackedConv(wp.to(device), sc.to(device) if sc is not None else None, bi.to(device), cin, cout, kh, kw,
+                      stride, pad, block_n, act)
+
+
+def pack_conv_split(weight, bias=None, device=None, block_n=None):
+    """Linear layer (cout, cin) for split-precision operands: K-concatenation [W_hi | W_hi | W_lo] with
+    W_hi = fp16(W), W_lo = fp16(W - W_hi), to be multiplied with activation rows [x_hi | x_lo | x_hi]
+    (af_split3_f16 / af_gru_gates split=1).  One ordinary tcgen05 GEMM with K = 3*cin then accumulates
+    x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32, i.e. ~22-bit operands.  cin must be a multiple of 64."""
+    w = host(weight)
+    assert w.dim() == 2 and w.shape[1] % BLOCK_K == 0, w.shape
+    hi = w.half().float()
+    lo = (w - hi).half().float()
+    pc = pack_conv(torch.cat([hi, hi, lo], 1), None, bias, device=device or weight.device, block_n=block_n)
+    pc.split = True
+    return pc
 
 
 def pack_stem(weight, scale, bias, stride, pad, act, device=None, kpad=None):
     """3-input-channel stem conv as a GEMM over the im2col matrix produced by af_stem_im2col:
     k = (r*kw+s)*3 + c."""
-    w = weight.detach().float()
-    device = device or w.device
-    w = w.to(device)
+    device = device or weight.device
+    w = host(weight)
     cout, cin, kh, kw = w.shape
     assert cin == 3
     kreal = kh * kw * 3
     # the im2col rows only need 16-byte granularity: the GEMM's TMA box zero-fills k beyond the row (147 -> 152, not 192)
     kpad = kpad or round_up(kreal, 8)
-    flat = torch.zeros(cout, kpad, dtype=torch.float32, device=device)
+    flat = torch.zeros(cout, kpad, dtype=torch.float32)
     flat[:, :kreal] = w.permute(0, 2, 3, 1).reshape(cout, kreal)
     pc = pack_conv(flat, scale, bias, 1, 0, act, device=device)
     pc.stem = dict(kh=kh, kw=kw, stride=stride, pad=pad, kpad=kpad)
@@ -117,7 +137,7 @@ def pack_stem_s2d(w, scale, bias, act, device):
     cout, _, k, _ = w.shape
     R = (k + 1) // 2
     vt = 2 if R == 2 else 1   # 3x3: fold the two vertical taps into the pixel too -> one k-block, a 1x1 conv
-    w64 = torch.zeros(cout, 64, R // vt, 1, dtype=torch.float32, device=device)
+    w64 = torch.zeros(cout, 64, R // vt, 1, dtype=torch.float32)
     for r in range(k):
         for s_ in range(k):
             ch = (s_ // 2) * 16 * vt + ((r // 2) % vt) * 16 + ((r % 2) * 2 + (s_ % 2)) * 3
@@ -145,19 +165,19 @@ def mbconv_supported(n, h, w, cin, cexp, cout, stride):
 def pack_mbconv(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, device=None):
     """w_exp (cexp, cin[,1,1]), w_dw (cexp, 1, 3, 3), w_proj (cout, cexp[,1,1]) fp32 in torch layout; (s, b) = folded
     BatchNorm of each conv.  Returns a PackedMbconv on `device`."""
-    w_exp = w_exp.detach().float().flatten(1)
-    w_proj = w_proj.detach().float().flatten(1)
     device = device or w_exp.device
+    w_exp = host(w_exp).flatten(1)
+    w_proj = host(w_proj).flatten(1)
     cexp, cin = w_exp.shape
     cout = w_proj.shape[0]
     ce = round_up(cexp, 64)
-    e = pack_conv(w_exp, s1, b1, act=AF_ACT_RELU6, block_n=64, device=device, fold_scale=True)
-    pj = pack_conv(w_proj, s3, b3, act=AF_ACT_NONE, block_n=round_up(cout, 16), device=device, fold_scale=True)
+    e = pack_conv(w_exp, s1, b1, act=AF_ACT_RELU6, block_n=64, device="cpu", fold_scale=True)
+    pj = pack_conv(w_proj, s3, b3, act=AF_ACT_NONE, block_n=round_up(cout, 16), device="cpu", fold_scale=True)
     assert e.w.shape == (ce, 64) and pj.w.shape == (round_up(cout, 16), ce), (e.w.shape, pj.w.shape)
-    dw = torch.zeros(9, ce, dtype=torch.float32, device=device)
-    dw[:, :cexp] = (w_dw.detach().float().reshape(cexp, 9).to(device) * s2.detach().float().to(device)[:, None]).t()
-    bias2 = torch.zeros(ce, dtype=torch.float32, device=device)
-    bias2[:cexp] = b2.detach().float().to(device)
+    dw = torch.zeros(9, ce, dtype=torch.float32)
+    dw[:, :cexp] = (host(w_dw).reshape(cexp, 9) * host(s2)[:, None]).t()
+    bias2 = torch.zeros(ce, dtype=torch.float32)
+    bias2[:cexp] = host(b2)
     # expand bias as two extra K columns (fp16 hi + lo parts) multiplied by a constant-1 channel pair the kernel adds
     # to the input tile: the bias add and the zeroing outside the image leave the epilogue (include/adafocus_b200.h)
     bias_in_w1 = cin + 2 <= 64 and os.environ.get("AF_MB_NO_BIAS_MMA") is None
@@ -165,7 +185,9 @@ def pack_mbconv(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, device=None
         hi = e.bias.half()
         e.w[:, cin] = hi
         e.w[:, cin + 1] = (e.bias - hi.float()).half()
-    return PackedMbconv(e.w, e.bias, dw.contiguous(), bias2, pj.w, pj.bias, cin, cexp, cout, stride, bias_in_w1)
+    d = device
+    return PackedMbconv(e.w.to(d), e.bias.to(d), dw.contiguous().to(d), bias2.to(d), pj.w.to(d), pj.bias.to(d), cin,
+                        cexp, cout, stride, bias_in_w1)
 
 
 class Workspace:
@@ -451,11 +473,12 @@ class Engine:
         return yx
 
     def gru_gates(self, xg, xg_stride, hg, h_prev, h_new, h_new_f16=None, hseq_f16=None, hseq_stride=0,
-                  hseq_f32=None, hseq_f32_stride=0):
+                  hseq_f32=None, hseq_f32_stride=0, split=False):
+        """split=True: the fp16 outputs are split-precision rows [hi | lo | hi] (h_new_f16 (B,3H); hseq rows 3H wide)."""
         b, hd = h_prev.shape
         check(self.lib.af_gru_gates(self.h, _ptr(xg), xg_stride, _ptr(hg), _ptr(h_prev), _ptr(h_new), _ptr(h_new_f16),
                                     _ptr(hseq_f16), hseq_stride, _ptr(hseq_f32), hseq_f32_stride, b, hd,
-                                    self._stream()), "af_gru_gates")
+                                    1 if split else 0, self._stream()), "af_gru_gates")
         self._count()
         self.keep(xg, hg, h_prev, h_new, h_new_f16, hseq_f16, hseq_f32)
 
@@ -465,14 +488,16 @@ class Engine:
         return b <= self.GRU_SEQ_MAX_BATCH and hd % 256 == 0 and hd <= 1024 and hd // 8 <= self.ctx.sm_count
 
     def gru_sequence(self, xg, pc_hh, b, t, hseq16, h0=None, h_out=None):
-        """All T steps of a GRU in one persistent launch. xg (B*T,3H) fp32, pc_hh = PackedConv of W_hh (+ b_hh)."""
-        hd = pc_hh.cin
-        assert pc_hh.w.shape == (3 * hd, hd) and xg.shape == (b * t, 3 * hd)
+        """All T steps of a GRU in one persistent launch. xg (B*T,3H) fp32, pc_hh = PackedConv of W_hh (+ b_hh);
+        a split-precision packing (pack_conv_split) makes hseq16 rows [hi | lo | hi]."""
+        split = bool(getattr(pc_hh, "split", False))
+        hd = pc_hh.cin // 3 if split else pc_hh.cin
+        assert pc_hh.w.shape == (3 * hd, pc_hh.cin) and xg.shape == (b * t, 3 * hd)
         hbuf = self.empty((2, b, hd), torch.float32)
         counter = self.empty((1,), torch.int32)
         check(self.lib.af_gru_sequence(self.h, _ptr(xg), _ptr(pc_hh.w), _ptr(pc_hh.bias), _ptr(h0), _ptr(hbuf),
                                        _ptr(hseq16), hseq16.stride(0), _ptr(h_out), _ptr(counter), b, t, hd,
-                                       self._stream()), "af_gru_sequence")
+                                       1 if split else 0, self._stream()), "af_gru_sequence")
         self._count()
         self.keep(xg, pc_hh.w, pc_hh.bias, h0, hbuf, hseq16, h_out, counter)
         self.release(hbuf)
@@ -542,6 +567,17 @@ class Engine:
               "af_frames_u8_to_f32")
         self._count()
         self.keep(frames_u8, out)
+        return out
+
+    def split3(self, x, out=None):
+        """fp32 (rows, cols) [row stride >= cols] -> split-precision fp16 rows [hi | lo | hi] (rows, 3*cols)."""
+        rows, cols = x.shape
+        if out is None:
+            out = self.empty((rows, 3 * cols), torch.float16)
+        check(self.lib.af_split3_f16(self.h, _ptr(x), x.stride(0), _ptr(out), rows, cols, self._stream()),
+              "af_split3_f16")
+        self._count()
+        self.keep(x, out)
         return out
 
     def f32_to_f16(self, x, out=None):

@@ -17,8 +17,9 @@ import math
 import torch
 from torch import nn
 
-from ..engine import get_engine, pack_conv
-from .mobilenet import _param_key, mobilenet_v2
+from ..engine import get_engine, pack_conv_split
+from ..packcache import cached_runner
+from .mobilenet import _param_key, invalidate_packed, mobilenet_v2
 from .ppo import PPO, Memory
 from .resnet import resnet50
 from .utils import get_patch
@@ -141,45 +142,50 @@ class Focuser(nn.Module):
 
 
 class GRUHeadRunner:
-    """RecurrentClassifier weights in kernel layout + the T-step schedule."""
+    """RecurrentClassifier weights in kernel layout + the T-step schedule.
+
+    The head is < 1 % of the FLOPs but every logit passes through it, so it runs at ~fp32 operand precision on the
+    tensor core: features and the recurrent state stay fp32 and enter the GEMMs as split-precision fp16 rows
+    [x_hi | x_lo | x_hi] against weights packed [W_hi | W_hi | W_lo] (engine.pack_conv_split)."""
 
     def __init__(self, clf, key=None):
         self.key = key
         g = clf.gru
         dev = g.weight_ih_l0.device
         self.hidden = clf.hidden_dim
-        self.gru_ih = pack_conv(g.weight_ih_l0, None, g.bias_ih_l0, device=dev)
-        self.gru_hh = pack_conv(g.weight_hh_l0, None, g.bias_hh_l0, device=dev, block_n=32)
-        self.fc = pack_conv(clf.fc.weight, None, clf.fc.bias, device=dev)
+        self.gru_ih = pack_conv_split(g.weight_ih_l0, g.bias_ih_l0, device=dev)
+        self.gru_hh = pack_conv_split(g.weight_hh_l0, g.bias_hh_l0, device=dev, block_n=32)
+        self.fc = pack_conv_split(clf.fc.weight, clf.fc.bias, device=dev)
         self.num_classes = clf.fc.weight.shape[0]
         self.logit_stride = (self.num_classes + 7) // 8 * 8
 
-    def sequence(self, eng, feat16, b, t, logits, h0=None, h_out=None):
-        """feat16 (B*T, F) fp16 rows b*T+t -> logits fp32 (B*T, logit_stride)."""
+    def sequence(self, eng, feat32, b, t, logits, h0=None, h_out=None):
+        """feat32 (B*T, F) fp32 rows b*T+t -> logits fp32 (B*T, logit_stride)."""
         hd = self.hidden
-        xg = eng.linear(feat16, self.gru_ih, out_f32=True)
+        feat3 = eng.split3(feat32)
+        xg = eng.linear(feat3, self.gru_ih, out_f32=True)
+        eng.release(feat3)
+        hseq3 = eng.empty((b * t, 3 * hd), torch.float16)
         if eng.can_gru_sequence(b, hd):
             # small batch: the whole T-step recurrence is one persistent warp-reduction kernel
-            hseq16 = eng.empty((b * t, hd), torch.float16)
-            eng.gru_sequence(xg, self.gru_hh, b, t, hseq16, h0=h0, h_out=h_out)
-            eng.linear(hseq16, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
+            eng.gru_sequence(xg, self.gru_hh, b, t, hseq3, h0=h0, h_out=h_out)
+            eng.linear(hseq3, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
             eng.release(xg)
-            eng.release(hseq16)
+            eng.release(hseq3)
             return
         h = eng.empty((b, hd), torch.float32) if h_out is None else h_out
         if h0 is None:
             eng.fill(h, 0.0)
         elif h0 is not h:
             h.copy_(h0)
-        h16 = eng.f32_to_f16(h)
+        h3 = eng.split3(h)
         hg = eng.empty((b, 3 * hd), torch.float32)
-        hseq16 = eng.empty((b * t, hd), torch.float16)
-        xg3, hs3 = xg.view(b, t, 3 * hd), hseq16.view(b, t, hd)
+        xg3, hs3 = xg.view(b, t, 3 * hd), hseq3.view(b, t, 3 * hd)
         for step in range(t):
-            eng.linear(h16, self.gru_hh, out=hg, out_f32=True, out_stride=3 * hd)
-            eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h16, hs3[:, step], t * hd)
-        eng.linear(hseq16, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
-        for tmp in (xg, h16, hg, hseq16) + ((h,) if h_out is None else ()):
+            eng.linear(h3, self.gru_hh, out=hg, out_f32=True, out_stride=3 * hd)
+            eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h3, hs3[:, step], t * 3 * hd, split=True)
+        eng.linear(hseq3, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
+        for tmp in (xg, h3, hg, hseq3) + ((h,) if h_out is None else ()):
             eng.release(tmp)
 
 
@@ -200,7 +206,7 @@ class RecurrentClassifier(nn.Module):
     def runner(self):
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = GRUHeadRunner(self, key)
+            self._runner = cached_runner(self, "GRUHeadRunner", lambda: GRUHeadRunner(self, key), key)
         return self._runner
 
     def _run(self, feature, h0, keep_state):
@@ -209,10 +215,10 @@ class RecurrentClassifier(nn.Module):
         b, t, f = feature.shape
         eng = get_engine(feature.device)
         r = self.runner()
-        feat16 = eng.f32_to_f16(feature.contiguous().view(b * t, f))
+        feat32 = feature.contiguous().view(b * t, f).float()
         logits = torch.empty(b * t, r.logit_stride, dtype=torch.float32, device=feature.device)
         h = torch.empty(b, self.hidden_dim, dtype=torch.float32, device=feature.device)
-        r.sequence(eng, feat16, b, t, logits, h0=h0, h_out=h)
+        r.sequence(eng, feat32, b, t, logits, h0=h0, h_out=h)
         logits = logits[:, : self.num_classes].contiguous()
         last_out = logits.reshape(b, t, -1)[:, -1, :].reshape(b, -1)
         return logits, last_out, h
@@ -247,7 +253,7 @@ class _FusedPlan:
         self.scan = self.input if share_scan else torch.empty(b, 3 * t, g, g, dtype=torch.float32, device=device)
         clf = model.classifier.runner()
         fdim = model.classifier.input_dim
-        self.feat16 = torch.zeros(b * t, fdim, dtype=torch.float16, device=device)
+        self.feat32 = torch.zeros(b * t, fdim, dtype=torch.float32, device=device)
         self.logits = torch.zeros(b * t, clf.logit_stride, dtype=torch.float32, device=device)
         self.num_classes = clf.num_classes
         glancer = model.glancer.net.runner()
@@ -259,15 +265,15 @@ class _FusedPlan:
             m0 = eng.mark()
             fmap = glancer.run_chunked(eng, self.scan.view(b * t, 3, g, g), model.fg_chunk)
             if model.with_glancer:
-                eng.avgpool(fmap, out_f16=self.feat16, out_f16_stride=fdim)
+                eng.avgpool(fmap, out_f32=self.feat32, out_f32_stride=fdim)
             m1 = eng.mark()
             self.yx, self.action_idx, self.action_yx = policy.rollout(eng, fmap, b, t, h, p)
             eng.release(fmap)
             m2 = eng.mark()
-            focuser.run_pooled_chunked(eng, self.input.view(b * t, 3, h, w), self.feat16[:, gdim:], fdim,
-                                       model.fl_chunk, yx=self.yx, patch=p)
+            focuser.run_pooled_chunked(eng, self.input.view(b * t, 3, h, w), self.feat32[:, gdim:], fdim,
+                                       model.fl_chunk, yx=self.yx, patch=p, out_f32=True)
             m3 = eng.mark()
-            clf.sequence(eng, self.feat16, b, t, self.logits)
+            clf.sequence(eng, self.feat32, b, t, self.logits)
             m4 = eng.mark()
             self.marks = {"fG": (m0, m1), "policy": (m1, m2), "fL": (m2, m3), "head": (m3, m4), "total": (m0, m4)}
         finally:
@@ -297,6 +303,10 @@ class _FusedPlan:
             self.plan.run(torch.cuda.current_stream(dev).cuda_stream)
         self.graph = g
         return g
+
+    def features(self):
+        """[global | local] features (B*T, F) of the last replay, as the classifier consumed them."""
+        return self.feat32
 
     def stage_ms(self):
         """Device time of each stage in the last completed replay (call after a synchronize)."""
@@ -349,8 +359,26 @@ class GFV(nn.Module):
     def train_mode(self, args):
         raise NotImplementedError("training stages are outside the inference hot path")
 
+    def _require_eval(self):
+        """The plans fold BatchNorm running statistics and drop dropout: that is only the reference's arithmetic in
+        eval mode (the reference would use batch statistics and classifier dropout in train mode)."""
+        if self.training or self.glancer.training or self.focuser.training or self.classifier.training:
+            raise NotImplementedError("adafocus_b200 implements inference only: call model.eval() first "
+                                      "(ACT/main_dist.py:316)")
+
+    def invalidate_packed(self):
+        """Drop every packed (kernel-layout) weight copy and recorded plan; call after editing weights in place through
+        `.data` (load_state_dict / .to() are tracked automatically)."""
+        for m in (self.glancer.net, self.focuser.net, self.classifier):
+            invalidate_packed(m)
+        if self.focuser.policy is not None:
+            invalidate_packed(self.focuser.policy.policy_old)
+            invalidate_packed(self.focuser.policy.policy)
+        self._plans.clear()
+
     # ------------------------------------------------------------------ fused stage-3 inference
     def fused_plan(self, b, t, h, w, g, device, share_scan, slot=0):
+        self._require_eval()
         key = (b, t, h, w, g, share_scan, str(device), slot)
         plan = self._plans.get(key)
         if plan is not None:
@@ -381,6 +409,7 @@ class GFV(nn.Module):
             raise NotImplementedError("training=True samples actions for PPO; only inference is implemented")
         if self.focuser.random:
             raise NotImplementedError("random_patch=True has no policy rollout; stage-3 inference needs a policy")
+        self._require_eval()
         inp, scan = kwargs["input"], kwargs["scan"]
         if not inp.is_cuda:
             raise RuntimeError("adafocus_b200 has no CPU path: inputs must be CUDA tensors")

@@ -9,7 +9,8 @@ import os
 import torch
 from torch import nn
 
-from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv,
+from ..packcache import cached_runner
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_supported, pack_conv, pack_mbconv,
                       pack_stem)
 
 # Experiment knob: blocks whose input is smaller than this run unfused (1x1 conv -> depthwise -> 1x1 conv).  Measured
@@ -82,7 +83,7 @@ class MobileNetV2(nn.Module):
         """Packed-weight runner, rebuilt when parameters were reloaded / moved."""
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = MobileNetV2Runner(self, key)
+            self._runner = cached_runner(self, "MobileNetV2Runner", lambda: MobileNetV2Runner(self, key), key)
         return self._runner
 
     def get_featmap(self, x):
@@ -99,8 +100,43 @@ class MobileNetV2(nn.Module):
         raise NotImplementedError("classification head of fG is outside the inference hot path (stage-0 training)")
 
 
+class _PackState:
+    __slots__ = ("epoch", "probes")
+
+    def __init__(self):
+        self.epoch = 0
+        self.probes = ()
+
+
+def _pack_state(module):
+    st = module.__dict__.get("_af_pack_state")
+    if st is None:
+        st = _PackState()
+        tensors = list(module.parameters()) + list(module.buffers())
+        st.probes = tuple(tensors[i] for i in sorted({0, len(tensors) // 2, len(tensors) - 1})) if tensors else ()
+
+        def bump(_m, _incompatible):
+            st.epoch += 1
+        # load_state_dict() runs the post hooks of every module it visits: registering on each sub-module catches a
+        # load on this module, on any ancestor and on any descendant
+        for sub in module.modules():
+            sub.register_load_state_dict_post_hook(bump)
+        module.__dict__["_af_pack_state"] = st
+    return st
+
+
+def invalidate_packed(module):
+    """Force the packed (kernel-layout) copy of `module`'s weights to be rebuilt on next use.  Needed only after
+    writes the hooks cannot see: in-place edits through `.data` / `torch.no_grad()` of individual tensors."""
+    _pack_state(module).epoch += 1
+
+
 def _param_key(module):
-    return tuple((p.data_ptr(), p._version) for p in module.state_dict().values())
+    """O(1) identity of a module's weights for the packed-copy caches: an epoch bumped by load_state_dict() post
+    hooks (on the module, its ancestors or descendants) + (data_ptr, _version) of three probe tensors, which change on
+    .to()/.cuda()/.half() and on in-place optimiser-style updates.  (Round 1 walked the whole state_dict per call.)"""
+    st = _pack_state(module)
+    return (id(module), st.epoch) + tuple((p.data_ptr(), p._version) for p in st.probes)
 
 
 class MobileNetV2Runner:
@@ -115,7 +151,7 @@ class MobileNetV2Runner:
         self.stem_direct = tuple(c0.weight.shape) == (32, 3, 3, 3) and c0.stride == (2, 2)
         if self.stem_direct:
             # fp32 [27][32], k = (r*3+s)*3 + c
-            self.stem_w = c0.weight.detach().float().permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
+            self.stem_w = host(c0.weight).permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
             self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
         # tensor-core form (space-to-depth + windowed 2x1 conv) -- preferred for even frame sizes
         self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
@@ -132,18 +168,18 @@ class MobileNetV2Runner:
                 entry["expand"] = None
             dw, bn = seq[0][0], seq[0][1]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-            entry["dw_w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
+            entry["dw_w"] = host(dw.weight).reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
             entry["dw_s"], entry["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
-            entry["_dw_raw"] = dw.weight.detach().float().to(dev)
+            entry["_dw_raw"], entry["_dw_sb"] = host(dw.weight), (s, b)
             pw, bn = seq[1], seq[2]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             entry["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=entry["res"])
-            entry["_proj"] = (pw.weight.detach().float().flatten(1).to(dev), s.to(dev), b.to(dev))
+            entry["_proj"] = (host(pw.weight).flatten(1), s, b)
             entry["_exp"] = None
             if blk.expand != 1:
                 cv, bne = list(blk.conv)[0][0], list(blk.conv)[0][1]
                 se, be = fold_bn(bne.weight, bne.bias, bne.running_mean, bne.running_var, bne.eps)
-                entry["_exp"] = (cv.weight.detach().float().flatten(1).to(dev), se.to(dev), be.to(dev))
+                entry["_exp"] = (host(cv.weight).flatten(1), se, be)
             self.blocks.append(entry)
         # A linear project conv (+BN) whose only consumer is the next block's expand conv (+BN+ReLU6) -- i.e. neither
         # block has a residual connection -- composes into ONE 1x1 conv: W = W_e diag(s_p) W_p, bias = s_e (W_e b_p) + b_e.
@@ -168,10 +204,10 @@ class MobileNetV2Runner:
                 we, se, be = e["_exp"]
                 wp, sp, bp = e["_proj"]
                 if mbconv_supported(1, 32, 32, we.shape[1], we.shape[0], wp.shape[0], e["stride"]):
-                    e["fused"] = pack_mbconv(we, se, be, e["_dw_raw"], e["dw_s"], e["dw_b"], wp, sp, bp, e["stride"],
-                                             device=dev)
+                    e["fused"] = pack_mbconv(we, se, be, e["_dw_raw"], e["_dw_sb"][0], e["_dw_sb"][1], wp, sp, bp,
+                                             e["stride"], device=dev)
         for e in self.blocks:
-            e.pop("_proj"), e.pop("_exp"), e.pop("_dw_raw")
+            e.pop("_proj"), e.pop("_exp"), e.pop("_dw_raw"), e.pop("_dw_sb")
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
@@ -181,6 +217,8 @@ class MobileNetV2Runner:
         the 126 MB L2 between the layer that writes it and the layer that reads it (the workspace arena hands the same
         hot buffers to every sub-batch).  Returns the full (N,h,w,1280) map."""
         n = frames.shape[0]
+        if chunk is not None and tsm is not None and chunk % tsm[0]:
+            chunk = max(tsm[0], chunk // tsm[0] * tsm[0])      # the temporal shift needs whole clips in a sub-batch
         if chunk is None or chunk >= n:
             return self.run(eng, frames, tsm=tsm)
         out = None

@@ -10,7 +10,7 @@ import math
 import torch
 from torch import nn
 
-from ..engine import AF_ACT_NONE, AF_ACT_RELU, fold_bn, get_engine, pack_conv
+from ..engine import AF_ACT_NONE, AF_ACT_RELU, fold_bn, get_engine, host, pack_conv
 
 
 class Memory:
@@ -46,10 +46,11 @@ class ActorCritic(nn.Module):
         raise NotImplementedError
 
     def runner(self):
+        from ..packcache import cached_runner
         from .mobilenet import _param_key
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = PolicyRunner(self, key)
+            self._runner = cached_runner(self, "PolicyRunner", lambda: PolicyRunner(self, key), key)
         return self._runner
 
     def act(self, state_ini, memory, restart_batch=False, training=True):
@@ -95,7 +96,7 @@ class PolicyRunner:
         lin = next(m for m in enc if isinstance(m, nn.Linear))
         bn1 = next((m for m in enc if isinstance(m, nn.BatchNorm1d)), None)
         # conv over [t*C + c] channels == a (fps x 1) convolution over the frame axis of (M, fps, h*w, C)
-        w4 = conv.weight.detach().float().reshape(self.enc_c, self.fps, self.map_channels).permute(0, 2, 1)[..., None]
+        w4 = host(conv.weight).reshape(self.enc_c, self.fps, self.map_channels).permute(0, 2, 1)[..., None]
         sc, bi = (None, None)
         if bn2 is not None:
             sc, bi = fold_bn(bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var, bn2.eps)
@@ -106,7 +107,7 @@ class PolicyRunner:
         perm = (j % self.enc_c) * hw + (j // self.enc_c)         # NHWC-flatten index -> NCHW-flatten index
         if bn1 is not None:
             s1, b1 = fold_bn(bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.eps)
-            lb = lin.bias.detach().float() * s1 + b1 if lin.bias is not None else b1
+            lb = host(lin.bias) * s1 + b1 if lin.bias is not None else b1
             self.enc_fc = pack_conv(lin.weight, s1, lb, act=AF_ACT_RELU, device=dev, cin_perm=perm)
         else:
             self.enc_fc = pack_conv(lin.weight, None, lin.bias, act=AF_ACT_RELU, device=dev, cin_perm=perm)

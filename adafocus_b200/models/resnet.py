@@ -66,10 +66,11 @@ class ResNet(nn.Module):
         return self.fc.weight.shape[-1]
 
     def runner(self):
+        from ..packcache import cached_runner
         from .mobilenet import _param_key
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = ResNetRunner(self, key)
+            self._runner = cached_runner(self, "ResNetRunner", lambda: ResNetRunner(self, key), key)
         return self._runner
 
     def get_featmap(self, x, pooled=True):
@@ -130,16 +131,22 @@ class ResNetRunner:
                     e["ds"] = None
                 self.blocks.append(e)
 
-    def run_pooled_chunked(self, eng, frames, out_f16, out_stride, chunk, yx=None, patch=None, yx_div=1):
+    def run_pooled_chunked(self, eng, frames, out, out_stride, chunk, yx=None, patch=None, yx_div=1, out_f32=False):
         """Trunk + global average pool over sub-batches of `chunk` patches (L2-resident intermediates, see
-        MobileNetV2Runner.run_chunked); pooled fp16 features go to out_f16 rows (row stride out_stride)."""
+        MobileNetV2Runner.run_chunked); pooled features go to `out` rows (fp16, or fp32 with out_f32; row stride
+        out_stride).  A chunk never splits a group of yx_div frames that share one crop origin."""
         n = frames.shape[0]
         chunk = n if chunk is None else max(1, min(chunk, n))
+        if chunk < n and chunk % yx_div:
+            chunk = max(yx_div, chunk // yx_div * yx_div)
         for s0 in range(0, n, chunk):
             s1 = min(n, s0 + chunk)
             sub_yx = None if yx is None else yx[s0 // yx_div:(s1 + yx_div - 1) // yx_div]
             fmap = self.run(eng, frames[s0:s1], yx=sub_yx, patch=patch, yx_div=yx_div)
-            eng.avgpool(fmap, out_f16=out_f16[s0:s1], out_f16_stride=out_stride)
+            if out_f32:
+                eng.avgpool(fmap, out_f32=out[s0:s1], out_f32_stride=out_stride)
+            else:
+                eng.avgpool(fmap, out_f16=out[s0:s1], out_f16_stride=out_stride)
             eng.release(fmap)
 
     def run(self, eng, frames, yx=None, patch=None, yx_div=1):

@@ -11,7 +11,7 @@ import math
 import torch
 from torch import nn
 
-from ..engine import get_engine, pack_conv
+from ..engine import get_engine, pack_conv_split
 from ..models.gfv_net import standard_action_table
 from ..models.mobilenet import _param_key
 from .basic_ops import ConsensusModule
@@ -77,7 +77,7 @@ class Focuser(nn.Module):
         if not self.random:
             assert policy_params is not None
             self.patch_sizes = torch.Tensor([self.patch_size, 0])
-            self.standard_actions_set = {a: standard_action_table(a) for a in (16, 25)}
+            self.standard_actions_set = {a: standard_action_table(a) for a in (16, 25, 36, 49, 64, 81, 100)}
             self.policy_feature_dim = policy_params["feature_dim"]
             self.policy_state_dim = policy_params["state_dim"]
             self.policy_action_dim = policy_params["action_dim"]
@@ -156,11 +156,14 @@ class _SthPlan:
             eng.release(fmap)
             m2 = eng.mark()
             lmap = fl.run(eng, self.focuser_images.view(b * tf, 3, s, s), yx=self.yx, patch=p, yx_div=tf // vd)
-            lvec = eng.empty((b * tf, lmap.shape[-1]), torch.float16)
-            eng.avgpool(lmap, out_f16=lvec, out_f16_stride=lmap.shape[-1])
+            lvec = eng.empty((b * tf, lmap.shape[-1]), torch.float32)
+            eng.avgpool(lmap, out_f32=lvec, out_f32_stride=lmap.shape[-1])
             eng.release(lmap)
+            lvec3 = eng.split3(lvec)                  # split-precision rows for the classifier (see GRUHeadRunner)
+            eng.release(lvec)
             llog = eng.empty((b * tf, cs), torch.float32)
-            eng.linear(lvec, head, out=llog, out_f32=True, out_stride=cs)
+            eng.linear(lvec3, head, out=llog, out_f32=True, out_stride=cs)
+            eng.release(lvec3)
             m3 = eng.mark()
             self.pred_padded = eng.consensus_avg(llog, b, tf, add=gcons)    # (B, cs)
             m4 = eng.mark()
@@ -219,8 +222,8 @@ class GFV(nn.Module):
     def _head_pack(self):
         key = _param_key(self.classifier)
         if self._head is None or self._head[0] != key:
-            self._head = (key, pack_conv(self.classifier.weight, None, self.classifier.bias,
-                                         device=self.classifier.weight.device))
+            self._head = (key, pack_conv_split(self.classifier.weight, self.classifier.bias,
+                                               device=self.classifier.weight.device))
         return self._head[1]
 
     def _weights_key(self):
@@ -234,11 +237,11 @@ class GFV(nn.Module):
         eng = get_engine(patches.device)
         fmap = self.focuser.net.runner().run(eng, patches.contiguous())
         n, h, w, c = fmap.shape
-        vec = torch.empty(n, c, dtype=torch.float16, device=patches.device)
-        eng.avgpool(fmap, out_f16=vec, out_f16_stride=c)
+        vec = torch.empty(n, c, dtype=torch.float32, device=patches.device)
+        eng.avgpool(fmap, out_f32=vec, out_f32_stride=c)
         cs = (self.num_class + 7) // 8 * 8
         out = torch.empty(n, cs, dtype=torch.float32, device=patches.device)
-        eng.linear(vec, self._head_pack(), out=out, out_f32=True, out_stride=cs)
+        eng.linear(eng.split3(vec), self._head_pack(), out=out, out_f32=True, out_stride=cs)
         return out[:, : self.num_class]
 
     # ------------------------------------------------------------------ reference API

@@ -5,8 +5,9 @@ import os
 import torch
 from torch import nn
 
-from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, mbconv_supported, pack_conv, pack_mbconv,
-                      pack_stem)
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_supported, pack_conv,
+                      pack_conv_split, pack_mbconv, pack_stem)
+from ..packcache import cached_runner
 from ..models.mobilenet import _FUSE_MIN_HW, _MBV2_SETTING, MobileNetV2Runner, _param_key
 
 
@@ -58,7 +59,7 @@ class MobileNetV2(nn.Module):
     def runner(self):
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = SthGlancerRunner(self, key)
+            self._runner = cached_runner(self, "SthGlancerRunner", lambda: SthGlancerRunner(self, key), key)
         return self._runner
 
     def get_featmap(self, x):
@@ -84,7 +85,7 @@ class SthGlancerRunner(MobileNetV2Runner):
         c0, b0 = f[0][0], f[0][1]
         s, b = fold_bn(b0.weight, b0.bias, b0.running_mean, b0.running_var, b0.eps)
         self.stem_direct = True
-        self.stem_w = c0.weight.detach().float().permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
+        self.stem_w = host(c0.weight).permute(2, 3, 1, 0).reshape(27, 32).contiguous().to(dev)
         self.stem_s, self.stem_b = s.contiguous().to(dev), b.contiguous().to(dev)
         self.stem = pack_stem(c0.weight, s, b, stride=2, pad=1, act=AF_ACT_RELU6, device=dev)
         self.blocks = []
@@ -104,8 +105,9 @@ class SthGlancerRunner(MobileNetV2Runner):
                 seq = seq[3:]
             dw, bn = seq[0], seq[1]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-            e["dw_w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
+            e["dw_w"] = host(dw.weight).reshape(dw.weight.shape[0], 9).t().contiguous().to(dev)
             e["dw_s"], e["dw_b"] = s.contiguous().to(dev), b.contiguous().to(dev)
+            dw_s, dw_b = s, b
             pw, bn = seq[3], seq[4]
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             e["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=e["res"])
@@ -113,13 +115,13 @@ class SthGlancerRunner(MobileNetV2Runner):
             if (fuse and blk.expand != 1 and
                     mbconv_supported(1, 32, 32, cv.weight.shape[1], cv.weight.shape[0], pw.weight.shape[0], blk.stride)):
                 # expand -> depthwise -> project as one launch (adafocus_b200/csrc/mbconv_fused.cu)
-                e["fused"] = pack_mbconv(cv.weight, s1, b1, dw.weight, e["dw_s"], e["dw_b"], pw.weight, s, b, blk.stride,
+                e["fused"] = pack_mbconv(cv.weight, s1, b1, dw.weight, dw_s, dw_b, pw.weight, s, b, blk.stride,
                                          device=dev)
             self.blocks.append(e)
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
-        self.fc = pack_conv(net.classifier.weight, None, net.classifier.bias, device=dev)
+        self.fc = pack_conv_split(net.classifier.weight, net.classifier.bias, device=dev)
         self.num_classes = net.classifier.weight.shape[0]
         self.logit_stride = (self.num_classes + 7) // 8 * 8
 
@@ -158,14 +160,14 @@ class SthGlancerRunner(MobileNetV2Runner):
     def logits(self, eng, fmap, vec16=None, padded=False):
         """classifier(mean over H,W) -> fp32 (N, n_class) [or the row-padded (N, logit_stride) buffer]."""
         n, h, w, c = fmap.shape
-        own = vec16 is None
-        if own:
-            vec16 = eng.empty((n, c), torch.float16)
-            eng.avgpool(fmap, out_f16=vec16, out_f16_stride=c)
+        assert vec16 is None, "the glancer head consumes fp32 pooled features (split-precision GEMM)"
+        vec = eng.empty((n, c), torch.float32)
+        eng.avgpool(fmap, out_f32=vec, out_f32_stride=c)
+        vec3 = eng.split3(vec)
+        eng.release(vec)
         out = eng.empty((n, self.logit_stride), torch.float32)
-        eng.linear(vec16, self.fc, out=out, out_f32=True, out_stride=self.logit_stride)
-        if own:
-            eng.release(vec16)
+        eng.linear(vec3, self.fc, out=out, out_f32=True, out_stride=self.logit_stride)
+        eng.release(vec3)
         if padded or self.logit_stride == self.num_classes:
             return out
         return out[:, : self.num_classes].contiguous()

@@ -10,6 +10,7 @@ from torch import nn
 
 from ..engine import get_engine
 from ..models.mobilenet import _param_key
+from ..packcache import cached_runner
 from ..models.ppo import Memory, PolicyRunner  # noqa: F401  (Memory re-exported like the reference module)
 
 
@@ -40,7 +41,7 @@ class ActorCritic(nn.Module):
     def runner(self):
         key = _param_key(self)
         if self._runner is None or self._runner.key != key:
-            self._runner = PolicyRunner(self, key)
+            self._runner = cached_runner(self, "PolicyRunner", lambda: PolicyRunner(self, key), key)
         return self._runner
 
     def act(self, state_ini, memory, restart_batch=False, training=False):

@@ -9,6 +9,7 @@ from torch import nn
 
 from ..engine import get_engine
 from ..models.mobilenet import _param_key
+from ..packcache import cached_runner
 from ..models.resnet import ResNet, ResNetRunner
 from .temporal_shift import make_temporal_shift
 
@@ -43,7 +44,7 @@ class TSN(nn.Module):
     def runner(self):
         key = (id(self.base_model), _param_key(self.base_model))
         if self._runner is None or self._runner.key != key:
-            self._runner = ResNetRunner(self.base_model, key)
+            self._runner = cached_runner(self.base_model, "ResNetRunner", lambda: ResNetRunner(self.base_model, key), key)
         return self._runner
 
     def forward(self, input, no_reshape=False):

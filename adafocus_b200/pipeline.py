@@ -39,19 +39,37 @@ class StreamingEvaluator:
             self.u8 = [torch.empty(batch, s, s, 3 * t, dtype=torch.uint8, device=self.device) for _ in range(slots)]
             self.mean, self.std = list(model.input_mean), list(model.input_std)
 
+    def _refresh_plans(self):
+        """Plans are re-fetched on every run(): after a checkpoint reload the model hands back re-recorded plans over
+        freshly packed weights (an O(1) key check per plan otherwise)."""
+        m = self.model
+        self.plans = [m.fused_plan(self.batch, self.t, m.input_size, m.input_size, m.glance_size, self.device, True,
+                                   slot=i) for i in range(len(self.plans))]
+
     def run(self, host_batches, collect=True):
-        """host_batches: iterable of pinned (B,3T,H,W) fp32 CPU tensors -- or (B,H,W,3T) uint8 with
-        input_format="u8_hwc".  Returns the list of (B,C) host logits (last time step, the reference's `pred`)."""
+        """host_batches: sequence of pinned (B,3T,H,W) fp32 CPU tensors -- or (B,H,W,3T) uint8 with
+        input_format="u8_hwc"; the last one may hold fewer than B clips.  Returns the list of (n_i, C) host logits
+        (last time step, the reference's `pred`).  collect=True keeps every batch's result (rows of ONE pinned
+        (num_batches, B, C) buffer allocated up front); collect=False recycles one pinned buffer per slot, for timing."""
+        self._refresh_plans()
+        host_batches = list(host_batches)
         results = []
         n = len(self.plans)
+        if collect:
+            ring = torch.empty(max(1, len(host_batches)), self.batch, self.num_classes, dtype=torch.float32).pin_memory()
         for s in range(n):
             self.consumed[s].record(self.compute_stream)
         for i, hb in enumerate(host_batches):
             s = i % n
             plan = self.plans[s]
+            nb = hb.shape[0]
+            if nb > self.batch or (nb < self.batch and i != len(host_batches) - 1):
+                raise ValueError(f"batch {i} has {nb} clips: every batch but the last must hold exactly {self.batch}")
+            dst = plan.input if self.u8 is None else self.u8[s]
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(self.consumed[s])        # slot's previous compute has read its input
-                (plan.input if self.u8 is None else self.u8[s]).copy_(hb, non_blocking=True)
+                # ragged final batch: clips are independent, rows >= nb keep the slot's previous (valid) clips
+                dst[:nb].copy_(hb, non_blocking=True)
                 self.copied[s].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self.copied[s])
@@ -60,11 +78,8 @@ class StreamingEvaluator:
                 plan.run()
                 self.consumed[s].record(self.compute_stream)
                 last = plan.logits.view(self.batch, self.t, -1)[:, -1, : self.num_classes]
-                if collect:
-                    out = torch.empty(self.batch, self.num_classes, dtype=torch.float32).pin_memory()
-                else:
-                    out = self.out_host[s]
+                out = ring[i] if collect else self.out_host[s]
                 out.copy_(last, non_blocking=True)
-                results.append(out)
+                results.append(out[:nb])
         self.compute_stream.synchronize()
         return results

@@ -193,7 +193,15 @@ int af_nchw_f32_to_nhwc_f16(af_ctx* ctx, const float* in, void* out, int N, int 
  * xg (B,3H) row stride xg_stride = W_ih x + b_ih; hg (B,3H) = W_hh h + b_hh (both produced by af_conv2d_nhwc_f16). */
 int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* hg, const float* h_prev, float* h_new,
                  void* h_new_f16, void* hseq_f16, int64_t hseq_stride, float* hseq_f32, int64_t hseq_f32_stride,
-                 int B, int Hd, void* stream);
+                 int B, int Hd, int split, void* stream);
+
+/* fp32 rows (row stride in_stride) -> split-precision fp16 operand rows [hi | lo | hi], 3*cols wide, x = hi + lo.
+ * Multiplied with weights packed [W_hi | W_hi | W_lo] (engine.pack_conv_split) the tensor core accumulates
+ * x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32: ~22-bit operands for the classifier head (ACT/models/gfv_net.py:427-435),
+ * which is < 1 % of the FLOPs but sets the logit error.  `split` != 0 in af_gru_gates / af_gru_sequence makes their
+ * fp16 outputs (h_new_f16 row stride 3*Hd, hseq_f16) use the same three-part rows and, for af_gru_sequence, reads
+ * w_hh_f16 as (3H, 3H) [W_hi | W_hi | W_lo] rows. */
+int af_split3_f16(af_ctx* ctx, const float* in, int64_t in_stride, void* out, int rows, int cols, void* stream);
 
 /* A whole GRU sequence (all T steps, h0 = zeros when NULL) in ONE persistent cooperative launch, for small batches:
  * the policy rollout of ACT/models/ppo.py:67-96 / ACT/models/gfv_net.py:110 and the classifier GRU of
@@ -203,7 +211,7 @@ int af_gru_gates(af_ctx* ctx, const float* xg, int64_t xg_stride, const float* h
  * Constraints: H % 256 == 0, H <= 1024 and H / 8 <= number of SMs. */
 int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const float* b_hh, const float* h0, float* hbuf,
                     void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter, int B, int T, int Hd,
-                    void* stream);
+                    int split, void* stream);
 
 /* softmax -> argmax -> standard action table -> patch origin; ACT/models/ppo.py:84,94,
  * ACT/models/gfv_net.py:272-307,345-347, ACT/models/utils.py:42.  grid_n = sqrt(action_dim). */

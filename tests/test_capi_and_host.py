@@ -228,3 +228,75 @@ def test_checkpoint_ingest_formats(tmp_path):
     ck_s = synth.synth_checkpoint_sth(s, seed=5)
     checkpoint.load_sth_checkpoint(s, ck_s)
     assert torch.equal(s.classifier.weight, ck_s["fc"]["weight"])
+
+
+def test_packing_is_host_arithmetic_and_split_layout():
+    """engine.pack_* work on host tensors (no device kernels: a CUDA-less machine can pack) and pack_conv_split lays
+    out [W_hi | W_hi | W_lo] with W_hi + W_lo == W to ~2^-22."""
+    from adafocus_b200.engine import fold_bn, pack_conv, pack_conv_split
+    torch.manual_seed(1)
+    w = torch.randn(40, 128)
+    pc = pack_conv_split(w, torch.randn(40), device="cpu")
+    assert pc.w.shape == (48, 384) and pc.cin == 384 and pc.w.dtype == torch.float16
+    hi, hi2, lo = pc.w[:40, :128].float(), pc.w[:40, 128:256].float(), pc.w[:40, 256:].float()
+    assert torch.equal(hi, hi2) and torch.equal(hi, w.half().float())
+    assert float((hi + lo - w).abs().max()) <= 2.0 ** -21 * float(w.abs().max())
+    bn = torch.nn.BatchNorm2d(8)
+    bn.running_var.uniform_(0.5, 2)
+    s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    assert s.device.type == "cpu" and b.device.type == "cpu"
+    pc = pack_conv(torch.randn(8, 3, 3, 3), s, b, device="cpu")
+    assert pc.w.shape == (16, 9 * 64)
+
+
+def test_param_key_is_constant_time_and_tracks_reloads():
+    """The packed-weight cache key is O(1) (epoch + three probe tensors) and is bumped by load_state_dict on the module,
+    an ancestor or a descendant, by in-place updates of the probe tensors, and by invalidate_packed()."""
+    from adafocus_b200 import synth
+    from adafocus_b200.models.gfv_net import GFV
+    from adafocus_b200.models.mobilenet import _param_key, invalidate_packed
+    m = GFV(synth.act_args(num_segments=2, num_classes=10))
+    net = m.focuser.net
+    k0 = _param_key(net)
+    assert _param_key(net) == k0 and len(k0) <= 8
+    net.load_state_dict(net.state_dict())
+    k1 = _param_key(net)
+    assert k1 != k0
+    m.focuser.load_state_dict(m.focuser.state_dict(), strict=False)        # ancestor
+    k2 = _param_key(net)
+    assert k2 != k1
+    net.layer3[2].conv2.load_state_dict(net.layer3[2].conv2.state_dict())  # descendant
+    k3 = _param_key(net)
+    assert k3 != k2
+    invalidate_packed(net)
+    assert _param_key(net) != k3
+    assert _param_key(m.glancer.net) == _param_key(m.glancer.net)
+
+
+def test_pack_cache_content_hash(tmp_path):
+    """packcache keys on the CONTENT of the state_dict: equal weights in another module instance hit, changed weights
+    miss; the stored object is the runner itself."""
+    from adafocus_b200 import packcache
+    lin = torch.nn.Linear(64, 8)
+    lin2 = torch.nn.Linear(64, 8)
+    lin2.load_state_dict(lin.state_dict())
+    assert packcache.content_hash(lin) == packcache.content_hash(lin2)
+    with torch.no_grad():
+        lin2.weight[0, 0] += 1
+    assert packcache.content_hash(lin) != packcache.content_hash(lin2)
+
+    packcache.set_cache_dir(str(tmp_path))
+    R = lambda: _PickleRunner(lin.weight.detach().clone())      # noqa: E731
+    try:
+        before = dict(packcache.stats)
+        r1 = packcache.cached_runner(lin, "R", R, "k1")
+        r2 = packcache.cached_runner(lin, "R", lambda: (_ for _ in ()).throw(AssertionError("must hit")), "k2")
+        assert r2.key == "k2" and torch.equal(r1.t, r2.t)
+        assert packcache.stats["hits"] == before["hits"] + 1 and packcache.stats["stores"] == before["stores"] + 1
+    finally:
+        packcache.set_cache_dir(None)
+
+
+class _PickleRunner:
+    def __init__(self, t):
+        self.key, self.t = None, t

@@ -422,6 +422,70 @@ def test_gru_sequence_kernel_vs_torch(eng, b, t, hd):
     assert torch.allclose(h_out.cpu(), hn0[0], rtol=2e-4, atol=2e-4)
 
 
+def test_split_precision_linear(eng):
+    """af_split3_f16 + a GEMM against [W_hi | W_hi | W_lo] (engine.pack_conv_split): ~22-bit operands on the tensor core.
+    Reference: fp64 matmul of the UNROUNDED fp32 operands; a plain fp16 GEMM of the same operands is ~100x further away."""
+    from adafocus_b200.engine import pack_conv, pack_conv_split
+    torch.manual_seed(3)
+    m, k, n = 96, 3328, 200
+    x = torch.randn(m, k) * 3.0
+    x[0, :7] = torch.tensor([0.0, 1e-6, -1e-6, 6.1e-5, 65000.0, -7.3e-4, 1.0])       # subnormal lo parts, large values
+    w = torch.randn(n, k) / math.sqrt(k)
+    bias = torch.randn(n) * 0.1
+    ref = (x.double() @ w.double().t() + bias.double()).float()
+    xd = x.to(DEV)
+    x3 = eng.split3(xd)
+    hi = xd.half()
+    assert torch.equal(x3[:, :k], hi) and torch.equal(x3[:, 2 * k:], hi)
+    assert torch.equal(x3[:, k:2 * k], (xd - hi.float()).half())
+    pc = pack_conv_split(w, bias, device=DEV)
+    out = eng.linear(x3, pc, out_f32=True)
+    plain = eng.linear(hi, pack_conv(w, None, bias, device=DEV), out_f32=True)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err_split = float((out.cpu() - ref).abs().max()) / scale
+    err_plain = float((plain.cpu() - ref).abs().max()) / scale
+    assert err_split <= 2e-6, err_split
+    assert err_plain >= 20 * err_split, (err_plain, err_split)
+    # strided input rows (a column block of a wider feature matrix)
+    wide = torch.randn(m, k + 64, device=DEV)
+    assert torch.equal(eng.split3(wide[:, 64:])[:, :k], wide[:, 64:].half())
+
+
+@pytest.mark.parametrize("b,t,hd", [(2, 5, 1024), (8, 4, 512)])
+def test_gru_sequence_and_gates_split_precision(eng, b, t, hd):
+    """The split-precision forms of the persistent GRU kernel and of the per-step GEMM + gate kernel against a CPU
+    fp32 torch.nn.GRU with UNROUNDED weights: both stay within 2e-5 (the plain fp16 forms are ~1e-3)."""
+    from adafocus_b200.engine import pack_conv_split
+    torch.manual_seed(b + t)
+    gru = torch.nn.GRU(64, hd, batch_first=True)
+    with torch.no_grad():
+        x = torch.randn(b, t, 64)
+        ref, hn = gru(x)
+        xg = (x.reshape(b * t, 64) @ gru.weight_ih_l0.t() + gru.bias_ih_l0).contiguous().to(DEV)
+    pc = pack_conv_split(gru.weight_hh_l0, gru.bias_hh_l0, device=DEV, block_n=32)
+    hseq3 = torch.zeros(b * t, 3 * hd, device=DEV, dtype=torch.float16)
+    h_out = torch.zeros(b, hd, device=DEV)
+    eng.gru_sequence(xg, pc, b, t, hseq3, h_out=h_out)
+    torch.cuda.synchronize()
+    assert float((h_out.cpu() - hn[0]).abs().max()) <= 2e-5
+    seq = (hseq3[:, :hd].float() + hseq3[:, hd:2 * hd].float()).cpu().view(b, t, hd)
+    assert float((seq - ref).abs().max()) <= 2e-5
+    assert torch.equal(hseq3[:, :hd], hseq3[:, 2 * hd:])
+    # per-step path: h3 -> GEMM -> gates(split=True)
+    h = torch.zeros(b, hd, device=DEV)
+    h3 = eng.split3(h)
+    hg = torch.empty(b, 3 * hd, device=DEV)
+    hs3 = torch.zeros(b * t, 3 * hd, device=DEV, dtype=torch.float16).view(b, t, 3 * hd)
+    xg3 = xg.view(b, t, 3 * hd)
+    for step in range(t):
+        eng.linear(h3, pc, out=hg, out_f32=True, out_stride=3 * hd)
+        eng.gru_gates(xg3[:, step], t * 3 * hd, hg, h, h, h3, hs3[:, step], t * 3 * hd, split=True)
+    torch.cuda.synchronize()
+    assert float((h.cpu() - hn[0]).abs().max()) <= 2e-5
+    assert torch.equal(h3[:, :hd], h.half()) and torch.equal(h3[:, hd:2 * hd], (h - h.half().float()).half())
+
+
 @pytest.mark.parametrize("a,p", [(49, 128), (25, 96), (36, 160), (64, 192), (100, 144)])
 def test_policy_head_argmax_and_coords(eng, a, p):
     from oracle import adafocus_oracle as orc

@@ -273,3 +273,54 @@ def test_other_configurations_vs_oracle(over, batch):
     scale = max(1.0, float(ref["logits"].abs().max()))
     assert float((logits.cpu() - ref["logits"]).abs().max()) <= 5e-3 * scale
     assert torch.equal(last.argmax(1).cpu(), ref["last_out"].argmax(1))
+
+
+def test_packed_weight_cache_round_trip(tmp_path):
+    """f-3: with a cache directory set the packed runners are persisted under a content hash; a fresh model instance
+    loading the same checkpoint maps the blobs (no repacking) and produces bit-identical logits."""
+    from adafocus_b200 import packcache
+    over = dict(num_segments=2, patch_size=96, action_dim=25, num_classes=10)
+    packcache.set_cache_dir(str(tmp_path))
+    try:
+        s0 = dict(packcache.stats)
+        args, model, ck, x = _model(over, 1)
+        xd = x.to(DEV)
+        a = model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)[0].clone()
+        assert packcache.stats["stores"] - s0["stores"] == 4 and packcache.stats["hits"] == s0["hits"]
+        args, model2, _, _ = _model(over, 1)
+        b = model2(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)[0]
+        assert packcache.stats["hits"] - s0["hits"] == 4 and packcache.stats["stores"] - s0["stores"] == 4
+        assert torch.equal(a, b)
+    finally:
+        packcache.set_cache_dir(None)
+
+
+def test_streaming_evaluator_ragged_last_batch_and_reload(c3):
+    """A last batch with fewer clips than the plan's batch is evaluated on its own rows; after a checkpoint reload
+    the evaluator picks up re-recorded plans."""
+    from adafocus_b200 import synth
+    from adafocus_b200.pipeline import StreamingEvaluator
+    model, x = c3["model"], c3["x"]
+    ev = StreamingEvaluator(model, 2, DEV)
+    full = ev.run([x.pin_memory()])[0].clone()
+    assert torch.allclose(full, c3["last"].cpu(), atol=0, rtol=0)
+    out = ev.run([x.pin_memory(), x[:1].pin_memory()])
+    assert out[1].shape == (1, c3["args"].num_classes) and torch.equal(out[1][0], full[0])
+    with pytest.raises(ValueError):
+        ev.run([x[:1].pin_memory(), x.pin_memory()])
+    ck2 = synth.synth_checkpoint_act(model, seed=31)
+    synth.load_checkpoint_act(model, ck2)
+    changed = ev.run([x.pin_memory()])[0].clone()
+    assert not torch.equal(changed, full)
+    synth.load_checkpoint_act(model, c3["ck"])
+    assert torch.equal(ev.run([x.pin_memory()])[0], full)
+
+
+def test_train_mode_is_rejected(c3):
+    model, xd = c3["model"], c3["xd"]
+    torch.nn.Module.train(model, True)
+    try:
+        with pytest.raises(NotImplementedError):
+            model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)
+    finally:
+        model.eval()

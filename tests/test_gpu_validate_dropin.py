@@ -1,0 +1,141 @@
+"""The drop-in claim, tested: the reference's OWN validate() loops (ACT/main_dist.py:307-422 stage 3 and stage 2,
+STH/evaluate.py:165-226), imported unmodified from baseline/_ref with a hydra stand-in (oracle/stubs), run over
+adafocus_b200/dropin/{act,sth} -- `from models.gfv_net import GFV` resolves to the B200 implementation -- on a tiny
+synthetic loader, and agree with the same loops run over the reference's own `models` package on the same GPU and
+with the committed CPU goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN_ACT = os.path.join(ROOT, "adafocus_b200", "dropin", "act")
+DROPIN_STH = os.path.join(ROOT, "adafocus_b200", "dropin", "sth")
+TOL = 1e-3
+
+
+def _need_reference(tree):
+    from oracle import reference_loader as rl
+    if not rl.available(tree):
+        pytest.skip("reference sources not on this machine (tools/vendor_reference.py makes baseline/_ref)")
+    return rl
+
+
+def _run_act_validate(dropin, args, clips, targets, batches):
+    """validate() of the reference's main_dist.py over `models` = dropin or the reference's own package."""
+    from adafocus_b200 import synth
+    from oracle import reference_loader as rl
+    mod = rl.import_entry("ACT", dropin=dropin)
+    import models.gfv_net as g
+    model = g.GFV(args)
+    ck = synth.synth_checkpoint_act(model, synth.SEED)
+    synth.load_checkpoint_act(model, ck)              # = ACT/main_dist.py:100-110
+    model = model.cuda(0)
+    seen = {"pred": [], "acc": []}
+    real_acc = mod.accuracy
+
+    def spy(pred, target, topk=(1,)):
+        out = real_acc(pred, target, topk=topk)
+        seen["pred"].append(pred.detach().float().cpu().clone())
+        seen["acc"].append([float(o) for o in out])
+        return out
+    mod.accuracy = spy
+    loader = [(clips[i], targets[i]) for i in range(batches)]
+    crit = torch.nn.CrossEntropyLoss().cuda(0)
+    np.random.seed(7)
+    metric, logs = mod.validate(loader, model, crit, args)
+    mod.accuracy = real_acc
+    rl.unload()
+    return float(metric), logs, seen
+
+
+def _act_args(**over):
+    from adafocus_b200 import synth
+    a = synth.act_args(**over)
+    a.evaluate, a.seed, a.gpu, a.dataset = True, synth.SEED, 0, "actnet"
+    return a
+
+
+def test_act_stage3_validate_runs_unmodified_over_the_dropin(golden_dir):
+    _need_reference("ACT")
+    from adafocus_b200 import synth
+    over = dict(num_segments=4, patch_size=96, action_dim=36, num_classes=51, train_stage=3)
+    args = _act_args(**over)
+    x = synth.synth_clips(3, 4, 224)
+    tgt = torch.tensor([[3], [7], [11]])
+    clips, targets = [x, x[:2].contiguous()], [tgt, tgt[:2]]
+    m_ours, logs_ours, ours = _run_act_validate(DROPIN_ACT, args, clips, targets, 2)
+    m_ref, logs_ref, ref = _run_act_validate(None, args, clips, targets, 2)
+    gold = np.load(os.path.join(golden_dir, "act_t4_p96_b3.npz"))
+    scale = max(1.0, float(np.abs(gold["last_out"]).max()))
+    assert np.abs(ours["pred"][0].numpy() - gold["last_out"]).max() <= TOL * scale
+    for a, b in zip(ours["pred"], ref["pred"]):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2.5 * TOL * scale      # reference on GPU runs TF32 convs (its own band)
+        assert torch.equal(a.argmax(1), b.argmax(1))
+    assert ours["acc"] == ref["acc"]
+    assert (np.isnan(m_ours) and np.isnan(m_ref)) or abs(m_ours - m_ref) < 1e-6
+    assert len(logs_ours) == len(logs_ref)
+
+
+def test_act_stage2_validate_runs_unmodified_over_the_dropin(golden_dir):
+    """train_stage=2 branch (ACT/main_dist.py:343-366): glance + one_step_act per step with the numpy-RNG random
+    baseline patches."""
+    _need_reference("ACT")
+    from adafocus_b200 import synth
+    over = dict(num_segments=4, patch_size=96, action_dim=36, num_classes=51, train_stage=2)
+    args = _act_args(**over)
+    x = synth.synth_clips(3, 4, 224)
+    tgt = torch.tensor([[3], [7], [11]])
+    m_ours, _, ours = _run_act_validate(DROPIN_ACT, args, [x], [tgt], 1)
+    m_ref, _, ref = _run_act_validate(None, args, [x], [tgt], 1)
+    scale = max(1.0, float(ref["pred"][0].abs().max()))
+    assert float((ours["pred"][0] - ref["pred"][0]).abs().max()) <= 2.5 * TOL * scale
+    assert ours["acc"] == ref["acc"]
+
+
+def _run_sth_validate(dropin, args, loader):
+    from adafocus_b200 import synth
+    from oracle import reference_loader as rl
+    mod = rl.import_entry("STH", dropin=dropin)
+    import models.gfv_net as g
+    model = g.GFV(args).cuda(0)
+    synth.strip_fc_sth(model)                                        # STH/evaluate.py:83
+    ck = synth.synth_checkpoint_sth(model, synth.SEED)
+    synth.load_checkpoint_sth(model, ck)                             # :141-146
+    model.focuser.policy.policy.cuda(0)
+    model.focuser.policy.policy_old.cuda(0)
+    seen = {"pred": [], "acc": []}
+    real_acc = mod.accuracy
+
+    def spy(pred, target, topk=(1,)):
+        out = real_acc(pred, target, topk=topk)
+        seen["pred"].append(pred.detach().float().cpu().clone())
+        seen["acc"].append([float(o) for o in out])
+        return out
+    mod.accuracy = spy
+    torch.manual_seed(123)                                           # the random-patch baseline draws torch.rand on CPU
+    top1, logs = mod.validate(loader, model, torch.nn.CrossEntropyLoss().cuda(0), args)
+    mod.accuracy = real_acc
+    rl.unload()
+    return float(top1), logs, seen
+
+
+def test_sth_validate_runs_unmodified_over_the_dropin(golden_dir):
+    _need_reference("STH")
+    from adafocus_b200 import synth
+    args = synth.sth_args(num_classes=174, batch_size=2, gpu=0)
+    gi = synth.synth_clips(2, args.num_segments_glancer, 224, synth.SEED + 1)
+    fi = synth.synth_clips(2, args.num_segments_focuser, 224, synth.SEED + 2)
+    tgt = torch.tensor([5, 9])
+    loader = [(gi, fi, tgt)]
+    t_ours, logs_ours, ours = _run_sth_validate(DROPIN_STH, args, loader)
+    t_ref, logs_ref, ref = _run_sth_validate(None, args, loader)
+    gold = np.load(os.path.join(golden_dir, "sth_r50_p144_b2.npz"))
+    scale = max(1.0, float(ref["pred"][0].abs().max()))
+    assert float((ours["pred"][0] - ref["pred"][0]).abs().max()) <= 2.5 * TOL * scale
+    assert np.abs(ours["pred"][0].numpy() - gold["pred_stage2"][-1]).max() <= 2 * TOL * scale
+    assert ours["acc"] == ref["acc"] and t_ours == t_ref
+    assert len(logs_ours) == len(logs_ref)
