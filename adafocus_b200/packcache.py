@@ -46,7 +46,7 @@ def content_hash(module, extra=""):
     for name, t in module.state_dict().items():
         c = t.detach().to("cpu").contiguous()
         h.update(f"{name}|{tuple(c.shape)}|{c.dtype}".encode())
-        h.update(c.view(torch.uint8).numpy().tobytes() if c.numel() else b"")
+        h.update(c.reshape(-1).view(torch.uint8).numpy().tobytes() if c.numel() else b"")
     return h.hexdigest()
 
 
