@@ -28,6 +28,7 @@ class ConvDesc(ctypes.Structure):
         ("block_n", c_int32), ("act", c_int32), ("out_f32", c_int32),
         ("in_stride", c_int64), ("out_stride", c_int64), ("res_stride", c_int64),
         ("in_row_stride", c_int64), ("in_img_stride", c_int64),
+        ("tsm_t", c_int32), ("tsm_fold", c_int32),
     ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "af_stem_conv3x3s2_c32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),
+    "af_conv_tsm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_fused_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32)]),
     "af_mbconv_fused": (c_int, [c_void_p, POINTER(MbconvDesc), c_void_p]),

@@ -127,11 +127,39 @@ void choose_tile(int N, int Ho, int Wo, int* TW, int* TH, int* TN) {
   }
 }
 
+// Same, with the image-axis extent of the box restricted to divisors of T (temporal-shift mode: a tile must not
+// straddle two clips).
+void choose_tile_tsm(int N, int Ho, int Wo, int T, int* TW, int* TH, int* TN) {
+  long long best_cost = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tn = 128 / (tw * th);
+      if (T % tn != 0) continue;
+      const long long cost = static_cast<long long>(ceil_div(Wo, tw)) * ceil_div(Ho, th) * ceil_div(N, tn);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        *TW = tw;
+        *TH = th;
+        *TN = tn;
+      }
+    }
+  }
+}
+
+bool tsm_fold_ok(int n, int h, int w, int cin, long long in_stride, int fold, int t) {
+  return t >= 1 && n >= t && n % t == 0 && h >= 1 && w >= 1 && cin % af::kConvBlockK == 0 && fold >= 16 &&
+         fold % 16 == 0 && 2 * fold <= cin && in_stride >= cin && in_stride % 8 == 0;
+}
+
 }  // namespace
 
 extern "C" {
 
 int af_version(void) { return AF_VERSION; }
+
+int af_conv_tsm_supported(int n, int h, int w, int cin, int in_stride, int fold, int t) {
+  return tsm_fold_ok(n, h, w, cin, in_stride, fold, t) ? 1 : 0;
+}
 const char* af_last_error(void) { return g_last_error.c_str(); }
 
 int af_ctx_create(af_ctx** out, int device) {
@@ -360,7 +388,18 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   p.Wo = (d->w_ + 2 * d->pad - d->kw) / d->stride + 1;
   if (p.Ho < 1 || p.Wo < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: empty output");
   p.Cout = d->cout;
-  choose_tile(p.N, p.Ho, p.Wo, &p.TW, &p.TH, &p.TN);
+  const bool tsm = d->tsm_t > 0;
+  if (tsm) {
+    if (d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad != 0 || windowed ||
+        !tsm_fold_ok(d->n, d->h, d->w_, d->cin, d->in_stride, d->tsm_fold, d->tsm_t))
+      return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: temporal shift needs a dense 1x1 stride-1 conv, cin % 64 == 0, "
+                                  "fold % 16 == 0 and n % tsm_t == 0 (see af_conv_tsm_supported)");
+    choose_tile_tsm(p.N, p.Ho, p.Wo, d->tsm_t, &p.TW, &p.TH, &p.TN);
+    p.tsm_T = d->tsm_t;
+    p.tsm_f16 = d->tsm_fold / 16;
+  } else {
+    choose_tile(p.N, p.Ho, p.Wo, &p.TW, &p.TH, &p.TN);
+  }
   {
     // vertical-halo mode (conv_gemm.cuh): stride-1 filters taller than one row whose weights stay resident; the tile
     // is one image's TW x TH pixels, chosen to minimise the rows loaded per tile (TH + KH - 1 per TH produced)
@@ -422,6 +461,16 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
       strides[2] = static_cast<cuuint64_t>(d->in_img_stride) * 2;
     }
     if (!encode_map(ctx, &maps.a[0], in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+    if (tsm) {
+      // {C, W, H, T, clips}: the frame axis is its own dimension so that t-1 / t+1 outside the clip are out of bounds
+      const cuuint64_t dims5[5] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
+                                   static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->tsm_t),
+                                   static_cast<cuuint64_t>(d->n / d->tsm_t)};
+      const cuuint64_t strides5[4] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h, pix_b * d->w_ * d->h * d->tsm_t};
+      const cuuint32_t box5[5] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.TW),
+                                  static_cast<cuuint32_t>(p.TH), static_cast<cuuint32_t>(p.TN), 1};
+      if (!encode_map(ctx, &maps.a5, in, 5, dims5, strides5, box5, &err)) return fail(AF_ERR_CUDA, err);
+    }
     if (p.vhalo) {
       const cuuint32_t hbox[4] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.TW),
                                   static_cast<cuuint32_t>(p.TH + p.KH - 1), 1};

@@ -37,6 +37,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// source frame offset of 16-channel step j under the temporal shift: +1 for the first fold, -1 for the second, else 0
+__device__ __forceinline__ int tsm_source(int j, int f16) { return j < f16 ? 1 : (j < 2 * f16 ? -1 : 0); }
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActRelu) return fmaxf(x, 0.f);
   if (act == kActRelu6) return fminf(fmaxf(x, 0.f), 6.f);
@@ -180,6 +183,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     if (p.tma_store) tma_prefetch_desc(&maps.out);
     if (p.res_mma) tma_prefetch_desc(&maps.res);
     if (VHALO) tma_prefetch_desc(&maps.ah);
+    if (p.tsm_T > 0) tma_prefetch_desc(&maps.a5);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -248,7 +252,31 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        for (int kh = 0; kh < (VHALO ? 0 : p.KH); ++kh) {
+        if (!VHALO && p.tsm_T > 0) {
+          // temporal shift folded into the loads: per 64-channel k-block one box per run of 16-channel steps that
+          // share a source frame (t+1 / t-1 / t); the frame axis of maps.a5 zero-fills outside the clip
+          const int tpc = p.tsm_T / p.TN;
+          const int tb = cur.tn / tpc, t0 = (cur.tn - tb * tpc) * p.TN;
+          for (int cb = 0; cb < p.cblks; ++cb) {
+            int k = 0;
+            while (k < 4) {
+              const int src = tsm_source(4 * cb + k, p.tsm_f16);
+              int ke = k + 1;
+              while (ke < 4 && tsm_source(4 * cb + ke, p.tsm_f16) == src) ++ke;
+              mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
+              uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+              tma_load_5d_elect(sa, &maps.a5, &ctrl->full[stage], cb * kConvBlockK, ow0, oh0, t0 + src, tb);
+              if (!p.wres) tma_load_2d_elect(sa + kStageABytes, &maps.b, &ctrl->full[stage], cb * kConvBlockK, nb * p.BN);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              k = ke;
+            }
+          }
+        }
+        for (int kh = 0; kh < ((VHALO || p.tsm_T > 0) ? 0 : p.KH); ++kh) {
           for (int kw = 0; kw < p.KW; ++kw) {
             int map_idx = 0, ch, cw;
             if (p.stride == 1) {
@@ -338,7 +366,30 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        for (int kb = 0; kb < (VHALO ? 0 : num_kb); ++kb) {
+        if (!VHALO && p.tsm_T > 0) {
+          for (int cb = 0; cb < p.cblks; ++cb) {
+            int k = 0;
+            while (k < 4) {
+              const int src = tsm_source(4 * cb + k, p.tsm_f16);
+              int ke = k + 1;
+              while (ke < 4 && tsm_source(4 * cb + ke, p.tsm_f16) == src) ++ke;
+              mbar_wait_backoff(&ctrl->full[stage], phase, bo);
+              tc_fence_after();
+              const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+              const uint32_t lb = p.wres ? w_lo0 + static_cast<uint32_t>(cb) * b_step : la + (kStageABytes >> 4);
+              for (int kk = k; kk < ke; ++kk)
+                umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(kk * 2), lb + static_cast<uint32_t>(kk * 2), idesc,
+                                     (cb | kk) != 0 ? 1u : 0u);
+              umma_commit_elect(&ctrl->empty[stage]);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              k = ke;
+            }
+          }
+        }
+        for (int kb = 0; kb < ((VHALO || p.tsm_T > 0) ? 0 : num_kb); ++kb) {
           mbar_wait_backoff(&ctrl->full[stage], phase, bo);
           tc_fence_after();
           const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;

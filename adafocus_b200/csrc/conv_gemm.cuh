@@ -58,11 +58,17 @@ struct ConvKernelParams {
   int backoff_ns;                  // sleep between mbarrier probes of the single-thread roles (0 = spin on try_wait)
   int epi_backoff_ns;              // same for the epilogue warps waiting for an accumulator
   int debug_flags;                 // bring-up only (env AF_CONV_DEBUG): 1 = skip TMA stores
+  // Temporal shift folded into the A-operand loads of a 1x1 conv (STH/ops/temporal_shift.py:29-46): the N images are
+  // N / tsm_T clips of tsm_T frames; input channels [0, 16*tsm_f16) are read from frame t+1, the next 16*tsm_f16 from
+  // frame t-1, the rest from frame t; frames outside the clip read as zeros (TMA out-of-bounds fill on the frame
+  // axis of the 5-D map maps.a5).  0 = off.  TN divides tsm_T (a tile never straddles two clips).
+  int tsm_T, tsm_f16;
 };
 
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
   CUtensorMap ah;     // vhalo: same tensor as a[0], box {64, TW, TH+KH-1, 1}
+  CUtensorMap a5;     // temporal-shift mode: the input as {C, W, H, T, clips}, box {64, TW, TH, TN, 1}
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
   CUtensorMap out;    // output tensor {Cout, Wo, Ho, N}, box {64, TW, TH, TN} (only when tma_store)
   CUtensorMap res;    // residual tensor, same dims / box as `out` (only when res_mma)

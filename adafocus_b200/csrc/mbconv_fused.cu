@@ -59,6 +59,18 @@ struct MbCursor {
 __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
+#ifndef AF_MB_EPI_SLEEP
+#define AF_MB_EPI_SLEEP 0
+#endif
+#ifndef AF_MB_DW_SLEEP
+#define AF_MB_DW_SLEEP 0
+#endif
+template <int NS>
+__device__ __forceinline__ void group_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (NS > 0) __nanosleep(NS);
+  }
+}
 
 template <int S>
 __global__ void __launch_bounds__(kMbThreads, 1)
@@ -269,7 +281,7 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
 
     // project epilogue of tile `pit` (this CTA's pit-th tile): D2 (TMEM) -> +bias (+ residual) -> fp16 -> staging -> TMA store
     auto project_epilogue = [&](int pit, int n, int th_i, int tw_i) {
-      mbar_wait(&ctrl->d2_full[pit & 1], (static_cast<uint32_t>(pit) >> 1) & 1u);
+      group_wait<AF_MB_EPI_SLEEP>(&ctrl->d2_full[pit & 1], (static_cast<uint32_t>(pit) >> 1) & 1u);
       tc_fence_after();
       if (et == 0) tma_store_wait_read0();    // the previous tile's store has released the staging tile
       named_barrier_sync(kEpilogueBarrier, kGroupThreads);
@@ -339,9 +351,9 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         const int vc = min(64, p.Cexp - c * 64);
         const int eb = g & (p.EB - 1);   // EB is 1 or 2
         // ---- expand epilogue: D1 (TMEM) -> +bias, ReLU6, zero outside the image -> E (smem, fp16)
-        mbar_wait(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
+        group_wait<AF_MB_EPI_SLEEP>(&ctrl->d1_full[g & 1], (static_cast<uint32_t>(g) >> 1) & 1u);
         tc_fence_after();
-        mbar_wait(&ctrl->e_empty[eb], (static_cast<uint32_t>(g >> (p.EB - 1)) & 1u) ^ 1u);
+        group_wait<AF_MB_EPI_SLEEP>(&ctrl->e_empty[eb], (static_cast<uint32_t>(g >> (p.EB - 1)) & 1u) ^ 1u);
         if (colhalf * 32 < vc) {
           uint8_t* e_buf = s_e + eb * p.e_bytes;
 #pragma unroll
@@ -438,8 +450,8 @@ mbconv_fused_kernel(const __grid_constant__ MbTensorMaps maps, const MbParams p)
         bias[0] = make_float2(b2.x, b2.y);
         bias[1] = make_float2(b2.z, b2.w);
       }
-      mbar_wait(&ctrl->e_full[eb], static_cast<uint32_t>(g >> (p.EB - 1)) & 1u);
-      mbar_wait(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
+      group_wait<AF_MB_DW_SLEEP>(&ctrl->e_full[eb], static_cast<uint32_t>(g >> (p.EB - 1)) & 1u);
+      group_wait<AF_MB_DW_SLEEP>(&ctrl->a2_empty[g & 1], ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u);
       if (q0 < q_count) {
         const uint8_t* e_buf = s_e + eb * p.e_bytes;
         uint8_t* a2 = s_a2 + (g & 1) * 16384;

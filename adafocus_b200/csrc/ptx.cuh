@@ -117,6 +117,21 @@ __device__ __forceinline__ void tma_load_4d_elect(void* smem_dst, const CUtensor
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d_elect(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // TMA store: smem tile (128-B swizzled box) -> global tensor; out-of-bounds parts of the box are not written.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
                                              int c3) {

@@ -284,10 +284,18 @@ class Engine:
             self.launch_count += 1
 
     # ------------------------------------------------------------------ kernels
+    def conv_tsm_ok(self, x, t, fold):
+        """Can conv() fold TemporalShift(n_segment=t, fold channels) into this input's loads?  (af_conv_tsm_supported)"""
+        if os.environ.get("AF_NO_TSM_FOLD") is not None or not x.is_contiguous():
+            return False
+        n, h, w, c = x.shape
+        return bool(self.lib.af_conv_tsm_supported(int(n), int(h), int(w), int(c), int(x.stride(2)), int(fold), int(t)))
+
     def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None,
-             row_stride=0, img_stride=0):
+             row_stride=0, img_stride=0, tsm=None):
         """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given; row_stride /
-        img_stride (elements) describe a sliding-window view, see af_conv_desc]."""
+        img_stride (elements) describe a sliding-window view, see af_conv_desc].  tsm=(T, fold): the convolution reads
+        TemporalShift.shift(x) (STH/ops/temporal_shift.py:29-46) without materialising it (1x1 convs, conv_tsm_ok)."""
         if shape is None:
             n, h, w, cin = x.shape
             in_stride = x.stride(2)
@@ -314,6 +322,7 @@ class Engine:
         d.in_stride, d.out_stride = in_stride, out_stride
         d.res_stride = residual.stride(-2) if residual is not None else 0
         d.in_row_stride, d.in_img_stride = row_stride, img_stride
+        d.tsm_t, d.tsm_fold = (int(tsm[0]), int(tsm[1])) if tsm is not None else (0, 0)
         check(self.lib.af_conv2d_nhwc_f16(self.h, byref(d), self._stream()), "af_conv2d_nhwc_f16")
         self._count()
         self.keep(x, pc.w, pc.scale, pc.bias, out, residual)

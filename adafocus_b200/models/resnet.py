@@ -159,9 +159,14 @@ class ResNetRunner:
         for e in self.blocks:
             inp = x
             a = x
+            tsm = None
             if e["shift"] is not None:
-                a = eng.tsm_shift(x, e["shift"][0], x.shape[-1] // e["shift"][1])
-            h1 = eng.conv(a, e["c1"])
+                t_seg, fold = e["shift"][0], x.shape[-1] // e["shift"][1]
+                if eng.conv_tsm_ok(x, t_seg, fold):
+                    tsm = (t_seg, fold)         # the shift rides in conv1's TMA loads (no shifted copy in HBM)
+                else:
+                    a = eng.tsm_shift(x, t_seg, fold)
+            h1 = eng.conv(a, e["c1"], tsm=tsm)
             if a is not inp:
                 eng.release(a)
             h2 = eng.conv(h1, e["c2"])

@@ -68,7 +68,16 @@ typedef struct af_conv_desc {
    * set, in_stride may be smaller than cin: consecutive "pixels" then overlap in memory (a sliding window over a
    * narrower tensor, e.g. the space-to-depth stem input of af_stem_s2d).  stride-1 convolutions only. */
   int64_t in_row_stride, in_img_stride;
+  /* Temporal shift (STH/ops/temporal_shift.py:29-46, TemporalShift.shift) folded into the input loads of a 1x1
+   * stride-1 convolution: the n images are n / tsm_t clips of tsm_t frames; input channels [0, tsm_fold) are read
+   * from the next frame, [tsm_fold, 2*tsm_fold) from the previous one, the rest from the frame itself, zeros outside
+   * the clip -- conv(shift(x)) without materialising shift(x).  tsm_t = 0: off.  Needs af_conv_tsm_supported(). */
+  int32_t tsm_t, tsm_fold;
 } af_conv_desc;
+
+/* 1 when af_conv2d_nhwc_f16 can fold the temporal shift for this geometry (cin % 64 == 0, fold % 16 == 0,
+ * n % t == 0, dense input); otherwise use af_tsm_shift_nhwc_f16 in front of the convolution. */
+int af_conv_tsm_supported(int n, int h, int w, int cin, int in_stride, int fold, int t);
 
 int af_version(void);
 const char* af_last_error(void);

@@ -518,6 +518,40 @@ def test_tsm_shift_bit_exact(eng):
         assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("nclips,t,hw,cin,cout,res", [
+    (3, 4, 9, 256, 64, False),      # fold 32: the first k-block mixes t+1 and t-1 (two boxes, half the MMAs each)
+    (2, 12, 5, 512, 128, False),    # fold 64: whole k-blocks per source; 5x5 maps -> two frames per tile
+    (2, 8, 18, 1024, 256, False),   # fold 128
+    (1, 8, 4, 2048, 512, False),    # 4x4 maps: eight frames per tile == the whole clip
+    (2, 6, 6, 256, 256, True),      # several n-blocks are not needed; residual rides along; T not a power of two
+])
+def test_conv_with_folded_temporal_shift_bit_exact(eng, nclips, t, hw, cin, cout, res):
+    """conv1x1(TemporalShift.shift(x)) with the shift folded into the A-operand TMA loads (frame t+1 / t-1 boxes,
+    out-of-clip frames zero-filled by the 5-D tensor map) == the same conv over the shifted copy written by the
+    stand-alone shift kernel, bit for bit, and the shifted copy equals the oracle's temporal_shift."""
+    from adafocus_b200.engine import AF_ACT_RELU, pack_conv
+    from oracle import adafocus_oracle as orc
+    torch.manual_seed(cin + t)
+    n = nclips * t
+    x = torch.randn(n, hw, hw, cin, device=DEV).half()
+    w = torch.randn(cout, cin, device=DEV) / math.sqrt(cin)
+    scale = None if res else torch.rand(cout, device=DEV) + 0.5
+    pc = pack_conv(w, scale, torch.randn(cout, device=DEV) * 0.1, act=AF_ACT_RELU, device=DEV, fold_scale=res)
+    fold = cin // 8
+    assert eng.conv_tsm_ok(x, t, fold)
+    r = torch.randn(n, hw, hw, cout, device=DEV).half() if res else None
+    shifted = eng.tsm_shift(x, t, fold)
+    ref_shift = orc.temporal_shift(x.permute(0, 3, 1, 2).float().cpu(), t, 8).permute(0, 2, 3, 1).half()
+    assert torch.equal(shifted.cpu(), ref_shift)
+    want = eng.conv(shifted, pc, residual=r)
+    got = eng.conv(x, pc, residual=r, tsm=(t, fold))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    # unsupported geometries are refused by the query (the caller then keeps the shift kernel)
+    assert not eng.conv_tsm_ok(x[:, :, :, :64].contiguous(), t, 8)
+    assert not eng.conv_tsm_ok(x[: n - 1], t, fold)
+
+
 def test_plan_replay_matches_eager(eng):
     from adafocus_b200.engine import pack_conv
     torch.manual_seed(1)
