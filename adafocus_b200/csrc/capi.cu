@@ -388,6 +388,9 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
   p.Wo = (d->w_ + 2 * d->pad - d->kw) / d->stride + 1;
   if (p.Ho < 1 || p.Wo < 1) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: empty output");
   p.Cout = d->cout;
+  p.pair = af::conv_gemm_pair_ok(p.N, p.Ho, p.Wo, d->cout, d->block_n,
+                                 d->kh * d->kw * ceil_div(d->cin, af::kConvBlockK) * af::kConvBlockK,
+                                 d->residual != nullptr && d->scale == nullptr && !d->out_f32, ctx->sm_count) ? 1 : 0;
   const bool tsm = d->tsm_t > 0;
   if (tsm) {
     if (d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad != 0 || windowed ||
@@ -405,7 +408,7 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
     // is one image's TW x TH pixels, chosen to minimise the rows loaded per tile (TH + KH - 1 per TH produced)
     static const bool no_vhalo = getenv("AF_NO_VHALO") != nullptr;
     const int nb = ceil_div(d->cout, d->block_n), cb = ceil_div(d->cin, af::kConvBlockK);
-    if (!no_vhalo && d->stride == 1 && d->kh > 1 && af::conv_gemm_wres_ok(nb, d->block_n, d->kh, d->kw, cb)) {
+    if (!no_vhalo && d->stride == 1 && d->kh > 1 && af::conv_gemm_wres_ok(nb, d->block_n, d->kh, d->kw, cb, p.pair)) {
       long long best = -1;
       int btw = 0, bth = 0;
       for (int tw = 128; tw >= 8; tw >>= 1) {
@@ -492,7 +495,8 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
     const cuuint64_t kpad = static_cast<cuuint64_t>(d->kh) * d->kw * p.cblks * af::kConvBlockK;
     const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(p.n_blocks) * p.BN};
     const cuuint64_t strides[1] = {kpad * 2};
-    const cuuint32_t bbox[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.BN)};
+    // (CTA pairs: each CTA loads its own half of the tile's rows)
+    const cuuint32_t bbox[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN)};
     if (!encode_map(ctx, &maps.b, d->w, 2, dims, strides, bbox, &err)) return fail(AF_ERR_CUDA, err);
   }
   // fp16 outputs leave through the smem-staged TMA store when 64-channel slices never straddle an n-block

@@ -129,7 +129,14 @@ struct TileCursor {
   }
 };
 
-template <bool VHALO>
+// PAIR: the kernel runs as clusters of two CTAs (cta_group::2, see ptx.cuh): the pair shares every weight tile (each
+// CTA keeps and loads only half of its BN rows) and one tcgen05.mma of M = 256 covers both CTAs' 128-pixel tiles --
+// twice the work per issued instruction for the small-N layers whose bound is the MMA issue rate, half the weight
+// traffic per CTA for the wide-N layers whose bound is the L2 -> SM operand rate.  The two tiles of a pair are
+// image groups 2*tn and 2*tn + 1 of the same (n-block, tile row, tile column).
+// TSM: temporal shift folded into the loads (ConvKernelParams::tsm_T); a template parameter so that the ordinary
+// kernels' single-thread roles carry no trace of it.
+template <bool VHALO, bool PAIR, bool TSM>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -138,7 +145,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
-  const int stage_b_bytes = p.BN * kConvBlockK * 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int bn_local = PAIR ? p.BN / 2 : p.BN;            // weight rows this CTA keeps in shared memory
+  const int stage_b_bytes = bn_local * kConvBlockK * 2;
   // Resident weights (p.wres): a layer with a single n-block and a small filter keeps ALL its weight k-blocks in
   // shared memory for the life of the CTA; pipeline stages then carry the A operand only, which removes the
   // per-tile weight re-load (a third of the L2 -> SM traffic of the 64-channel layers) and deepens the A prefetch.
@@ -159,8 +168,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_tiles = p.tiles_w * p.tiles_h * (PAIR ? (p.tiles_n + 1) / 2 : p.tiles_n);
   const int total_tiles = m_tiles * p.n_blocks;
+  const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // first tile of this CTA (pair)
+  const int tstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = p.KH * p.KW * p.cblks;
 
   if (threadIdx.x == 0) {
@@ -173,7 +184,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     for (int a = 0; a < 4; ++a) {
       // one arrive per warp of every epilogue group that reads the stage: both groups of the stage when a tile has
       // several 64-column slices (they split the slices), one group when it has a single slice (they alternate tiles)
-      mbar_init(&ctrl->tmem_empty[a], ((p.tma_store && p.BN <= 64) || (VHALO && p.epi_groups == 2)) ? 4 : 8);
+      // (pair: the leader's barrier also takes the arrivals of the peer CTA's epilogue warps)
+      mbar_init(&ctrl->tmem_empty[a],
+                (((p.tma_store && p.BN <= 64) || (VHALO && p.epi_groups == 2)) ? 4 : 8) * (PAIR ? 2 : 1));
     }
     fence_mbar_init();
   }
@@ -183,7 +196,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     if (p.tma_store) tma_prefetch_desc(&maps.out);
     if (p.res_mma) tma_prefetch_desc(&maps.res);
     if (VHALO) tma_prefetch_desc(&maps.ah);
-    if (p.tsm_T > 0) tma_prefetch_desc(&maps.a5);
+    if (TSM) tma_prefetch_desc(&maps.a5);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -191,13 +204,20 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     }
   }
   if (warp == 1) {
-    tmem_alloc(&ctrl->tmem_base, 512);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(&ctrl->tmem_base, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&ctrl->tmem_base, 512);
+      tmem_relinquish();
+    }
   }
   if (p.res_mma && warp >= 2) {
     // B operand of the residual MMA: I[n][k] = (n == k), 64 rows of 128 B, 16-byte chunk c of row n at (c ^ (n & 7))
-    for (int i = threadIdx.x - 64; i < 64 * 8; i += kEpilogueGroups * kEpilogueThreads) {
-      const int n = i >> 3, c = i & 7;
+    // (pair: this CTA supplies rows [32 * rank, 32 * rank + 32) of the 64 x 64 identity, stored as rows 0..31)
+    for (int i = threadIdx.x - 64; i < (PAIR ? 32 : 64) * 8; i += kEpilogueGroups * kEpilogueThreads) {
+      const int row_l = i >> 3, c = i & 7;
+      const int n = row_l + (PAIR ? 32 * static_cast<int>(rank) : 0);
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
       if ((n >> 3) == c) {
         const uint32_t one = (n & 1) ? 0x3C000000u : 0x00003C00u;   // fp16 1.0 in the high / low half
@@ -207,14 +227,41 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         val.z = wsel == 2 ? one : 0u;
         val.w = wsel == 3 ? one : 0u;
       }
-      *reinterpret_cast<uint4*>(ident + n * 128 + ((c ^ (n & 7)) << 4)) = val;
+      *reinterpret_cast<uint4*>(ident + row_l * 128 + ((c ^ (row_l & 7)) << 4)) = val;
     }
     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA completion
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  // pair: completion bytes of both CTAs' loads are counted on the LEADER's full / wfull barriers
+  const uint32_t full0_addr = PAIR ? mapa_u32(&ctrl->full[0], 0) : 0u;
+  const uint32_t wfull_addr = PAIR ? mapa_u32(&ctrl->wfull, 0) : 0u;
+  const uint32_t tmem_empty0_addr = PAIR ? mapa_u32(&ctrl->tmem_empty[0], 0) : 0u;
+  (void)full0_addr;
+  (void)wfull_addr;
+  (void)tmem_empty0_addr;
+  auto load2 = [&](void* dst, const CUtensorMap* m, int st, int c0, int c1) {
+    if constexpr (PAIR) {
+      tma_load_2d_elect_pair(dst, m, st < 0 ? wfull_addr : full0_addr + 8u * static_cast<uint32_t>(st), c0, c1);
+    } else {
+      tma_load_2d_elect(dst, m, st < 0 ? &ctrl->wfull : &ctrl->full[st], c0, c1);
+    }
+  };
+  auto load4 = [&](void* dst, const CUtensorMap* m, int st, int c0, int c1, int c2, int c3) {
+    if constexpr (PAIR) tma_load_4d_elect_pair(dst, m, full0_addr + 8u * static_cast<uint32_t>(st), c0, c1, c2, c3);
+    else tma_load_4d_elect(dst, m, &ctrl->full[st], c0, c1, c2, c3);
+  };
+  auto load5 = [&](void* dst, const CUtensorMap* m, int st, int c0, int c1, int c2, int c3, int c4) {
+    if constexpr (PAIR) tma_load_5d_elect_pair(dst, m, full0_addr + 8u * static_cast<uint32_t>(st), c0, c1, c2, c3, c4);
+    else tma_load_5d_elect(dst, m, &ctrl->full[st], c0, c1, c2, c3, c4);
+  };
+  // the leader announces the bytes of BOTH CTAs; the peer's loads only complete on that barrier
+  auto expect = [&](uint64_t* bar, uint32_t bytes) {
+    if (!PAIR || rank == 0) mbar_arrive_expect_tx_elect(bar, PAIR ? 2u * bytes : bytes);
+  };
 
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous
   // kernel in the stream; nothing below may read or write global memory before that kernel has completed.
@@ -227,24 +274,26 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       int stage = 0;
       uint32_t phase = 0;
       const int bo = p.backoff_ns;
+      const int brow = static_cast<int>(rank) * bn_local;   // pair: this CTA's half of every weight tile
       if (p.wres) {
-        mbar_arrive_expect_tx_elect(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
+        expect(&ctrl->wfull, static_cast<uint32_t>(num_kb * stage_b_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
-          tma_load_2d_elect(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, &ctrl->wfull, kb * kConvBlockK, 0);
+          load2(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, -1, kb * kConvBlockK, brow);
       }
       TileCursor cur;
-      cur.init(blockIdx.x, gridDim.x, p);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, cur.advance(p)) {
+      cur.init(tile0, tstep, p);
+      for (int tile = tile0; tile < total_tiles; tile += tstep, cur.advance(p)) {
         const int nb = cur.nb;
-        const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = cur.tn * p.TN;
+        const int tn_eff = PAIR ? cur.tn * 2 + static_cast<int>(rank) : cur.tn;
+        const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = tn_eff * p.TN;
         int kb = 0;
         if constexpr (VHALO) {
           for (int kw = 0; kw < p.KW; ++kw) {
             for (int cb = 0; cb < p.cblks; ++cb) {
               mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_a_bytes));
-              tma_load_4d_elect(sa, &maps.ah, &ctrl->full[stage], cb * kConvBlockK, ow0 + kw - p.pad, oh0 - p.pad, n0);
+              expect(&ctrl->full[stage], static_cast<uint32_t>(stage_a_bytes));
+              load4(sa, &maps.ah, stage, cb * kConvBlockK, ow0 + kw - p.pad, oh0 - p.pad, n0);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -252,11 +301,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        if (!VHALO && p.tsm_T > 0) {
+        if constexpr (!VHALO && TSM) {
           // temporal shift folded into the loads: per 64-channel k-block one box per run of 16-channel steps that
           // share a source frame (t+1 / t-1 / t); the frame axis of maps.a5 zero-fills outside the clip
           const int tpc = p.tsm_T / p.TN;
-          const int tb = cur.tn / tpc, t0 = (cur.tn - tb * tpc) * p.TN;
+          const int tb = tn_eff / tpc, t0 = (tn_eff - tb * tpc) * p.TN;
           for (int cb = 0; cb < p.cblks; ++cb) {
             int k = 0;
             while (k < 4) {
@@ -265,9 +314,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               while (ke < 4 && tsm_source(4 * cb + ke, p.tsm_f16) == src) ++ke;
               mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
-              tma_load_5d_elect(sa, &maps.a5, &ctrl->full[stage], cb * kConvBlockK, ow0, oh0, t0 + src, tb);
-              if (!p.wres) tma_load_2d_elect(sa + kStageABytes, &maps.b, &ctrl->full[stage], cb * kConvBlockK, nb * p.BN);
+              expect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+              load5(sa, &maps.a5, stage, cb * kConvBlockK, ow0, oh0, t0 + src, tb);
+              if (!p.wres) load2(sa + kStageABytes, &maps.b, stage, cb * kConvBlockK, nb * p.BN + brow);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -276,7 +325,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        for (int kh = 0; kh < ((VHALO || p.tsm_T > 0) ? 0 : p.KH); ++kh) {
+        for (int kh = 0; kh < ((VHALO || TSM) ? 0 : p.KH); ++kh) {
           for (int kw = 0; kw < p.KW; ++kw) {
             int map_idx = 0, ch, cw;
             if (p.stride == 1) {
@@ -293,9 +342,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
               uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
               uint8_t* sb = sa + kStageABytes;
-              mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
-              tma_load_4d_elect(sa, &maps.a[map_idx], &ctrl->full[stage], cb * kConvBlockK, cw, ch, n0);
-              if (!p.wres) tma_load_2d_elect(sb, &maps.b, &ctrl->full[stage], kb * kConvBlockK, nb * p.BN);
+              expect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+              load4(sa, &maps.a[map_idx], stage, cb * kConvBlockK, cw, ch, n0);
+              if (!p.wres) load2(sb, &maps.b, stage, kb * kConvBlockK, nb * p.BN + brow);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -308,8 +357,8 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-            mbar_arrive_expect_tx_elect(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
-            tma_load_4d_elect(sa, &maps.res, &ctrl->full[stage], nb * p.BN + j * 64, ow0, oh0, n0);
+            expect(&ctrl->full[stage], static_cast<uint32_t>(kStageABytes));
+            load4(sa, &maps.res, stage, nb * p.BN + j * 64, ow0, oh0, n0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -319,10 +368,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    {
+    // ============================ MMA issuer (pair: the leader CTA only) ============================
+    if (!PAIR || rank == 0) {
       // the whole warp runs the loop (converged); one elected lane issues each MMA / commit
-      const uint32_t idesc = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(p.BN));
+      auto mma = [&](uint32_t d, uint32_t la, uint32_t lb, uint32_t id, uint32_t acc) {
+        if constexpr (PAIR) umma_f16_ss_lo_elect_pair(d, la, lb, id, acc);
+        else umma_f16_ss_lo_elect(d, la, lb, id, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) umma_commit_elect_pair(bar);   // same barrier in both CTAs of the pair
+        else umma_commit_elect(bar);
+      };
+      const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * kConvBlockM : kConvBlockM, static_cast<uint32_t>(p.BN));
       const bool alternate_tiles = p.tma_store && p.BN <= 64 && !(VHALO && p.epi_groups == 2);
       int stage = 0;
       uint32_t phase = 0;
@@ -332,10 +389,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem)), a_step = static_cast<uint32_t>(stage_bytes) >> 4;
       const uint32_t w_lo0 = smem_desc_lo(smem_u32(wres)), b_step = static_cast<uint32_t>(stage_b_bytes) >> 4;
       if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
-      int mma_nb = static_cast<int>(blockIdx.x) % p.n_blocks;
-      const int mma_dnb = static_cast<int>(gridDim.x) % p.n_blocks;
-      for (int tile = blockIdx.x; tile < total_tiles;
-           tile += gridDim.x, ++it, mma_nb = mma_nb + mma_dnb >= p.n_blocks ? mma_nb + mma_dnb - p.n_blocks : mma_nb + mma_dnb) {
+      int mma_nb = tile0 % p.n_blocks;
+      const int mma_dnb = tstep % p.n_blocks;
+      for (int tile = tile0; tile < total_tiles;
+           tile += tstep, ++it, mma_nb = mma_nb + mma_dnb >= p.n_blocks ? mma_nb + mma_dnb - p.n_blocks : mma_nb + mma_dnb) {
         // accumulator of this tile: two 256-column stages, or -- single-slice tiles handled by four alternating
         // epilogue groups -- four 128-column ones, so that four tiles are in flight between the MMA and the epilogue
         const int as = it & 1;
@@ -355,10 +412,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                 const uint32_t la = la0 + static_cast<uint32_t>(kh * p.TW) * 8u;   // kh rows down: kh * TW * 128 B
 #pragma unroll
                 for (int k = 0; k < kConvBlockK / 16; ++k)
-                  umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+                  mma(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
                                  (kw | cb | kh | k) != 0 ? 1u : 0u);
               }
-              umma_commit_elect(&ctrl->empty[stage]);
+              commit(&ctrl->empty[stage]);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -366,7 +423,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        if (!VHALO && p.tsm_T > 0) {
+        if constexpr (!VHALO && TSM) {
           for (int cb = 0; cb < p.cblks; ++cb) {
             int k = 0;
             while (k < 4) {
@@ -378,9 +435,9 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
               const uint32_t lb = p.wres ? w_lo0 + static_cast<uint32_t>(cb) * b_step : la + (kStageABytes >> 4);
               for (int kk = k; kk < ke; ++kk)
-                umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(kk * 2), lb + static_cast<uint32_t>(kk * 2), idesc,
+                mma(tmem_d, la + static_cast<uint32_t>(kk * 2), lb + static_cast<uint32_t>(kk * 2), idesc,
                                      (cb | kk) != 0 ? 1u : 0u);
-              umma_commit_elect(&ctrl->empty[stage]);
+              commit(&ctrl->empty[stage]);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -389,7 +446,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
-        for (int kb = 0; kb < ((VHALO || p.tsm_T > 0) ? 0 : num_kb); ++kb) {
+        for (int kb = 0; kb < ((VHALO || TSM) ? 0 : num_kb); ++kb) {
           mbar_wait_backoff(&ctrl->full[stage], phase, bo);
           tc_fence_after();
           const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
@@ -397,10 +454,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
-            umma_f16_ss_lo_elect(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
+            mma(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc,
                            (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_elect(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
+          commit(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -412,15 +469,15 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
           const uint32_t li = smem_desc_lo(smem_u32(ident));
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
             const int nj = p.BN - j * 64 < 64 ? p.BN - j * 64 : 64;
-            const uint32_t idesc_r = make_idesc_f16_f32(kConvBlockM, static_cast<uint32_t>(nj));
+            const uint32_t idesc_r = make_idesc_f16_f32(PAIR ? 2 * kConvBlockM : kConvBlockM, static_cast<uint32_t>(nj));
             mbar_wait_backoff(&ctrl->full[stage], phase, bo);
             tc_fence_after();
             const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
 #pragma unroll
             for (int k = 0; k < kConvBlockK / 16; ++k)
-              umma_f16_ss_lo_elect(tmem_d + static_cast<uint32_t>(j * 64), la + static_cast<uint32_t>(k * 2),
+              mma(tmem_d + static_cast<uint32_t>(j * 64), la + static_cast<uint32_t>(k * 2),
                                    li + static_cast<uint32_t>(k * 2), idesc_r, 1u);
-            umma_commit_elect(&ctrl->empty[stage]);
+            commit(&ctrl->empty[stage]);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -429,7 +486,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         // accumulator complete -> epilogue.  With single-slice tiles the stage's two groups take alternate tiles and
         // each waits on its own barrier, so that every waiter sees every phase of the barrier it polls.
-        umma_commit_elect(&ctrl->tmem_full[alternate_tiles ? as + 2 * ((it >> 1) & 1) : as]);
+        commit(&ctrl->tmem_full[alternate_tiles ? as + 2 * ((it >> 1) & 1) : as]);
       }
     }
   } else {
@@ -462,14 +519,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     pdl_wait_prior_grid();
     TileCursor cur;
     {
-      const long long first = blockIdx.x + static_cast<long long>(as) * gridDim.x;
-      cur.init(first < total_tiles ? static_cast<int>(first) : 0, 2 * static_cast<int>(gridDim.x), p);
+      const long long first = tile0 + static_cast<long long>(as) * tstep;
+      cur.init(first < total_tiles ? static_cast<int>(first) : 0, 2 * tstep, p);
     }
-    for (int it = as; !(solo && sub == 1) && blockIdx.x + static_cast<long long>(it) * gridDim.x < total_tiles;
+    auto release_acc = [&](int ai) {   // hand a TMEM accumulator back to the MMA warp (of the leader CTA)
+      if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0_addr + 8u * static_cast<uint32_t>(ai));
+      else mbar_arrive(&ctrl->tmem_empty[ai]);
+    };
+    for (int it = as; !(solo && sub == 1) && tile0 + static_cast<long long>(it) * tstep < total_tiles;
          it += 2, cur.advance(p)) {
       if (alternate_tiles && ((it >> 1) & 1) != sub) continue;
       const int nb = cur.nb;
-      const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = cur.tn * p.TN;
+      const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = (PAIR ? cur.tn * 2 + static_cast<int>(rank) : cur.tn) * p.TN;
       const int ow = ow0 + tw, oh = oh0 + th, n = n0 + tn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (n < p.N);
       const long long pix = (static_cast<long long>(n) * p.Ho + oh) * p.Wo + ow;
@@ -510,7 +571,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
               // this group's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&ctrl->tmem_empty[ai]);
+              if (lane == 0) release_acc(ai);
             }
             if (hf == 0) {
               // the group's staging buffer may still be feeding its previous TMA store
@@ -586,30 +647,51 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->tmem_empty[ai]);
+        if (lane == 0) release_acc(ai);
       }
     }
     if (p.tma_store && et == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal it / read its operands
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 }  // namespace
 
-bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks) {
+bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks, int pair) {
   static const bool no_wres = getenv("AF_NO_WRES") != nullptr;
-  const long long wbytes = 1LL * KH * KW * cblks * BN * kConvBlockK * 2;
+  const long long wbytes = 1LL * KH * KW * cblks * (pair ? BN / 2 : BN) * kConvBlockK * 2;   // per CTA
   return !no_wres && n_blocks == 1 && wbytes <= 80 * 1024;
+}
+
+bool conv_gemm_pair_ok(int N, int Ho, int Wo, int Cout, int BN, int K, int has_residual, int sm_count) {
+  static const char* env = getenv("AF_CONV_PAIR");
+  static const int mode = env ? atoi(env) : -1;      // -1 = heuristic
+  if (mode == 0) return false;
+  // legality: an even split of the weight tile in 8-row groups; the identity tile of the residual MMA is split per
+  // 64-column slice, so those layers need whole slices; at least two image groups to pair up
+  if (BN % 16 != 0 || N < 2) return false;
+  if (has_residual && BN % 64 != 0) return false;
+  if (mode == 1) return true;
+  // heuristic (measured per layer at 1024 patches, profiles/r2_pair_ab.txt): the pair pays for MMA-heavy tiles --
+  // K >= 512 and a tile at least 128 columns wide (-2 % .. -8 %: the weight half-tiles halve each CTA's L2 -> SM
+  // operand traffic); short-K, store-bound layers lose (the two CTAs' epilogues gate each other through the shared
+  // accumulator hand-back: 32 -> 96 @112^2 145 -> 248 us) and a cta_group::2 MMA of N <= 64 costs more than two
+  // cta_group::1 MMAs (3x3 64 -> 64 @32^2: 99 -> 110 us), so the issue-bound small-N layers stay single-CTA.
+  const long long tiles = (1LL * N * Ho * Wo + 127) / 128 * ((Cout + BN - 1) / BN);
+  return K >= 512 && BN >= 128 && tiles >= 4LL * sm_count;
 }
 
 size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int stage_a_bytes, int epi_groups, int* stages_out,
                             int* epi_bufs_out) {
+  // BN = weight rows per CTA (half the tile's N for CTA pairs)
   const int stage_bytes = stage_a_bytes + (wres_bytes ? 0 : BN * kConvBlockK * 2);
   // one 16 KiB staging buffer per epilogue group (other groups compute while a group's TMA store drains)
   const int epi_bufs = 1;
@@ -629,14 +711,15 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   ConvKernelParams p = p_in;
   int stages = 0, epi_bufs = 1;
   // resident weights: single n-block and at most 80 KiB of weights (>= 4 A-only stages remain)
-  const int wbytes = p.KH * p.KW * p.cblks * p.BN * kConvBlockK * 2;
-  p.wres = conv_gemm_wres_ok(p.n_blocks, p.BN, p.KH, p.KW, p.cblks) ? 1 : 0;
+  const int bn_local = p.pair ? p.BN / 2 : p.BN;
+  const int wbytes = p.KH * p.KW * p.cblks * bn_local * kConvBlockK * 2;
+  p.wres = conv_gemm_wres_ok(p.n_blocks, p.BN, p.KH, p.KW, p.cblks, p.pair) ? 1 : 0;
   if (!p.wres) p.vhalo = 0;
   const int stage_a_bytes = p.vhalo ? (p.TH + p.KH - 1) * p.TW * 128 : kStageABytes;
   static const bool four_groups = getenv("AF_VHALO_4GROUPS") != nullptr;
   p.epi_groups = (p.vhalo && p.tma_store && !four_groups) ? 2 : kEpilogueGroups;
   const size_t smem =
-      conv_gemm_smem_bytes(p.BN, p.res_mma, p.wres ? wbytes : 0, stage_a_bytes, p.epi_groups, &stages, &epi_bufs);
+      conv_gemm_smem_bytes(bn_local, p.res_mma, p.wres ? wbytes : 0, stage_a_bytes, p.epi_groups, &stages, &epi_bufs);
   if (p.vhalo && (stages < 2 || stage_a_bytes % 1024 != 0)) return cudaErrorInvalidValue;
   p.stages = stages;
   p.epi_bufs = epi_bufs;
@@ -651,29 +734,60 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kConvSmemBudget);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBudget);
-    if (e != cudaSuccess) return e;
+    using Kern = void (*)(const ConvTensorMaps, const ConvKernelParams);
+    const Kern kerns[6] = {conv_gemm_kernel<false, false, false>, conv_gemm_kernel<true, false, false>,
+                           conv_gemm_kernel<false, true, false>,  conv_gemm_kernel<true, true, false>,
+                           conv_gemm_kernel<false, false, true>,  conv_gemm_kernel<false, true, true>};
+    for (Kern k : kerns) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBudget);
+      if (e != cudaSuccess) return e;
+    }
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
-  int grid = total_tiles < sm_count ? total_tiles : sm_count;
-  if (grid < 1) grid = 1;
+  int grid;
+  if (p.pair) {
+    const int pairs = p.tiles_w * p.tiles_h * ((p.tiles_n + 1) / 2) * p.n_blocks;
+    const int max_pairs = sm_count / 2;
+    grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    if (grid < 2) grid = 2;
+  } else {
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+    grid = total_tiles < sm_count ? total_tiles : sm_count;
+    if (grid < 1) grid = 1;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   static const bool pdl = getenv("AF_NO_PDL") == nullptr;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (p.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;   // the two CTAs of a pair land on the two SMs of one TPC
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  if (p.vhalo) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, maps, p);
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, maps, p);
+  cfg.numAttrs = na;
+  if (p.tsm_T > 0) {
+    if (p.vhalo) return cudaErrorInvalidValue;
+    if (p.pair) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true, true>, maps, p);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, false, true>, maps, p);
+  }
+  if (p.pair) {
+    if (p.vhalo) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true, false>, maps, p);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true, false>, maps, p);
+  }
+  if (p.vhalo) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false, false>, maps, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, false, false>, maps, p);
 }
 
 }  // namespace af

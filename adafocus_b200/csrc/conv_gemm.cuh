@@ -63,6 +63,7 @@ struct ConvKernelParams {
   // frame t-1, the rest from frame t; frames outside the clip read as zeros (TMA out-of-bounds fill on the frame
   // axis of the 5-D map maps.a5).  0 = off.  TN divides tsm_T (a tile never straddles two clips).
   int tsm_T, tsm_f16;
+  int pair;                        // 1: clusters of two CTAs, cta_group::2 MMAs of M = 256 (conv_gemm.cu, PAIR); maps.b box = BN/2 rows
 };
 
 struct ConvTensorMaps {
@@ -78,6 +79,8 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
                              cudaStream_t stream);
 size_t conv_gemm_smem_bytes(int BN, int res_mma, int wres_bytes, int stage_a_bytes, int epi_groups, int* stages_out,
                             int* epi_bufs_out);
-bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks);
+bool conv_gemm_wres_ok(int n_blocks, int BN, int KH, int KW, int cblks, int pair = 0);
+// Should this layer run as CTA pairs?  (env AF_CONV_PAIR: 0 = never, 1 = wherever legal, unset = heuristic)
+bool conv_gemm_pair_ok(int N, int Ho, int Wo, int Cout, int BN, int K, int has_residual, int sm_count);
 
 }  // namespace af

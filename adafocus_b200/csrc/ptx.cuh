@@ -276,6 +276,112 @@ __device__ __forceinline__ void ldg256_nc(const void* p, uint4& lo, uint4& hi) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- CTA pair (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA supplies its own 128 rows of
+// A and HALF of the N rows of B from the same shared-memory offsets and receives its 128 rows of D in its own TMEM.
+// Only the leader (cluster rank 0) issues MMAs / commits; both CTAs issue their own TMA loads, which complete on the
+// leader's mbarrier (".cta_group::2" form of the bulk-tensor copy).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) in the CTA of rank `cta`
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_lo_elect_pair(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc,
+                                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+// arrive (once all previously issued MMAs of this thread have completed) on the barrier at the SAME shared-memory
+// offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_elect_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// bulk-tensor loads into THIS CTA's shared memory whose completion bytes are counted on `bar_cluster_addr`, an
+// mbarrier of the pair's leader CTA (shared::cluster address, see mapa_u32)
+__device__ __forceinline__ void tma_load_2d_elect_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                       int c0, int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                       int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_elect_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                       int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 B (64 fp16) wide and
 // laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused.

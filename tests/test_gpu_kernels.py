@@ -552,6 +552,20 @@ def test_conv_with_folded_temporal_shift_bit_exact(eng, nclips, t, hw, cin, cout
     assert not eng.conv_tsm_ok(x[: n - 1], t, fold)
 
 
+def test_conv_cases_in_forced_cta_pair_mode():
+    """Every convolution case above again with AF_CONV_PAIR=1: clusters of two CTAs, cta_group::2 MMAs of M = 256, each
+    CTA holding half of every weight tile (conv_gemm.cu, PAIR).  The mode is a process-wide knob, hence the child
+    process; by default only large MMA-heavy layers take it (conv_gemm_pair_ok)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, AF_CONV_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-m", "gpu",
+                          "-k", "conv and not forced_cta_pair", "-x", "--timeout=60"], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_plan_replay_matches_eager(eng):
     from adafocus_b200.engine import pack_conv
     torch.manual_seed(1)

@@ -14,6 +14,17 @@ CASES = {
     "conv3_l2": (1024, 16, 16, 128, 512, 1, 1, 0, 1, True),      # fL layer2 conv3 + residual
     "conv3_l3": (1024, 8, 8, 256, 1024, 1, 1, 0, 1, True),       # fL layer3 conv3 + residual
     "expand56": (1024, 56, 56, 24, 144, 1, 1, 0, 2, False),      # fG block 3 expand
+    "conv1_l2": (1024, 16, 16, 512, 128, 1, 1, 0, 1, False),     # fL layer2 conv1
+    "conv2_l2": (1024, 16, 16, 128, 128, 3, 1, 1, 1, False),     # fL layer2 3x3
+    "conv1_l3": (1024, 8, 8, 1024, 256, 1, 1, 0, 1, False),      # fL layer3 conv1
+    "conv1_l4": (1024, 4, 4, 2048, 512, 1, 1, 0, 1, False),      # fL layer4 conv1
+    "conv2_l4": (1024, 4, 4, 512, 512, 3, 1, 1, 1, False),       # fL layer4 3x3
+    "conv3_l4": (1024, 4, 4, 512, 2048, 1, 1, 0, 1, True),       # fL layer4 conv3 + residual
+    "ds_l3": (1024, 16, 16, 512, 1024, 1, 2, 0, 0, False),       # fL layer3 downsample (stride 2)
+    "conv2s2_l3": (1024, 16, 16, 256, 256, 3, 2, 1, 1, False),   # fL layer3.0 3x3 stride 2
+    "last_fg": (1024, 7, 7, 320, 1280, 1, 1, 0, 2, False),       # fG last 1x1
+    "exp_fg14": (1024, 14, 14, 96, 576, 1, 1, 0, 2, False),      # fG 14x14 expand
+    "proj_fg14": (1024, 14, 14, 576, 96, 1, 1, 0, 0, True),      # fG 14x14 project + residual
 }
 
 def main():
