@@ -98,6 +98,8 @@ SIGNATURES = {
     "af_frames_u8_to_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                     c_void_p]),
     "af_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "af_resize_crop_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

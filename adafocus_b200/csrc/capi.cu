@@ -847,6 +847,21 @@ int af_split3_f16(af_ctx* ctx, const float* in, int64_t in_stride, void* out, in
                   [=](cudaStream_t s) { return af::launch_split3_f16(in, in_stride, o, rows, cols, s); });
 }
 
+int af_resize_crop_u8(af_ctx* ctx, const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int H, int W, int C,
+                      const int32_t* hbounds, const int32_t* hkk, int hks, int OW, const int32_t* vbounds,
+                      const int32_t* vkk, int vks, int OH, int row0, int rows, void* stream) {
+  if (in == nullptr || tmp == nullptr || out == nullptr || hbounds == nullptr || hkk == nullptr || vbounds == nullptr ||
+      vkk == nullptr)
+    return fail(AF_ERR_INVALID, "af_resize_crop_u8: null argument");
+  if (N < 0 || H < 1 || W < 1 || C < 1 || OW < 1 || OH < 1 || hks < 1 || vks < 1 || row0 < 0 || rows < 1 ||
+      row0 + rows > H || W * C > 12288 || N > 65535)
+    return fail(AF_ERR_INVALID, "af_resize_crop_u8: bad geometry (need row0 + rows <= H, W * C <= 12288, N <= 65535)");
+  return dispatch(ctx, stream, "af_resize_crop_u8", [=](cudaStream_t s) {
+    return af::launch_pil_resize_crop_u8(in, tmp, out, N, H, W, C, hbounds, hkk, hks, OW, vbounds, vkk, vks, OH, row0,
+                                         rows, s);
+  });
+}
+
 int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stream) {
   if (in == nullptr || out == nullptr) return fail(AF_ERR_INVALID, "af_f32_to_f16: null tensor");
   __half* o = static_cast<__half*>(out);

@@ -978,6 +978,103 @@ __global__ void fill_f32_kernel(float* p, float v, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// ------------------------------------------------------------------------------------------------ PIL-exact resampling
+// One pass of Pillow's 8-bit resampler (libImaging/Resample.c, ImagingResampleHorizontal_8bpc / Vertical_8bpc) behind
+// torchvision.transforms.Resize, i.e. the reference's GroupScale (ACT/ops/transforms.py:78-93): per output index the
+// host-computed window (first input index, tap count) and 22-bit fixed-point weights; acc = 2^21 + sum(pixel * k),
+// >> 22, clipped to [0, 255].  Integer arithmetic throughout -> bit-identical to Pillow.  The tables only cover the
+// rows / columns the centre crop keeps (GroupCenterCrop, :37-43), so the crop is free.
+//   horizontal: in (N, H, W, C) -> tmp (N, rows, OW, C), rows = source rows [row0, row0 + rows)
+//   vertical  : tmp (row r = source row row0 + r) -> out (N, OH, OW, C)
+// Frames stay separate: af_frames_u8_to_f32 over N "clips" of C channels writes (N, C, HW), which IS the (B, T*C, HW)
+// layout of Stack() + ToTorchFormatTensor (np.concatenate(img_group, axis=2) then permute, :303-336).
+// Horizontal pass: one block per (frame, source row): the row is staged in shared memory with coalesced 16-byte loads,
+// then every thread forms 4 consecutive output bytes (different pixels / channels) and stores them as one word.
+constexpr int kResampleMaxRowBytes = 12288;   // W * C of the source frame (e.g. 4096 x 3)
+__global__ void __launch_bounds__(kThreads)
+pil_resample_h_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ bounds,
+                         const int32_t* __restrict__ kk, int ksize, int H, int W, int C, int rows, int OW, int row0) {
+  __shared__ __align__(16) uint8_t srow[kResampleMaxRowBytes + 32];
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int in_bytes = W * C;
+  const uint8_t* src = in + (static_cast<long long>(n) * H + (row0 + y)) * in_bytes;
+  const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);   // stage from the aligned address below
+  const uint8_t* asrc = src - mis;
+  for (int i = threadIdx.x * 16; i < in_bytes + mis; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(srow + i) = __ldg(reinterpret_cast<const uint4*>(asrc + i));   // may over-read < 16 B inside the allocation's 256-B granule
+  __syncthreads();
+  const uint8_t* row = srow + mis;
+  const int out_bytes = OW * C;
+  uint8_t* dst = out + (static_cast<long long>(n) * rows + y) * out_bytes;
+  for (int j0 = threadIdx.x * 4; j0 < out_bytes; j0 += blockDim.x * 4) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j0 + e;
+      if (j < out_bytes) {
+        const int x = j / C, c = j - x * C;
+        const int first = __ldg(bounds + 2 * x), taps = __ldg(bounds + 2 * x + 1);
+        const int32_t* k = kk + x * ksize;
+        int acc = 1 << 21;
+        for (int t = 0; t < taps; ++t) acc += static_cast<int>(row[(first + t) * C + c]) * __ldg(k + t);
+        acc >>= 22;
+        acc = acc < 0 ? 0 : (acc > 255 ? 255 : acc);
+        packed |= static_cast<uint32_t>(acc) << (8 * e);
+      }
+    }
+    if (j0 + 4 <= out_bytes && (reinterpret_cast<uintptr_t>(dst + j0) & 3u) == 0) {
+      *reinterpret_cast<uint32_t*>(dst + j0) = packed;
+    } else {
+      for (int e = 0; e < 4 && j0 + e < out_bytes; ++e) dst[j0 + e] = static_cast<uint8_t>(packed >> (8 * e));
+    }
+  }
+}
+
+// Vertical pass: a thread forms 4 consecutive bytes of an output row from word loads of the tap rows.
+__global__ void __launch_bounds__(kThreads)
+pil_resample_v_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ bounds,
+                         const int32_t* __restrict__ kk, int ksize, int N, int rows, int row_bytes, int OH, int row0) {
+  const int words = (row_bytes + 3) >> 2;
+  const long long total = static_cast<long long>(N) * OH * words;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wj = static_cast<int>(idx % words);
+  const long long r = idx / words;
+  const int y = static_cast<int>(r % OH);
+  const int n = static_cast<int>(r / OH);
+  const int first = __ldg(bounds + 2 * y), taps = __ldg(bounds + 2 * y + 1);
+  const int32_t* k = kk + y * ksize;
+  const uint8_t* src = in + (static_cast<long long>(n) * rows + (first - row0)) * row_bytes + wj * 4;
+  uint8_t* dst = out + (static_cast<long long>(n) * OH + y) * row_bytes + wj * 4;
+  const bool whole = wj * 4 + 4 <= row_bytes && (row_bytes & 3) == 0;   // aligned word access (buffers are 256-B aligned)
+  int acc[4] = {1 << 21, 1 << 21, 1 << 21, 1 << 21};
+  for (int t = 0; t < taps; ++t) {
+    const int kv = __ldg(k + t);
+    const uint8_t* p = src + static_cast<long long>(t) * row_bytes;
+    if (whole) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+      acc[0] += static_cast<int>(v & 255u) * kv;
+      acc[1] += static_cast<int>((v >> 8) & 255u) * kv;
+      acc[2] += static_cast<int>((v >> 16) & 255u) * kv;
+      acc[3] += static_cast<int>(v >> 24) * kv;
+    } else {
+      for (int e = 0; e < 4 && wj * 4 + e < row_bytes; ++e) acc[e] += static_cast<int>(p[e]) * kv;
+    }
+  }
+  uint32_t packed = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int a = acc[e] >> 22;
+    a = a < 0 ? 0 : (a > 255 ? 255 : a);
+    packed |= static_cast<uint32_t>(a) << (8 * e);
+  }
+  if (whole) {
+    *reinterpret_cast<uint32_t*>(dst) = packed;
+  } else {
+    for (int e = 0; e < 4 && wj * 4 + e < row_bytes; ++e) dst[e] = static_cast<uint8_t>(packed >> (8 * e));
+  }
+}
+
 // fp32 rows -> split-precision fp16 operand rows [hi | lo | hi] (3*cols wide): x = hi + lo to ~22 bits; a GEMM against
 // weights packed as [W_hi | W_hi | W_lo] then accumulates x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32 on the tensor core
 // (the W_lo x_lo term, 2^-22 relative, is dropped).  Used by the classifier head (ACT/models/gfv_net.py:427-435).
@@ -1219,6 +1316,21 @@ cudaError_t launch_u8hwc_to_f32chw_norm(const uint8_t* in, float* out, int B, in
   dim3 grid((HW + kIngestPix - 1) / kIngestPix, B);
   u8hwc_to_f32chw_norm_kernel<<<grid, kThreads, 0, s>>>(in, out, HW, C, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
                                                         std3[2]);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pil_resize_crop_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int H, int W, int C,
+                                      const int32_t* hbounds, const int32_t* hkk, int hks, int OW,
+                                      const int32_t* vbounds, const int32_t* vkk, int vks, int OH, int row0, int rows,
+                                      cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  if (W * C > kResampleMaxRowBytes || N > 65535) return cudaErrorInvalidValue;
+  pil_resample_h_u8_kernel<<<dim3(rows, N), kThreads, 0, s>>>(in, tmp, hbounds, hkk, hks, H, W, C, rows, OW, row0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int row_bytes = OW * C;
+  const long long total = static_cast<long long>(N) * OH * ((row_bytes + 3) >> 2);
+  pil_resample_v_u8_kernel<<<grid_for(total), kThreads, 0, s>>>(tmp, out, vbounds, vkk, vks, N, rows, row_bytes, OH, row0);
   return cudaGetLastError();
 }
 

@@ -94,5 +94,10 @@ cudaError_t launch_class_ap(const float* probs, const long long* labels, int N, 
 
 cudaError_t launch_fill_f32(float* p, float v, long long n, cudaStream_t s);
 cudaError_t launch_f32_to_f16(const float* in, __half* out, long long n, cudaStream_t s);
+// GroupScale + GroupCenterCrop (+ Stack) on decoded uint8 frames, bit-identical to Pillow's bilinear resize
+cudaError_t launch_pil_resize_crop_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int H, int W, int C,
+                                      const int32_t* hbounds, const int32_t* hkk, int hks, int OW,
+                                      const int32_t* vbounds, const int32_t* vkk, int vks, int OH, int row0, int rows,
+                                      cudaStream_t s);
 
 }  // namespace af

@@ -29,6 +29,7 @@ METRICS = {
     "cfg4": "clips/sec (16-frame, 128^2 patch)",
     "cfg2": "clips/sec (16-frame, 128^2 patch), fL only",
     "cfg5": "videos/sec (Sth-Sth shape, 8+12 frames, 144^2 patch, ResNet-101 fL)",
+    "cfg1": "clips/sec (8-frame 224^2 clip, MobileNet-v2 fG only)",
 }
 WORKLOADS = {
     "cfg3": ("cfg3: full AdaFocus (ACT tree) MobileNet-V2 fG + ResNet-50 fL + GRU policy/classifier, T=16, 224^2 "
@@ -39,6 +40,8 @@ WORKLOADS = {
              "clip (fL kernels only)"),
     "cfg5": ("cfg5: Something-Something shape (STH tree), TSM-MobileNet-V2 fG over 8 frames + continuous policy + "
              "TSM-ResNet-101 fL over 12 patches of 144^2, 174 classes"),
+    "cfg1": ("cfg1: single 8-frame 224^2 synthetic clip, TSM-MobileNet-V2 fG only (STH tree GFV.glance(), the call "
+             "evaluate.py makes at STH/evaluate.py:195), 174 classes"),
 }
 FL_GFLOP_PER_PATCH = 2.669      # ResNet-50 trunk @128^2, 2*MAC
 R101_GFLOP_PER_PATCH_144 = 6.583
@@ -105,10 +108,32 @@ def reference_cpu(workload, steps, warmup, clips_per_step=None, budget_s=150.0, 
     from oracle import reference_runner as rr
     cores, cpu_model = rr.host_info()
     cands = sorted({max(1, min(cores, 64)), max(1, min(cores, 64) // 2)}, reverse=True)
-    tree = "STH" if workload == "cfg5" else "ACT"
+    tree = "STH" if workload in ("cfg5", "cfg1") else "ACT"
     kind = "reference" if rl.available(tree) else "port"
     with torch.no_grad():
-        if workload == "cfg5":
+        if workload == "cfg1":
+            args = synth.sth_args()
+            if kind == "reference":
+                model, _ = rr.build_sth(args)
+                what = "reference STH GFV.glance (STH/models/gfv_net.py:101-112, evaluate.py:188-196)"
+
+                def make(n):
+                    gi = synth.synth_clips(n, args.num_segments_glancer, 224, synth.SEED + 1)
+                    return lambda: model.glance(torch.nn.functional.interpolate(gi, (args.glance_size, args.glance_size)))
+            else:
+                from adafocus_b200.models_sth.gfv_net import GFV
+                from oracle import adafocus_oracle as orc
+                m = GFV(args)
+                synth.strip_fc_sth(m)
+                ck = synth.synth_checkpoint_sth(m)
+                del m
+                what = "oracle.mobilenet_v2_features_flat (TSM) + classifier"
+
+                def make(n):
+                    gi = synth.synth_clips(n, args.num_segments_glancer, 224, synth.SEED + 1)
+                    return lambda: orc.mobilenet_v2_features_flat(gi.view(n * 8, 3, 224, 224), ck["glancer"], "net.features.",
+                                                                  (8, args.shift_div))
+        elif workload == "cfg5":
             args = synth.sth_args(base_model="resnet101", num_segments_focuser=focuser_frames)
             if kind == "reference":
                 model, _ = rr.build_sth(args)
@@ -227,7 +252,7 @@ def torch_gpu_baseline(workload, batch, dev, focuser_frames=12):
     from adafocus_b200 import synth
     from oracle import reference_loader as rl
     from oracle import reference_runner as rr
-    tree = "STH" if workload == "cfg5" else "ACT"
+    tree = "STH" if workload in ("cfg5", "cfg1") else "ACT"
     if not rl.available(tree):
         return {"unavailable": "reference sources are not on this machine (baseline/_ref missing)"}
     out = {"batch": batch, "source": rl.tree_path(tree).replace(ROOT + "/", ""), "torch": torch.__version__,
@@ -236,7 +261,14 @@ def torch_gpu_baseline(workload, batch, dev, focuser_frames=12):
     try:
         torch.backends.cudnn.benchmark = True
         with torch.no_grad():
-            if workload == "cfg5":
+            if workload == "cfg1":
+                args = synth.sth_args(batch_size=batch)
+                model, _ = rr.build_sth(args, dev)
+                gi = synth.synth_clips(batch, args.num_segments_glancer, 224, synth.SEED + 1).to(dev)
+                fn = lambda: model.glance(gi)                                                # noqa: E731
+                fn2 = None
+                out["api"] = "GFV.glance (TSM-MobileNet-V2 features + per-frame logits)"
+            elif workload == "cfg5":
                 args = synth.sth_args(base_model="resnet101", num_segments_focuser=focuser_frames, batch_size=batch)
                 model, _ = rr.build_sth(args, dev)
                 gi = synth.synth_clips(batch, args.num_segments_glancer, 224, synth.SEED + 1).to(dev)
@@ -274,16 +306,24 @@ def torch_gpu_baseline(workload, batch, dev, focuser_frames=12):
             torch.backends.cudnn.allow_tf32 = False
             out["fp32_strict"] = timed(fn)
             torch.backends.cudnn.allow_tf32 = True
-            model.to(memory_format=torch.channels_last)
 
             def amp(f):
                 def g():
                     with torch.autocast("cuda", dtype=torch.float16):
                         return f()
                 return g
-            out["fp16_autocast_channels_last"] = timed(amp(fn))
-            if fn2 is not None:
-                out["fp16_autocast_channels_last_with_baseline"] = timed(amp(fn2))
+            try:
+                model.to(memory_format=torch.channels_last)
+                out["fp16_autocast_channels_last"] = timed(amp(fn))
+                if fn2 is not None:
+                    out["fp16_autocast_channels_last_with_baseline"] = timed(amp(fn2))
+            except RuntimeError as exc:
+                # the STH tree .view()s activations (STH/ops/temporal_shift.py:31): channels_last tensors cannot be viewed
+                out["fp16_autocast_channels_last"] = {"failed": str(exc).splitlines()[0][:160]}
+                model.to(memory_format=torch.contiguous_format)
+                out["fp16_autocast"] = timed(amp(fn))
+                if fn2 is not None:
+                    out["fp16_autocast_with_baseline"] = timed(amp(fn2))
         out["best"] = max(v["value"] for v in out.values() if isinstance(v, dict) and "value" in v)
     except Exception as exc:                       # the baseline is a report, never the product path
         out["failed"] = f"{type(exc).__name__}: {exc}"
@@ -506,7 +546,7 @@ def run_act(a):
                  "api": "adafocus_b200.models.gfv_net.GFV.forward(input=, scan=, one_step=True) -> (logits, last_out)"}
 
     # ---- end to end from pinned host buffers (H2D + compute + D2H inside the timed region)
-    e2e = e2e_u8 = ceiling = None
+    e2e = e2e_u8 = e2e_raw = ceiling = None
 
     def time_e2e(ev, host):
         nb = a.steps
@@ -547,7 +587,15 @@ def run_act(a):
         e2e_u8 = time_e2e(ev8, host8)
         e2e_u8["api"] = ("StreamingEvaluator(input_format='u8_hwc'): uint8 frames over PCIe, af_frames_u8_to_f32 "
                          "(bit-identical to the reference's transform chain) in front of the plan")
-        del host8, ev, ev8
+        # (3) decoded frames at their stored size (340x256, the reference's extracted-JPEG height, ACT/ops/video_jpg.py):
+        #     GroupScale + GroupCenterCrop + Stack + ToTorchFormatTensor + GroupNormalize all on the device (f-2)
+        evr = StreamingEvaluator(model, b, dev, slots=2, input_format="u8_frames", frame_hw=(256, 340))
+        hostr = [torch.randint(0, 256, (b * t, 256, 340, 3), dtype=torch.uint8, generator=gen8).pin_memory()
+                 for _ in range(2)]
+        e2e_raw = time_e2e(evr, hostr)
+        e2e_raw["api"] = ("StreamingEvaluator(input_format='u8_frames'): decoded 340x256 uint8 frames over PCIe, "
+                          "af_resize_crop_u8 (Pillow-exact GroupScale + GroupCenterCrop) + af_frames_u8_to_f32 on the device")
+        del host8, hostr, ev, ev8, evr
 
     if rank != 0:
         h.finish()
@@ -594,7 +642,8 @@ def run_act(a):
         "config": {"workload": WORKLOADS[a.workload], "clips_per_gpu_per_step": b, "global_clips_per_step": b * world,
                    "parallelism": f"dp{world} (clips sharded, weights replicated, one all-gather of (B,200) logits)",
                    "l2": f"per-step input {b * 3 * t * s * s * 4 / 2**20:.0f} MiB/GPU exceeds the 126 MB L2; no flush"},
-        "clocks": clocks, "e2e": e2e, "e2e_u8_frames": e2e_u8, "e2e_h2d_ceiling": ceiling, "value_api": value_api,
+        "clocks": clocks, "e2e": e2e, "e2e_u8_frames": e2e_u8, "e2e_decoded_frames": e2e_raw, "e2e_h2d_ceiling": ceiling,
+        "value_api": value_api,
         "gpu_launches": plan.plan.num_launches * a.steps,
         "roofline": roofline, "stages_ms": stage_acc, "first_forward_s": first_forward_s,
         "crop_roofline": {"bound": "hbm", "achieved": crop_bytes / (crop_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -859,10 +908,70 @@ def run_cfg5(a):
     h.finish()
 
 
+def run_cfg1(a):
+    """BASELINE config 1: one 8-frame 224^2 clip, fG only -- the reference's own CPU-runnable plumbing case; here the
+    same call (STH GFV.glance) on the GPU at batch 1 (latency) with the reference's CPU and GPU paths beside it."""
+    h = Harness(a)
+    torch, dev = h.torch, h.dev
+    from adafocus_b200 import synth
+    from adafocus_b200.models_sth.gfv_net import GFV
+    b = a.batch or 1
+    args = synth.sth_args(batch_size=b)
+    model = GFV(args).to(dev)
+    synth.strip_fc_sth(model)
+    synth.load_checkpoint_sth(model, synth.synth_checkpoint_sth(model))
+    model.eval()
+    gi = synth.synth_clips(b, args.num_segments_glancer, 224, synth.SEED + 1).to(dev)
+    host = gi.cpu().pin_memory()
+    out_host = torch.empty(b, args.num_segments_glancer, args.num_classes).pin_memory()
+    launches0 = None
+    from adafocus_b200.engine import get_engine
+    eng = get_engine(dev)
+
+    def step():
+        return model.glance(gi)
+    step()
+    launches0 = eng.launch_count
+    step()
+    per_step = eng.launch_count - launches0
+    sampler = ClockSampler(h.local)
+    sampler.start()
+    ms = h.timed(step, sampler) / a.steps
+    clocks = sampler.stop()
+
+    def step_e2e():
+        gi.copy_(host, non_blocking=True)
+        fmap, logit = model.glance(gi)
+        out_host.copy_(logit, non_blocking=True)
+    ems = h.timed(step_e2e) / a.steps
+    line = {
+        "metric": METRICS["cfg1"], "value": b / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+        "warmup": h.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOADS["cfg1"], "clips_per_step": b, "l2": "latency case: the working set fits the L2"},
+        "clocks": clocks, "gpu_launches": per_step * a.steps,
+        "e2e": {"value": b / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ems,
+                "api": "pinned clip -> GFV.glance (adafocus_b200.models_sth) -> pinned per-frame logits"},
+    }
+    if not a.no_torch_gpu_baseline:
+        line["torch_gpu_baseline"] = torch_gpu_baseline("cfg1", b, dev)
+    if not a.no_cpu_baseline:
+        try:
+            _, info = reference_cpu("cfg1", 5, 2, clips_per_step=b, budget_s=25.0)
+            line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    h.finish()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "cfg1":
+        run_cfg1(a)
     elif a.workload == "cfg5":
         run_cfg5(a)
     elif a.workload == "cfg2":

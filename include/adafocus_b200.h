@@ -262,6 +262,20 @@ int af_f32_to_f16(af_ctx* ctx, const float* in, void* out, int64_t n, void* stre
 int af_frames_u8_to_f32(af_ctx* ctx, const uint8_t* in, float* out, int B, int HW, int C, const float* mean3,
                         const float* std3, void* stream);
 
+/* GroupScale -> GroupCenterCrop (-> Stack) of the reference's validation transform (ACT/ops/transforms.py:78-93, 37-43,
+ * 303-316; ACT/main_dist.py:213-217) on decoded uint8 frames, on the device and bit-identical to Pillow's
+ * Image.resize(BILINEAR) behind torchvision.transforms.Resize: two integer passes (horizontal into `tmp`, then
+ * vertical) with the window bounds and 22-bit fixed-point weights Pillow's precompute_coeffs / normalize_coeffs_8bpc
+ * produce -- the caller computes them on the host (adafocus_b200.preprocess.resize_tables) for the OW columns / OH rows
+ * the centre crop keeps.
+ *   in   (N, H, W, C) uint8 frames (W * C <= 12288);  tmp (N, rows, OW, C) scratch for source rows [row0, row0 + rows);
+ *   out  (N, OH, OW, C) uint8.  af_frames_u8_to_f32 over these N frames (B = N, C channels) then writes (N, C, OH*OW)
+ *        fp32, which is the (clips, T*C, OH, OW) tensor Stack() + ToTorchFormatTensor produce for T frames per clip.
+ *   hbounds / vbounds int32 [OW|OH][2] = (first source index, taps), hkk / vkk int32 [OW|OH][hks|vks]: DEVICE pointers. */
+int af_resize_crop_u8(af_ctx* ctx, const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int H, int W, int C,
+                      const int32_t* hbounds, const int32_t* hkk, int hks, int OW, const int32_t* vbounds,
+                      const int32_t* vkk, int vks, int OH, int row0, int rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from adafocus_b200.models.gfv_net import GFV
 from oracle import adafocus_oracle as orc
 
 torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _ck(args):
@@ -128,3 +129,63 @@ def test_metrics_restatement_matches_reference(golden_dir):
     np.testing.assert_allclose(ap1, gold["ap_single"], rtol=1e-4, atol=2e-2)
     np.testing.assert_allclose(ap2, gold["ap_multi"], rtol=1e-4, atol=2e-2)
     assert abs(m1 - float(gold["map_single"])) < 5e-3 and abs(m2 - float(gold["map_multi"])) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ decoded-frame transforms
+def _transform_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_transforms",
+                                                  os.path.join(GOLDEN, "make_golden_transforms.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_pil_transform_oracle_vs_reference_golden():
+    """oracle/pil_transforms.py (integer restatement of Pillow's bilinear resampler + torchvision's size / crop rules +
+    the Stack / ToTorchFormatTensor / GroupNormalize chain) against the outputs of the reference's own transform
+    classes (tests/golden/transforms.npz): bit-exact, uint8 frames and fp32 tensors."""
+    import hashlib
+    from oracle import pil_transforms as pt
+    mod = _transform_cases()
+    gold = np.load(os.path.join(GOLDEN, "transforms.npz"))
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    for tag, n, h, w, scale, crop in mod.CASES:
+        frames = mod.synthetic_frames(tag, n, h, w)
+        u8 = pt.group_scale_center_crop(frames, scale, crop)
+        assert tuple(u8.shape) == tuple(gold[f"{tag}_shape"])
+        assert hashlib.sha256(u8.tobytes()).digest() == gold[f"{tag}_sha256"].tobytes(), tag
+        if f"{tag}_u8" in gold:
+            assert np.array_equal(u8[:1], gold[f"{tag}_u8"])
+        x = pt.stack_to_tensor_normalize(u8, mean, std)
+        assert hashlib.sha256(x.tobytes()).digest() == gold[f"{tag}_tensor_sha256"].tobytes(), tag
+
+
+def test_pil_transform_oracle_vs_pillow_when_available():
+    pil = pytest.importorskip("PIL.Image")
+    tvt = pytest.importorskip("torchvision.transforms")
+    from oracle import pil_transforms as pt
+    rng = np.random.default_rng(3)
+    for h, w, scale, crop in [(255, 341, 256, 224), (100, 60, 48, 40), (64, 64, 64, 64), (90, 200, 77, 70)]:
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(tvt.CenterCrop(crop)(tvt.Resize(scale, pil.BILINEAR)(pil.fromarray(a))))
+        assert np.array_equal(pt.group_scale_center_crop([a], scale, crop)[0], ref)
+
+
+def test_host_resize_tables_match_the_oracle_coefficients():
+    """adafocus_b200.preprocess.resize_tables (product, host side) == the oracle's coefficient tables restricted to the
+    centre crop; the scratch row window covers every vertical tap."""
+    from adafocus_b200 import preprocess as pp
+    from oracle import pil_transforms as pt
+    for h, w, scale, crop in [(256, 340, 256, 224), (320, 240, 256, 224), (224, 224, 256, 224), (97, 131, 64, 56)]:
+        t = pp.resize_tables(h, w, scale, crop)
+        oh, ow = pt.resized_output_size(h, w, scale)
+        assert (t["oh"], t["ow"]) == (oh, ow)
+        y0, x0 = pt.center_crop_origin(oh, ow, crop, crop)
+        assert (t["y0"], t["x0"]) == (y0, x0)
+        hb, hk = pt.bilinear_coeffs(w, ow)
+        vb, vk = pt.bilinear_coeffs(h, oh)
+        assert np.array_equal(t["hb"], hb[x0:x0 + crop]) and np.array_equal(t["hk"], hk[x0:x0 + crop])
+        assert np.array_equal(t["vb"], vb[y0:y0 + crop]) and np.array_equal(t["vk"], vk[y0:y0 + crop])
+        assert t["row0"] <= int(t["vb"][:, 0].min()) and t["row0"] + t["rows"] >= int((t["vb"][:, 0] + t["vb"][:, 1]).max())
+        assert t["row0"] >= 0 and t["row0"] + t["rows"] <= h
