@@ -70,7 +70,6 @@ SIGNATURES = {
     "af_conv2d_nhwc_f16": (c_int, [c_void_p, POINTER(ConvDesc), c_void_p]),
     "af_conv_tsm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
-    "af_mbconv_fused_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32)]),
     "af_mbconv_fused": (c_int, [c_void_p, POINTER(MbconvDesc), c_void_p]),
     "af_dwconv3x3_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),

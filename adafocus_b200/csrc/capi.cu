@@ -14,7 +14,6 @@
 #include "dwconv_tma.cuh"
 #include "kernels.cuh"
 #include "mbconv_fused.cuh"
-#include "mbconv_tc.cuh"
 #include "stem_gemm.cuh"
 
 namespace {
@@ -526,15 +525,6 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
 
 namespace {
 
-// The default is the second-generation kernel (depthwise on the FMA pipes, mbconv_fused.cu).  AF_MBCONV_V3=1 selects
-// the variant with the depthwise on the tensor core (mbconv_tc.cu): correct, but measured 3x slower -- every
-// tcgen05.mma of M=128, K=16 costs ~55 cycles whatever its N (tools/probe/umma_rate_probe.cu), and a depthwise chunk
-// needs 36 of them (profiles/README.md).
-bool use_mb3() {
-  static const bool v = getenv("AF_MBCONV_V3") != nullptr;
-  return v;
-}
-
 bool encode_mb_maps(af_ctx* ctx, const af_mbconv_desc* d, int BW, int BH, int TW, int TH, int Ho, int Wo, int nc,
                     int cout_pad, af::MbTensorMaps* maps, std::string* err) {
   {
@@ -572,27 +562,10 @@ bool encode_mb_maps(af_ctx* ctx, const af_mbconv_desc* d, int BW, int BH, int TW
 }  // namespace
 
 int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride) {
-  if (use_mb3()) {
-    af::Mb3Params q;
-    memset(&q, 0, sizeof(q));
-    q.N = n; q.H = h; q.W = w; q.Cin = cin; q.Cexp = cexp; q.Cout = cout; q.S = stride;
-    if (af::mbconv3_plan(&q)) return 1;
-  }
   af::MbParams p;
   memset(&p, 0, sizeof(p));
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cexp = cexp; p.Cout = cout; p.S = stride;
   return af::mbconv_plan(&p) ? 1 : 0;
-}
-
-int af_mbconv_fused_plan(int n, int h, int w, int cin, int cexp, int cout, int stride, int32_t* info) {
-  if (info == nullptr) return AF_ERR_INVALID;
-  af::Mb3Params q;
-  memset(&q, 0, sizeof(q));
-  q.N = n; q.H = h; q.W = w; q.Cin = cin; q.Cexp = cexp; q.Cout = cout; q.S = stride;
-  if (!use_mb3() || !af::mbconv3_plan(&q)) return 1;
-  const int32_t v[12] = {q.TW, q.TH, q.BW, q.BH, q.Mtiles, q.e_rows, q.XB, q.EB, q.AB, q.WB, q.nA, q.smem};
-  for (int i = 0; i < 12; ++i) info[i] = v[i];
-  return 0;
 }
 
 int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
@@ -606,20 +579,6 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
   memset(&maps, 0, sizeof(maps));
   std::string err;
   const int sms = ctx->sm_count;
-  if (use_mb3()) {
-    af::Mb3Params q;
-    memset(&q, 0, sizeof(q));
-    q.N = d->n; q.H = d->h; q.W = d->w_; q.Cin = d->cin; q.Cexp = d->cexp; q.Cout = d->cout; q.S = d->stride;
-    if (af::mbconv3_plan(&q)) {
-      q.bias1 = d->bias1; q.dw_w = d->dw_w; q.bias2 = d->bias2; q.bias3 = d->bias3;
-      q.residual = static_cast<const __half*>(d->residual);
-      q.res_stride = d->res_stride;
-      if (!encode_mb_maps(ctx, d, q.BW, q.BH, q.TW, q.TH, q.Ho, q.Wo, q.nc, q.cout_pad, &maps, &err))
-        return fail(AF_ERR_CUDA, err);
-      return dispatch(ctx, stream, "af_mbconv_fused",
-                      [=](cudaStream_t s) { return af::launch_mbconv3(maps, q, sms, s); });
-    }
-  }
   af::MbParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;

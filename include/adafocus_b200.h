@@ -168,9 +168,6 @@ typedef struct af_mbconv_desc {
 } af_mbconv_desc;
 int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream);
-/* Tiling the fused kernel would use for a shape (diagnostics / tests): info[12] = {TW, TH, BW, BH, Mtiles, e_rows, XB,
- * EB, AB, WB, nA, smem bytes}.  Returns 0 when the tensor-core-depthwise kernel handles the shape, 1 otherwise. */
-int af_mbconv_fused_plan(int n, int h, int w, int cin, int cexp, int cout, int stride, int32_t* info);
 
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
