@@ -54,6 +54,10 @@ SIGNATURES = {
     "af_plan_run": (c_int, [c_void_p, c_void_p]),
     "af_plan_num_launches": (c_int, [c_void_p]),
     "af_plan_destroy": (c_int, [c_void_p]),
+    "af_plan_bind_forward": (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p, ctypes.c_size_t, c_void_p, c_int, c_int,
+                                     c_int, c_int, ctypes.c_size_t]),
+    "af_workspace_bytes": (ctypes.c_size_t, [c_void_p]),
+    "af_gfv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "af_plan_mark": (c_int, [c_void_p, POINTER(c_int)]),
     "af_plan_mark_elapsed_ms": (c_int, [c_void_p, c_int, c_int, POINTER(c_float)]),
     "af_crop_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -43,6 +43,13 @@ struct af_plan {
   std::vector<char> is_mark;       // launches[i] is a timing-mark event record (skipped under stream capture)
   std::vector<cudaEvent_t> marks;
   int kernel_launches = 0;
+  // forward I/O of a whole-path plan (af_plan_bind_forward): the static buffers the recorded launches read / write
+  void* in_buf = nullptr;
+  void* scan_buf = nullptr;
+  size_t in_bytes = 0, scan_bytes = 0;
+  const float* logits_buf = nullptr;
+  int rows = 0, row_stride = 0, classes = 0, steps = 0;
+  size_t workspace_bytes = 0;
   ~af_plan() {
     for (cudaEvent_t e : marks) cudaEventDestroy(e);
   }
@@ -263,6 +270,55 @@ int af_plan_mark_elapsed_ms(af_plan* plan, int mark_a, int mark_b, float* ms) {
 
 int af_plan_destroy(af_plan* plan) {
   delete plan;
+  return AF_OK;
+}
+
+int af_plan_bind_forward(af_plan* plan, void* input_buf, size_t input_bytes, void* scan_buf, size_t scan_bytes,
+                         const float* logits_buf, int rows, int row_stride, int classes, int steps,
+                         size_t workspace_bytes) {
+  if (plan == nullptr || input_buf == nullptr || logits_buf == nullptr || rows < 1 || classes < 1 ||
+      row_stride < classes || steps < 1 || rows % steps != 0)
+    return fail(AF_ERR_INVALID, "af_plan_bind_forward: bad argument");
+  plan->in_buf = input_buf;
+  plan->in_bytes = input_bytes;
+  plan->scan_buf = scan_buf;
+  plan->scan_bytes = scan_buf ? scan_bytes : 0;
+  plan->logits_buf = logits_buf;
+  plan->rows = rows;
+  plan->row_stride = row_stride;
+  plan->classes = classes;
+  plan->steps = steps;
+  plan->workspace_bytes = workspace_bytes;
+  return AF_OK;
+}
+
+size_t af_workspace_bytes(const af_plan* plan) { return plan ? plan->workspace_bytes : 0; }
+
+int af_gfv_forward(af_plan* plan, const float* input, const float* scan, float* logits, float* last_out, void* stream) {
+  if (plan == nullptr || plan->in_buf == nullptr)
+    return fail(AF_ERR_STATE, "af_gfv_forward: the plan has no forward binding (af_plan_bind_forward)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DeviceGuard guard(plan->device);
+  cudaError_t e = cudaSuccess;
+  if (input != nullptr && input != plan->in_buf)
+    e = cudaMemcpyAsync(plan->in_buf, input, plan->in_bytes, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return fail_cuda(e, "af_gfv_forward: input copy");
+  if (plan->scan_buf != nullptr && scan != nullptr && scan != plan->scan_buf)
+    e = cudaMemcpyAsync(plan->scan_buf, scan, plan->scan_bytes, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return fail_cuda(e, "af_gfv_forward: scan copy");
+  const int rc = af_plan_run(plan, stream);
+  if (rc != AF_OK) return rc;
+  const size_t w = static_cast<size_t>(plan->classes) * sizeof(float);
+  const size_t pitch = static_cast<size_t>(plan->row_stride) * sizeof(float);
+  if (logits != nullptr) {     // (B*T, C) contiguous, ACT/models/gfv_net.py:433
+    e = cudaMemcpy2DAsync(logits, w, plan->logits_buf, pitch, w, plan->rows, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return fail_cuda(e, "af_gfv_forward: logits copy");
+  }
+  if (last_out != nullptr) {   // logits of the last step of every clip, :434
+    const float* src = plan->logits_buf + static_cast<size_t>(plan->steps - 1) * plan->row_stride;
+    e = cudaMemcpy2DAsync(last_out, w, src, pitch * plan->steps, w, plan->rows / plan->steps, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return fail_cuda(e, "af_gfv_forward: last_out copy");
+  }
   return AF_OK;
 }
 

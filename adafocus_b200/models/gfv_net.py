@@ -17,6 +17,7 @@ import math
 import torch
 from torch import nn
 
+from .. import _lib
 from ..engine import get_engine, pack_conv_split
 from ..packcache import cached_runner
 from .mobilenet import _param_key, invalidate_packed, mobilenet_v2
@@ -278,6 +279,12 @@ class _FusedPlan:
             self.marks = {"fG": (m0, m1), "policy": (m1, m2), "fL": (m2, m3), "head": (m3, m4), "total": (m0, m4)}
         finally:
             self.plan = eng.end_plan()
+        # name the plan's I/O so that the whole forward is ONE C-ABI call (af_gfv_forward)
+        _lib.check(self.plan.lib.af_plan_bind_forward(
+            self.plan.handle, self.input.data_ptr(), self.input.numel() * 4,
+            None if share_scan else self.scan.data_ptr(), 0 if share_scan else self.scan.numel() * 4,
+            self.logits.data_ptr(), b * t, clf.logit_stride, clf.num_classes, t, self.plan.workspace_bytes),
+            "af_plan_bind_forward")
         self.keys = (_param_key(model.glancer.net), _param_key(model.focuser.net),
                      _param_key(model.focuser.policy.policy_old), _param_key(model.classifier))
 
@@ -286,6 +293,17 @@ class _FusedPlan:
             self.graph.replay()
             return
         self.plan.run(torch.cuda.current_stream(self.input.device).cuda_stream)
+
+    def forward(self, inp, scan, logits, last_out):
+        """The whole stage-3 forward as ONE C-ABI call (af_gfv_forward): device-to-device copies of the caller's
+        tensors into the plan's static buffers (skipped when they already are those buffers), the recorded launch
+        sequence, and contiguous (B*T, C) / (B, C) outputs."""
+        from ctypes import c_void_p
+        stream = torch.cuda.current_stream(self.input.device).cuda_stream
+        _lib.check(self.plan.lib.af_gfv_forward(self.plan.handle, c_void_p(inp.data_ptr()),
+                                                c_void_p(scan.data_ptr()) if scan is not None else None,
+                                                c_void_p(logits.data_ptr()), c_void_p(last_out.data_ptr()),
+                                                c_void_p(stream)), "af_gfv_forward")
 
     def capture_graph(self):
         """Capture one replay of the plan into a CUDA graph (small batches are launch-bound: ~170 launches of a few
@@ -418,14 +436,19 @@ class GFV(nn.Module):
         g = scan.shape[-1]
         share = scan.data_ptr() == inp.data_ptr() and scan.shape == inp.shape
         plan = self.fused_plan(b, t, h, w, g, inp.device, share)
-        if inp.data_ptr() != plan.input.data_ptr():
-            plan.input.copy_(inp)
-        if not share and scan.data_ptr() != plan.scan.data_ptr():
-            plan.scan.copy_(scan)
-        plan.run()
+        if plan.graph is not None or not inp.is_contiguous() or not scan.is_contiguous() or inp.dtype != torch.float32:
+            if inp.data_ptr() != plan.input.data_ptr():
+                plan.input.copy_(inp)
+            if not share and scan.data_ptr() != plan.scan.data_ptr():
+                plan.scan.copy_(scan)
+            plan.run()
+            logits = plan.logits[:, : plan.num_classes].contiguous()
+            last_out = logits.reshape(b, t, -1)[:, -1, :].reshape(b, -1)
+        else:
+            logits = torch.empty(b * t, plan.num_classes, dtype=torch.float32, device=inp.device)
+            last_out = torch.empty(b, plan.num_classes, dtype=torch.float32, device=inp.device)
+            plan.forward(inp, None if share else scan, logits, last_out)      # one C-ABI call: af_gfv_forward
         self.last_plan = plan
-        logits = plan.logits[:, : plan.num_classes].contiguous()
-        last_out = logits.reshape(b, t, -1)[:, -1, :].reshape(b, -1)
         return logits, last_out
 
     # ------------------------------------------------------------------ reference-style pieces

@@ -100,6 +100,20 @@ int af_plan_mark(af_ctx* ctx, int* mark_index);
 int af_plan_mark_elapsed_ms(af_plan* plan, int mark_a, int mark_b, float* ms);
 int af_plan_destroy(af_plan* plan);
 
+/* Whole-path forward through the C ABI (SURVEY.md section 8(b) af_gfv_forward / af_workspace_bytes).  The layer schedule
+ * and the weight packing are host logic of the Python shim (north_star: "host code stays Python/PyTorch calling ...
+ * through a thin C-ABI extension"); once the shim has recorded a plan for a batch size, the plan IS the native forward
+ * of GFV.forward(one_step=True) (ACT/models/gfv_net.py:95-133): af_plan_bind_forward names the plan's static input /
+ * scan buffers and its padded logits buffer (rows = B*T of row_stride floats, `classes` valid, `steps` = T), and
+ * af_gfv_forward copies caller tensors in (device pointers; NULL or the bound buffer itself = already in place),
+ * replays the ~170 launches on `stream`, and writes logits (B*T, C) and / or last_out (B, C) contiguously.
+ * No host synchronisation, CUDA-graph capturable, no allocation. */
+int af_plan_bind_forward(af_plan* plan, void* input_buf, size_t input_bytes, void* scan_buf, size_t scan_bytes,
+                         const float* logits_buf, int rows, int row_stride, int classes, int steps,
+                         size_t workspace_bytes);
+size_t af_workspace_bytes(const af_plan* plan);
+int af_gfv_forward(af_plan* plan, const float* input, const float* scan, float* logits, float* last_out, void* stream);
+
 /* get_patch(images, action_sequence, patch_size) -- ACT/models/utils.py:37-51 (= STH/models/utils.py:44-58).
  * img (N,C,H,W) fp32 NCHW -> out (N,C,P,P) fp32.  Exactly one of action (N,2 fp32 in [0,1], coordinates computed
  * as floor(a*(H-P)) in fp32 like the reference) and yx (N,2 int32) is non-NULL.  yx_out (N,2 int32) optional. */

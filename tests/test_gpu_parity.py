@@ -330,3 +330,27 @@ def test_train_mode_is_rejected(c3):
             model(input=xd, scan=xd, training=False, backbone_pred=False, one_step=True, gpu=0)
     finally:
         model.eval()
+
+
+def test_c_abi_whole_forward_entry_point(c3):
+    """af_gfv_forward: the recorded plan as the native GFV.forward(one_step=True) -- caller tensors in, contiguous
+    (B*T, C) logits and (B, C) last_out out, in one C call; NULL outputs are skipped; af_workspace_bytes reports the
+    plan's arena."""
+    from ctypes import c_void_p
+    model, args, xd = c3["model"], c3["args"], c3["xd"]
+    b, t, c = 2, args.num_segments, args.num_classes
+    plan = model.fused_plan(b, t, args.input_size, args.input_size, model.glance_size, DEV, True, slot=5)
+    lib, h = plan.plan.lib, plan.plan.handle
+    assert lib.af_workspace_bytes(h) == plan.plan.workspace_bytes > 0
+    stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+    x2 = xd.clone()                                   # a caller-owned tensor, not the plan's static buffer
+    logits = torch.full((b * t, c), -7.0, device=DEV)
+    last = torch.full((b, c), -7.0, device=DEV)
+    assert lib.af_gfv_forward(h, c_void_p(x2.data_ptr()), None, c_void_p(logits.data_ptr()), c_void_p(last.data_ptr()),
+                              stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(logits, c3["logits"]) and torch.equal(last, c3["last"])
+    last2 = torch.zeros_like(last)
+    assert lib.af_gfv_forward(h, None, None, None, c_void_p(last2.data_ptr()), stream) == 0     # input already in place
+    torch.cuda.synchronize()
+    assert torch.equal(last2, c3["last"])
