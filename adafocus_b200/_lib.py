@@ -29,6 +29,7 @@ class ConvDesc(ctypes.Structure):
         ("in_stride", c_int64), ("out_stride", c_int64), ("res_stride", c_int64),
         ("in_row_stride", c_int64), ("in_img_stride", c_int64),
         ("tsm_t", c_int32), ("tsm_fold", c_int32),
+        ("pool", c_int32), ("reserved0", c_int32),
     ]
 
 

@@ -484,6 +484,21 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
       }
     }
   }
+  if (d->pool) {
+    // stem mode: MaxPool2d(3, 2, 1) in the epilogue -- tiles are two full output rows of one image
+    const int nb = ceil_div(d->cout, d->block_n), cb = ceil_div(d->cin, af::kConvBlockK);
+    if (d->stride != 1 || d->kh < 2 || p.Wo * 2 != af::kConvBlockM || (p.Ho & 1) || d->cout > 64 || d->cout % 8 != 0 ||
+        d->out_f32 || d->residual != nullptr || d->act == AF_ACT_NONE || tsm ||
+        !af::conv_gemm_wres_ok(nb, d->block_n, d->kh, d->kw, cb, 0))
+      return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: pool needs a stride-1 multi-row filter with resident weights, "
+                                  "a 64-pixel-wide even-height output, cout <= 64 and a ReLU-type activation");
+    p.pool = 1;
+    p.pair = 0;
+    p.vhalo = 1;
+    p.TW = p.Wo;
+    p.TH = 2;
+    p.TN = 1;
+  }
   p.tiles_w = ceil_div(p.Wo, p.TW);
   p.tiles_h = ceil_div(p.Ho, p.TH);
   p.tiles_n = ceil_div(p.N, p.TN);
@@ -562,7 +577,17 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
     if (p.tma_store && d->scale == nullptr) p.res_mma = 1;
     else p.tma_store = 0;
   }
-  if (p.tma_store) {
+  if (p.pool) {
+    // `out` is the POOLED tensor (N, Ho/2, Wo/2, cout); one pooled row of one image per TMA store
+    if (!p.tma_store) return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: pool needs the TMA-store epilogue");
+    const cuuint64_t opix_b = static_cast<cuuint64_t>(d->out_stride) * 2;
+    const cuuint64_t wp = static_cast<cuuint64_t>(p.Wo / 2), hp = static_cast<cuuint64_t>(p.Ho / 2);
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), wp, hp, static_cast<cuuint64_t>(p.N)};
+    const cuuint64_t strides[3] = {opix_b, opix_b * wp, opix_b * wp * hp};
+    const cuuint32_t pbox[4] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(wp), 1, 1};
+    if (!encode_map(ctx, &maps.pool, d->out, 4, dims, strides, pbox, &err)) return fail(AF_ERR_CUDA, err);
+    maps.out = maps.pool;   // (only prefetched in this mode)
+  } else if (p.tma_store) {
     const cuuint64_t opix_b = static_cast<cuuint64_t>(d->out_stride) * 2;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
                                 static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(p.N)};

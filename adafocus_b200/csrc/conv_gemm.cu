@@ -98,6 +98,7 @@ __device__ __forceinline__ void epilogue_half_slice_act(int act, const uint32_t 
 // Tile index -> (n-block, tile column, tile row, image group) as a mixed-radix counter advanced by a fixed step: the
 // persistent loops move by gridDim.x (or 2 * gridDim.x) tiles per iteration, and decoding every tile with four
 // integer divisions costs the single-thread roles ~1k cycles per tile -- more than a one-k-block tile's MMAs.
+template <bool POOL = false>
 struct TileCursor {
   int nb, tw, th, tn;
   int d_nb, d_tw, d_th, d_tn;
@@ -116,6 +117,14 @@ struct TileCursor {
     d_tn = r / p.tiles_h;
   }
   __device__ __forceinline__ void advance(const ConvKernelParams& p) {
+    if constexpr (POOL) {
+      // pool mode: a wrap of the tile-row digit moves on by a whole grid of images
+      if (++th == p.tiles_h) {
+        th = 0;
+        tn += d_tn;
+      }
+      return;
+    }
     nb += d_nb;
     int c = nb >= p.n_blocks ? 1 : 0;
     nb -= c ? p.n_blocks : 0;
@@ -127,6 +136,14 @@ struct TileCursor {
     th -= c ? p.tiles_h : 0;
     tn += d_tn + c;
   }
+  // pool mode (ConvKernelParams::pool): CTA `cta` of `ncta` walks the row-pair tiles of images cta, cta + ncta, ..
+  // top to bottom, so that the epilogue can pool across consecutive tiles of an image
+  __device__ __forceinline__ void init_pool(int cta, int ncta) {
+    nb = tw = th = 0;
+    tn = cta;
+    d_nb = d_tw = d_th = 0;
+    d_tn = ncta;
+  }
 };
 
 // PAIR: the kernel runs as clusters of two CTAs (cta_group::2, see ptx.cuh): the pair shares every weight tile (each
@@ -136,7 +153,8 @@ struct TileCursor {
 // image groups 2*tn and 2*tn + 1 of the same (n-block, tile row, tile column).
 // TSM: temporal shift folded into the loads (ConvKernelParams::tsm_T); a template parameter so that the ordinary
 // kernels' single-thread roles carry no trace of it.
-template <bool VHALO, bool PAIR, bool TSM>
+// POOL: stem mode (ConvKernelParams::pool), only with VHALO; a template parameter for the same reason as TSM.
+template <bool VHALO, bool PAIR, bool TSM, bool POOL = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -172,6 +190,19 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
   const int total_tiles = m_tiles * p.n_blocks;
   const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // first tile of this CTA (pair)
   const int tstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // tiles this CTA (pair) goes through; pool mode: whole images, tiles_h row-pair tiles each (evaluated inside the two
+  // single-thread roles only: the epilogue warps are the register-critical path)
+  auto count_iters = [&]() -> int {
+    return POOL ? (static_cast<int>(blockIdx.x) < p.N
+                       ? (p.N - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                             static_cast<int>(gridDim.x) * p.tiles_h
+                       : 0)
+                : (tile0 < total_tiles ? (total_tiles - tile0 + tstep - 1) / tstep : 0);
+  };
+  auto cursor_init = [&](TileCursor<POOL>& c) {
+    if constexpr (POOL) c.init_pool(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+    else c.init(tile0, tstep, p);
+  };
   const int num_kb = p.KH * p.KW * p.cblks;
 
   if (threadIdx.x == 0) {
@@ -197,6 +228,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     if (p.res_mma) tma_prefetch_desc(&maps.res);
     if (VHALO) tma_prefetch_desc(&maps.ah);
     if (TSM) tma_prefetch_desc(&maps.a5);
+    if (POOL) tma_prefetch_desc(&maps.pool);
     if (p.stride == 2) {
       tma_prefetch_desc(&maps.a[1]);
       tma_prefetch_desc(&maps.a[2]);
@@ -280,9 +312,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         for (int kb = 0; kb < num_kb; ++kb)
           load2(wres + static_cast<size_t>(kb) * stage_b_bytes, &maps.b, -1, kb * kConvBlockK, brow);
       }
-      TileCursor cur;
-      cur.init(tile0, tstep, p);
-      for (int tile = tile0; tile < total_tiles; tile += tstep, cur.advance(p)) {
+      TileCursor<POOL> cur;
+      cursor_init(cur);
+      const int n_iter = count_iters();
+      for (int pit = 0; pit < n_iter; ++pit, cur.advance(p)) {
         const int nb = cur.nb;
         const int tn_eff = PAIR ? cur.tn * 2 + static_cast<int>(rank) : cur.tn;
         const int ow0 = cur.tw * p.TW, oh0 = cur.th * p.TH, n0 = tn_eff * p.TN;
@@ -380,7 +413,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
         else umma_commit_elect(bar);
       };
       const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * kConvBlockM : kConvBlockM, static_cast<uint32_t>(p.BN));
-      const bool alternate_tiles = p.tma_store && p.BN <= 64 && !(VHALO && p.epi_groups == 2);
+      const bool alternate_tiles = p.tma_store && p.BN <= 64 && !(VHALO && (p.epi_groups == 2 || POOL));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -389,10 +422,11 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem)), a_step = static_cast<uint32_t>(stage_bytes) >> 4;
       const uint32_t w_lo0 = smem_desc_lo(smem_u32(wres)), b_step = static_cast<uint32_t>(stage_b_bytes) >> 4;
       if (p.wres) mbar_wait_backoff(&ctrl->wfull, 0);
+      const int n_iter = count_iters();
       int mma_nb = tile0 % p.n_blocks;
       const int mma_dnb = tstep % p.n_blocks;
-      for (int tile = tile0; tile < total_tiles;
-           tile += tstep, ++it, mma_nb = mma_nb + mma_dnb >= p.n_blocks ? mma_nb + mma_dnb - p.n_blocks : mma_nb + mma_dnb) {
+      for (; it < n_iter;
+           ++it, mma_nb = mma_nb + mma_dnb >= p.n_blocks ? mma_nb + mma_dnb - p.n_blocks : mma_nb + mma_dnb) {
         // accumulator of this tile: two 256-column stages, or -- single-slice tiles handled by four alternating
         // epilogue groups -- four 128-column ones, so that four tiles are in flight between the MMA and the epilogue
         const int as = it & 1;
@@ -517,7 +551,105 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     const bool alternate_tiles = p.tma_store && nslices == 1 && !solo;
     const int sl_first = (alternate_tiles || solo) ? 0 : sub, sl_step = (alternate_tiles || solo) ? 1 : 2;
     pdl_wait_prior_grid();
-    TileCursor cur;
+    if constexpr (POOL) {
+      // ---- stem mode: conv + BN + ReLU + MaxPool2d(3, stride 2, padding 1) (ACT/models/resnet.py:138-142, 213-216).
+      // A tile is two full output rows (TW == Wo, TH == 2) and the CTA walks an image top to bottom, so pooled row t =
+      // max over conv rows 2t-1 (second row of the previous tile), 2t, 2t+1 and columns 2x-1 .. 2x+1; the conv output
+      // itself never leaves the SM.  Values are post-ReLU (>= 0): the padding of the pool is "max with 0".
+      // The epilogue groups form a pipeline over a ring of three conv staging buffers: group 0 drains the accumulator of
+      // tile t into buffer t % 3, groups 1 and 2 (256 threads, one pooled 16-byte chunk each) pool tile t from buffers
+      // t % 3 and (t-1) % 3 and store the pooled row.
+      constexpr uint32_t kBarFull = 5, kBarFree = 8;      // named barriers 5..7 (staged), 8..10 (buffer may be rewritten)
+      constexpr uint32_t kBarPool = 11;                    // the two pooling groups among themselves
+      constexpr uint32_t kPoolThreads = 2 * kEpilogueThreads, kPipeThreads = 3 * kEpilogueThreads;
+      uint8_t* pool_st = staging_base + 3 * kConvStagingBytes;
+      if (group == 0) {
+        for (int i = et; i < kConvMaxBlockN; i += kEpilogueThreads) {
+          const bool in = i < p.BN;
+          g_scale[i] = (in && p.scale != nullptr) ? __ldg(p.scale + i) : (in ? 1.f : 0.f);
+          g_bias[i] = in ? __ldg(p.bias + i) : 0.f;
+        }
+        named_barrier_sync(bar_id, kEpilogueThreads);
+        int it = 0, b3 = 0;
+        for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+          for (int t = 0; t < p.tiles_h; ++t, ++it) {
+            const int as_t = it & 1;
+            uint8_t* cur_st = staging_base + b3 * kConvStagingBytes;
+            mbar_wait_backoff(&ctrl->tmem_full[as_t], (it >> 1) & 1, p.epi_backoff_ns);
+            tc_fence_after();
+            // buffer b3 was the "previous tile" operand of the pooling of tile it-2: wait until group 1 is done with it
+            if (it >= 3) asm volatile("bar.sync %0, %1;" ::"r"(kBarFree + static_cast<uint32_t>(b3)), "r"(kPipeThreads) : "memory");
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(as_t * kConvMaxBlockN);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (hf * 32 >= p.BN) break;
+              uint32_t v[32];
+              __syncwarp();
+              tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(hf * 32), v);
+              tmem_ld_wait();
+              if ((hf + 1) * 32 >= p.BN) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctrl->tmem_empty[as_t]);
+              }
+              epilogue_half_slice_act(p.act, v, g_scale + hf * 32, g_bias + hf * 32, cur_st + row * 128, row, hf * 4);
+            }
+            __threadfence_block();
+            asm volatile("bar.arrive %0, %1;" ::"r"(kBarFull + static_cast<uint32_t>(b3)), "r"(kPipeThreads) : "memory");
+            b3 = b3 == 2 ? 0 : b3 + 1;
+          }
+        }
+      } else if (group <= 2) {
+        const int half_w = p.TW >> 1;
+        const int pt = (group - 1) * kEpilogueThreads + et;   // 0..255 among the pooling threads
+        int it = 0, b3 = 0;
+        for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+          for (int t = 0; t < p.tiles_h; ++t, ++it) {
+            const int bprev = b3 == 0 ? 2 : b3 - 1;
+            const uint8_t* cur_st = staging_base + b3 * kConvStagingBytes;        // conv rows 2t, 2t+1
+            const uint8_t* prev_st = staging_base + bprev * kConvStagingBytes;    // conv rows 2t-2, 2t-1
+            asm volatile("bar.sync %0, %1;" ::"r"(kBarFull + static_cast<uint32_t>(b3)), "r"(kPipeThreads) : "memory");
+            if (pt == 0) tma_store_wait_read0();      // the previous pooled row has left the pool staging buffer
+            named_barrier_sync(kBarPool, kPoolThreads);
+            for (int item = pt; item < half_w * 8; item += kPoolThreads) {
+              const int px = item >> 3, c = item & 7;   // pooled pixel, 16-byte channel chunk
+              __half2 m[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) m[j] = __float2half2_rn(0.f);
+#pragma unroll
+              for (int dy = -1; dy <= 1; ++dy) {
+                if (dy < 0 && t == 0) continue;
+                const uint8_t* src = dy < 0 ? prev_st : cur_st;
+                const int rr = dy < 0 ? 1 : dy;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                  const int x = 2 * px + dx;
+                  if (x < 0) continue;
+                  const int srow = rr * p.TW + x;
+                  const uint4 q = *reinterpret_cast<const uint4*>(src + srow * 128 + ((c ^ (srow & 7)) << 4));
+                  const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], qh[j]);
+                }
+              }
+              *reinterpret_cast<uint4*>(pool_st + px * 128 + ((c ^ (px & 7)) << 4)) = *reinterpret_cast<const uint4*>(m);
+            }
+            // the "previous tile" buffer is no longer needed by anyone: group 0 may refill it (tile it+2)
+            if (it >= 1) asm volatile("bar.arrive %0, %1;" ::"r"(kBarFree + static_cast<uint32_t>(bprev)), "r"(kPipeThreads) : "memory");
+            fence_proxy_async();
+            named_barrier_sync(kBarPool, kPoolThreads);
+            if (pt == 0) {
+              tma_store_4d(&maps.pool, pool_st, 0, 0, t, n);
+              tma_store_commit();
+            }
+            b3 = b3 == 2 ? 0 : b3 + 1;
+          }
+        }
+        if (pt == 0) tma_store_wait_all();
+      }
+    } else {
+    TileCursor<false> cur;
     {
       const long long first = tile0 + static_cast<long long>(as) * tstep;
       cur.init(first < total_tiles ? static_cast<int>(first) : 0, 2 * tstep, p);
@@ -651,6 +783,7 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
       }
     }
     if (p.tma_store && et == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
+    }
   }
 
   tc_fence_before();
@@ -718,6 +851,12 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   const int stage_a_bytes = p.vhalo ? (p.TH + p.KH - 1) * p.TW * 128 : kStageABytes;
   static const bool four_groups = getenv("AF_VHALO_4GROUPS") != nullptr;
   p.epi_groups = (p.vhalo && p.tma_store && !four_groups) ? 2 : kEpilogueGroups;
+  if (p.pool) {
+    if (!p.vhalo || !p.wres || p.pair || p.tsm_T > 0 || p.BN > 64 || p.TH != 2 || p.TN != 1 || p.tiles_w != 1 ||
+        !p.tma_store || p.res_mma || p.act == kActNone)
+      return cudaErrorInvalidValue;
+    p.epi_groups = 4;   // a ring of three conv staging buffers + the pooled-row staging buffer
+  }
   const size_t smem =
       conv_gemm_smem_bytes(bn_local, p.res_mma, p.wres ? wbytes : 0, stage_a_bytes, p.epi_groups, &stages, &epi_bufs);
   if (p.vhalo && (stages < 2 || stage_a_bytes % 1024 != 0)) return cudaErrorInvalidValue;
@@ -735,9 +874,10 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     using Kern = void (*)(const ConvTensorMaps, const ConvKernelParams);
-    const Kern kerns[6] = {conv_gemm_kernel<false, false, false>, conv_gemm_kernel<true, false, false>,
+    const Kern kerns[7] = {conv_gemm_kernel<false, false, false>, conv_gemm_kernel<true, false, false>,
                            conv_gemm_kernel<false, true, false>,  conv_gemm_kernel<true, true, false>,
-                           conv_gemm_kernel<false, false, true>,  conv_gemm_kernel<false, true, true>};
+                           conv_gemm_kernel<false, false, true>,  conv_gemm_kernel<false, true, true>,
+                           conv_gemm_kernel<true, false, false, true>};
     for (Kern k : kerns) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBudget);
       if (e != cudaSuccess) return e;
@@ -777,6 +917,7 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (p.pool) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false, false, true>, maps, p);
   if (p.tsm_T > 0) {
     if (p.vhalo) return cudaErrorInvalidValue;
     if (p.pair) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true, true>, maps, p);

@@ -63,12 +63,14 @@ struct ConvKernelParams {
   // frame t-1, the rest from frame t; frames outside the clip read as zeros (TMA out-of-bounds fill on the frame
   // axis of the 5-D map maps.a5).  0 = off.  TN divides tsm_T (a tile never straddles two clips).
   int tsm_T, tsm_f16;
+  int pool;                        // 1: stem mode -- MaxPool2d(3, 2, 1) fused into the epilogue, output through maps.pool
   int pair;                        // 1: clusters of two CTAs, cta_group::2 MMAs of M = 256 (conv_gemm.cu, PAIR); maps.b box = BN/2 rows
 };
 
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
   CUtensorMap ah;     // vhalo: same tensor as a[0], box {64, TW, TH+KH-1, 1}
+  CUtensorMap pool;   // pool mode: pooled output {Cout, Wo/2, Ho/2, N}, box {64, Wo/2, 1, 1}
   CUtensorMap a5;     // temporal-shift mode: the input as {C, W, H, T, clips}, box {64, TW, TH, TN, 1}
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major
   CUtensorMap out;    // output tensor {Cout, Wo, Ho, N}, box {64, TW, TH, TN} (only when tma_store)

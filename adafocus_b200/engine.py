@@ -292,7 +292,7 @@ class Engine:
         return bool(self.lib.af_conv_tsm_supported(int(n), int(h), int(w), int(c), int(x.stride(2)), int(fold), int(t)))
 
     def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None,
-             row_stride=0, img_stride=0, tsm=None):
+             row_stride=0, img_stride=0, tsm=None, pool=False):
         """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given; row_stride /
         img_stride (elements) describe a sliding-window view, see af_conv_desc].  tsm=(T, fold): the convolution reads
         TemporalShift.shift(x) (STH/ops/temporal_shift.py:29-46) without materialising it (1x1 convs, conv_tsm_ok)."""
@@ -304,6 +304,8 @@ class Engine:
         assert cin == pc.cin, (cin, pc.cin)
         ho = (h + 2 * pc.pad - pc.kh) // pc.stride + 1
         wo = (w + 2 * pc.pad - pc.kw) // pc.stride + 1
+        if pool:
+            assert out is not None and tuple(out.shape) == (n, ho // 2, wo // 2, pc.cout)
         if out is None:
             out = self.empty((n, ho, wo, pc.cout), torch.float32 if out_f32 else torch.float16)
             out_stride = pc.cout
@@ -323,6 +325,7 @@ class Engine:
         d.res_stride = residual.stride(-2) if residual is not None else 0
         d.in_row_stride, d.in_img_stride = row_stride, img_stride
         d.tsm_t, d.tsm_fold = (int(tsm[0]), int(tsm[1])) if tsm is not None else (0, 0)
+        d.pool = 1 if pool else 0
         check(self.lib.af_conv2d_nhwc_f16(self.h, byref(d), self._stream()), "af_conv2d_nhwc_f16")
         self._count()
         self.keep(x, pc.w, pc.scale, pc.bias, out, residual)
@@ -338,8 +341,17 @@ class Engine:
                   shape=(1, 1, m, k, x2d.stride(0)))
         return out
 
-    def stem(self, frames, pc, yx=None, patch=None, yx_div=1):
-        """frames (N,3,H,W) fp32 NCHW -> NHWC fp16 stem output; crop at yx (N,2 int32) of size `patch` fused in."""
+    def stem_pool_ok(self, pc, patch):
+        """Can stem(..., pool=True) fuse MaxPool2d(3, 2, 1) into the stem convolution?  (64 x 64 conv output = 128^2
+        patches, s2d form, cout <= 64, ReLU; af_conv_desc.pool)"""
+        s = pc.stem
+        ho = (patch + 2 * s["pad"] - s["kh"]) // s["stride"] + 1
+        return (os.environ.get("AF_NO_STEM_POOL") is None and self.s2d_stem and getattr(pc, "s2d", None) is not None
+                and patch % 2 == 0 and ho == 64 and pc.cout <= 64 and pc.s2d.kh >= 2 and pc.act != AF_ACT_NONE)
+
+    def stem(self, frames, pc, yx=None, patch=None, yx_div=1, pool=False):
+        """frames (N,3,H,W) fp32 NCHW -> NHWC fp16 stem output; crop at yx (N,2 int32) of size `patch` fused in.
+        pool=True (stem_pool_ok): returns MaxPool2d(3, 2, 1) of the stem output, pooled inside the conv kernel."""
         n, c, h, w = frames.shape
         assert c == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
         s = pc.stem
@@ -356,11 +368,15 @@ class Engine:
                                        hs, ws, q.vt, self._stream()), "af_stem_s2d")
             self._count()
             self.keep(frames, yx, buf)
-            out = self.empty((n, ho, wo, pc.cout), torch.float16)
+            if pool:
+                out = self.empty((n, ho // 2, wo // 2, pc.cout), torch.float16)
+            else:
+                out = self.empty((n, ho, wo, pc.cout), torch.float16)
             self.conv(buf, q, out=out, out_stride=pc.cout, shape=(n, hs, wo, 64, pe), row_stride=ws * pe,
-                      img_stride=hs * ws * pe)
+                      img_stride=hs * ws * pe, pool=pool)
             self.release(buf)
             return out
+        assert not pool, "stem(pool=True) needs the space-to-depth form (stem_pool_ok)"
         fused_ok = (self.fused_stem and pc.cout % 16 == 0 and pc.cout <= 64 and s["kh"] * s["kw"] * 3 <= 256
                     and ho * wo >= 128 and s["stride"] <= 2 and s["kh"] <= 7 and s["kw"] <= 7)
         if fused_ok:

@@ -152,10 +152,14 @@ class ResNetRunner:
     def run(self, eng, frames, yx=None, patch=None, yx_div=1):
         """frames (N,3,H,W) fp32; with yx (N,2 int32) + patch the crop of ACT/models/utils.py:37-51 is fused into the
         stem staging.  Returns the layer4 output (N,h,w,2048) NHWC fp16."""
-        x = eng.stem(frames, self.stem, yx=yx, patch=patch, yx_div=yx_div)
-        y = eng.maxpool3x3s2(x)
-        eng.release(x)
-        x = y
+        p_eff = patch if patch is not None else frames.shape[-1]
+        if frames.shape[-1] == frames.shape[-2] and eng.stem_pool_ok(self.stem, p_eff):
+            x = eng.stem(frames, self.stem, yx=yx, patch=patch, yx_div=yx_div, pool=True)   # conv + BN + ReLU + maxpool
+        else:
+            x = eng.stem(frames, self.stem, yx=yx, patch=patch, yx_div=yx_div)
+            y = eng.maxpool3x3s2(x)
+            eng.release(x)
+            x = y
         for e in self.blocks:
             inp = x
             a = x

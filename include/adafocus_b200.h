@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AF_VERSION 100
+#define AF_VERSION 200
 
 typedef enum af_status {
   AF_OK = 0,
@@ -73,6 +73,11 @@ typedef struct af_conv_desc {
    * from the next frame, [tsm_fold, 2*tsm_fold) from the previous one, the rest from the frame itself, zeros outside
    * the clip -- conv(shift(x)) without materialising shift(x).  tsm_t = 0: off.  Needs af_conv_tsm_supported(). */
   int32_t tsm_t, tsm_fold;
+  /* pool != 0: the stem of the focus network -- conv + BN + ReLU + MaxPool2d(kernel 3, stride 2, padding 1)
+   * (ACT/models/resnet.py:138-142, 213-216) as ONE kernel: `out` is then the pooled tensor (n, Ho/2, Wo/2, cout) and the
+   * convolution's own output never reaches HBM.  Needs a stride-1 filter with kh >= 2 and resident weights, Wo == 64,
+   * Ho even, cout <= 64, a ReLU-type activation (the pool pads with 0). */
+  int32_t pool, reserved0;
 } af_conv_desc;
 
 /* 1 when af_conv2d_nhwc_f16 can fold the temporal shift for this geometry (cin % 64 == 0, fold % 16 == 0,

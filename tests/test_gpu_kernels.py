@@ -594,3 +594,23 @@ def test_device_metrics_vs_reference_golden(golden_dir):
     np.testing.assert_allclose(ap1.cpu().numpy(), gold["ap_single"], rtol=1e-3, atol=5e-2)
     np.testing.assert_allclose(ap2.cpu().numpy(), gold["ap_multi"], rtol=1e-3, atol=5e-2)
     assert abs(float(m1) - float(gold["map_single"])) < 2e-2 and abs(float(m2) - float(gold["map_multi"])) < 2e-2
+
+
+@pytest.mark.parametrize("n,yx_div", [(5, 1), (300, 1), (6, 3)])
+def test_stem_conv_with_fused_maxpool_bit_exact(eng, n, yx_div):
+    """ResNet stem (7x7/2 conv + BN + ReLU) with MaxPool2d(3, 2, 1) fused into the conv kernel's epilogue (128^2 patches:
+    two full 64-pixel output rows per tile, the CTA walks an image top to bottom) == the same stem followed by the
+    stand-alone max-pool kernel, bit for bit; 300 patches > SM count exercises several images per CTA."""
+    from adafocus_b200.engine import AF_ACT_RELU, pack_stem
+    torch.manual_seed(n)
+    frames = torch.randn(n, 3, 224, 224, device=DEV)
+    yx = torch.randint(0, 97, (n // yx_div, 2), device=DEV, dtype=torch.int32)
+    w = torch.randn(64, 3, 7, 7, device=DEV) / math.sqrt(147)
+    pc = pack_stem(w, torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV) * 0.2, stride=2, pad=3,
+                   act=AF_ACT_RELU, device=DEV)
+    assert eng.stem_pool_ok(pc, 128)
+    want = eng.maxpool3x3s2(eng.stem(frames, pc, yx=yx, patch=128, yx_div=yx_div))
+    got = eng.stem(frames, pc, yx=yx, patch=128, yx_div=yx_div, pool=True)
+    torch.cuda.synchronize()
+    assert got.shape == (n, 32, 32, 64) and torch.equal(got, want)
+    assert not eng.stem_pool_ok(pc, 144)          # 72-pixel rows do not fill a 128-row tile pair: separate pool kernel
