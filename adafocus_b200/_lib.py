@@ -30,6 +30,8 @@ class ConvDesc(ctypes.Structure):
         ("in_row_stride", c_int64), ("in_img_stride", c_int64),
         ("tsm_t", c_int32), ("tsm_fold", c_int32),
         ("pool", c_int32), ("reserved0", c_int32),
+        ("in2", c_void_p), ("w2", c_void_p), ("cin2", c_int32), ("stride2", c_int32), ("h2", c_int32), ("w2_", c_int32),
+        ("in2_stride", c_int64),
     ]
 
 

@@ -569,6 +569,29 @@ int af_conv2d_nhwc_f16(af_ctx* ctx, const af_conv_desc* d, void* stream) {
     const cuuint32_t bbox[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN)};
     if (!encode_map(ctx, &maps.b, d->w, 2, dims, strides, bbox, &err)) return fail(AF_ERR_CUDA, err);
   }
+  if (d->in2 != nullptr) {
+    // second GEMM accumulated into the same tile: the projection shortcut downsample(x) of a bottleneck
+    // (ACT/models/resnet.py:107-111), a 1x1 stride-s2 conv over the block input
+    if (d->w2 == nullptr || d->cin2 < 8 || d->cin2 % 8 != 0 || d->in2_stride < d->cin2 || d->in2_stride % 8 != 0 ||
+        (d->stride2 != 1 && d->stride2 != 2) || p.vhalo || tsm || p.pool || d->residual != nullptr || d->scale != nullptr)
+      return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: in2/w2 need scale == NULL (folded), no residual, a non-halo conv, "
+                                  "cin2 % 8 == 0 and stride2 in {1, 2}");
+    const int h2 = d->stride2 == 1 ? p.Ho : d->h2, w2 = d->stride2 == 1 ? p.Wo : d->w2_;
+    if ((h2 - 1) / d->stride2 + 1 != p.Ho || (w2 - 1) / d->stride2 + 1 != p.Wo)
+      return fail(AF_ERR_INVALID, "af_conv2d_nhwc_f16: in2 geometry does not produce the output grid");
+    p.k2_blocks = ceil_div(d->cin2, af::kConvBlockK);
+    const cuuint64_t pix2 = static_cast<cuuint64_t>(d->in2_stride) * 2;
+    const cuuint64_t s2 = static_cast<cuuint64_t>(d->stride2);
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin2), static_cast<cuuint64_t>(p.Wo),
+                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix2 * s2, pix2 * w2 * s2, pix2 * w2 * h2};
+    if (!encode_map(ctx, &maps.a2, d->in2, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+    const cuuint64_t kpad2 = static_cast<cuuint64_t>(p.k2_blocks) * af::kConvBlockK;
+    const cuuint64_t bdims[2] = {kpad2, static_cast<cuuint64_t>(p.n_blocks) * p.BN};
+    const cuuint64_t bstrides[1] = {kpad2 * 2};
+    const cuuint32_t bbox2[2] = {static_cast<cuuint32_t>(af::kConvBlockK), static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN)};
+    if (!encode_map(ctx, &maps.b2, d->w2, 2, bdims, bstrides, bbox2, &err)) return fail(AF_ERR_CUDA, err);
+  }
   // fp16 outputs leave through the smem-staged TMA store when 64-channel slices never straddle an n-block
   p.tma_store = (!d->out_f32 && d->cout % 8 == 0 && (p.BN % 64 == 0 || p.n_blocks == 1)) ? 1 : 0;
   // A residual is added on the tensor core (R * I accumulated into TMEM), which needs the per-channel scale folded

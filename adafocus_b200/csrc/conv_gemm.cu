@@ -227,6 +227,10 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
     if (p.tma_store) tma_prefetch_desc(&maps.out);
     if (p.res_mma) tma_prefetch_desc(&maps.res);
     if (VHALO) tma_prefetch_desc(&maps.ah);
+    if (p.k2_blocks > 0) {
+      tma_prefetch_desc(&maps.a2);
+      tma_prefetch_desc(&maps.b2);
+    }
     if (TSM) tma_prefetch_desc(&maps.a5);
     if (POOL) tma_prefetch_desc(&maps.pool);
     if (p.stride == 2) {
@@ -385,6 +389,18 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
             }
           }
         }
+        for (int kb2 = 0; kb2 < p.k2_blocks; ++kb2) {
+          // second GEMM (projection shortcut): its k-blocks ride the same ring as (A box, weight box) stages
+          mbar_wait_backoff(&ctrl->empty[stage], phase ^ 1, bo);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          expect(&ctrl->full[stage], static_cast<uint32_t>(stage_bytes));
+          load4(sa, &maps.a2, stage, kb2 * kConvBlockK, ow0, oh0, n0);
+          load2(sa + kStageABytes, &maps.b2, stage, kb2 * kConvBlockK, nb * p.BN + brow);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
         if (p.res_mma) {
           // the residual tile rides the same pipeline as extra A boxes (64 output channels each)
           for (int j = 0; j * 64 < p.BN && nb * p.BN + j * 64 < p.Cout; ++j) {
@@ -492,6 +508,20 @@ conv_gemm_kernel(const __grid_constant__ ConvTensorMaps maps, const ConvKernelPa
                            (kb | k) != 0 ? 1u : 0u);
           }
           commit(&ctrl->empty[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (int kb2 = 0; kb2 < p.k2_blocks; ++kb2) {
+          mbar_wait_backoff(&ctrl->full[stage], phase, bo);
+          tc_fence_after();
+          const uint32_t la = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+          const uint32_t lb = la + (kStageABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 16; ++k)
+            mma(tmem_d, la + static_cast<uint32_t>(k * 2), lb + static_cast<uint32_t>(k * 2), idesc, 1u);
+          commit(&ctrl->empty[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -846,7 +876,7 @@ cudaError_t launch_conv_gemm(const ConvTensorMaps& maps, const ConvKernelParams&
   // resident weights: single n-block and at most 80 KiB of weights (>= 4 A-only stages remain)
   const int bn_local = p.pair ? p.BN / 2 : p.BN;
   const int wbytes = p.KH * p.KW * p.cblks * bn_local * kConvBlockK * 2;
-  p.wres = conv_gemm_wres_ok(p.n_blocks, p.BN, p.KH, p.KW, p.cblks, p.pair) ? 1 : 0;
+  p.wres = (p.k2_blocks == 0 && conv_gemm_wres_ok(p.n_blocks, p.BN, p.KH, p.KW, p.cblks, p.pair)) ? 1 : 0;
   if (!p.wres) p.vhalo = 0;
   const int stage_a_bytes = p.vhalo ? (p.TH + p.KH - 1) * p.TW * 128 : kStageABytes;
   static const bool four_groups = getenv("AF_VHALO_4GROUPS") != nullptr;

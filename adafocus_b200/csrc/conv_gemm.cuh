@@ -63,6 +63,9 @@ struct ConvKernelParams {
   // frame t-1, the rest from frame t; frames outside the clip read as zeros (TMA out-of-bounds fill on the frame
   // axis of the 5-D map maps.a5).  0 = off.  TN divides tsm_T (a tile never straddles two clips).
   int tsm_T, tsm_f16;
+  int k2_blocks;                   // > 0: a second 1x1 GEMM accumulates into the same tile before the epilogue -- the
+                                   // projection shortcut of a bottleneck (maps.a2 = block input, strided; maps.b2 = its
+                                   // weights): out = act(conv(in) + conv1x1_s(in2) + bias), k2_blocks = ceil(Cin2 / 64)
   int pool;                        // 1: stem mode -- MaxPool2d(3, 2, 1) fused into the epilogue, output through maps.pool
   int pair;                        // 1: clusters of two CTAs, cta_group::2 MMAs of M = 256 (conv_gemm.cu, PAIR); maps.b box = BN/2 rows
 };
@@ -70,6 +73,8 @@ struct ConvKernelParams {
 struct ConvTensorMaps {
   CUtensorMap a[4];   // parity views (index = (h&1)*2 + (w&1)); stride-1 layers use a[0] only
   CUtensorMap ah;     // vhalo: same tensor as a[0], box {64, TW, TH+KH-1, 1}
+  CUtensorMap a2;     // second GEMM: input view {Cin2, Wo, Ho, N} (pixel (oh*s2, ow*s2) of the block input), box = a[0]'s
+  CUtensorMap b2;     // second GEMM: packed weights [Cout_pad][K2_pad], box {64, BN (BN/2 per CTA of a pair)}
   CUtensorMap pool;   // pool mode: pooled output {Cout, Wo/2, Ho/2, N}, box {64, Wo/2, 1, 1}
   CUtensorMap a5;     // temporal-shift mode: the input as {C, W, H, T, clips}, box {64, TW, TH, TN, 1}
   CUtensorMap b;      // packed weights [Cout_pad][K_pad], K-major

@@ -292,7 +292,7 @@ class Engine:
         return bool(self.lib.af_conv_tsm_supported(int(n), int(h), int(w), int(c), int(x.stride(2)), int(fold), int(t)))
 
     def conv(self, x, pc, out=None, residual=None, act=None, out_f32=False, out_stride=None, shape=None,
-             row_stride=0, img_stride=0, tsm=None, pool=False):
+             row_stride=0, img_stride=0, tsm=None, pool=False, shortcut=None):
         """x: NHWC fp16 (n,h,w,cin) [or any tensor when `shape`=(n,h,w,cin,in_stride) is given; row_stride /
         img_stride (elements) describe a sliding-window view, see af_conv_desc].  tsm=(T, fold): the convolution reads
         TemporalShift.shift(x) (STH/ops/temporal_shift.py:29-46) without materialising it (1x1 convs, conv_tsm_ok)."""
@@ -326,6 +326,16 @@ class Engine:
         d.in_row_stride, d.in_img_stride = row_stride, img_stride
         d.tsm_t, d.tsm_fold = (int(tsm[0]), int(tsm[1])) if tsm is not None else (0, 0)
         d.pool = 1 if pool else 0
+        if shortcut is not None:
+            # (x2, pc2): out = act(conv(x) + conv1x1_stride(x2) + bias) -- the projection shortcut accumulated in the
+            # same TMEM tile (af_conv_desc.in2); pc.bias must already hold the sum of both folded BN biases
+            x2, pc2 = shortcut
+            assert pc.scale is None and pc2.scale is None and residual is None and pc2.kh == 1 and pc2.cout == pc.cout
+            assert pc2.block_n == pc.block_n and x2.shape[-1] == pc2.cin
+            d.in2, d.w2 = x2.data_ptr(), pc2.w.data_ptr()
+            d.cin2, d.stride2, d.h2, d.w2_ = pc2.cin, pc2.stride, x2.shape[1], x2.shape[2]
+            d.in2_stride = x2.stride(2)
+            self.keep(x2, pc2.w)
         check(self.lib.af_conv2d_nhwc_f16(self.h, byref(d), self._stream()), "af_conv2d_nhwc_f16")
         self._count()
         self.keep(x, pc.w, pc.scale, pc.bias, out, residual)

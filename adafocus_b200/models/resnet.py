@@ -4,6 +4,8 @@ Mirror of ACT/models/resnet.py (Bottleneck :74-114, ResNet :117-240, get_featmap
 carries parameters under the reference's names (`conv1`, `bn1`, `layerL.B.convK`, `downsample.0/1`, `fc`); the
 trunk runs as tcgen05 implicit-GEMM convolutions on NHWC fp16 with BatchNorm folded into the epilogue.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -123,10 +125,18 @@ class ResNetRunner:
                                     device=dev)
                 s, b = _fold(blk.bn3)
                 e["c3"] = pack_conv(blk.conv3.weight, s, b, act=AF_ACT_RELU, device=dev, fold_scale=True)   # relu after the add
+                e["c3ds"] = None
                 if blk.downsample is not None:
-                    s, b = _fold(blk.downsample[1])
-                    e["ds"] = pack_conv(blk.downsample[0].weight, s, b, stride=blk.downsample[0].stride[0],
+                    sd, bd = _fold(blk.downsample[1])
+                    e["ds"] = pack_conv(blk.downsample[0].weight, sd, bd, stride=blk.downsample[0].stride[0],
                                         act=AF_ACT_NONE, device=dev)
+                    if os.environ.get("AF_NO_SHORTCUT_FUSION") is None:
+                        # projection shortcut accumulated inside conv3's tile: both BN scales folded into the fp16
+                        # weights, one bias; the downsample tensor is never written or re-read
+                        c3f = pack_conv(blk.conv3.weight, s, b + bd, act=AF_ACT_RELU, device=dev, fold_scale=True)
+                        dsf = pack_conv(blk.downsample[0].weight, sd, None, stride=blk.downsample[0].stride[0],
+                                        act=AF_ACT_NONE, device=dev, fold_scale=True, block_n=c3f.block_n)
+                        e["c3ds"] = (c3f, dsf)
                 else:
                     e["ds"] = None
                 self.blocks.append(e)
@@ -175,6 +185,11 @@ class ResNetRunner:
                 eng.release(a)
             h2 = eng.conv(h1, e["c2"])
             eng.release(h1)
+            if e["c3ds"] is not None:
+                x = eng.conv(h2, e["c3ds"][0], shortcut=(inp, e["c3ds"][1]))
+                eng.release(h2)
+                eng.release(inp)
+                continue
             if e["ds"] is not None:
                 idn = eng.conv(inp, e["ds"])
             else:

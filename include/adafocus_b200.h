@@ -78,6 +78,16 @@ typedef struct af_conv_desc {
    * convolution's own output never reaches HBM.  Needs a stride-1 filter with kh >= 2 and resident weights, Wo == 64,
    * Ho even, cout <= 64, a ReLU-type activation (the pool pads with 0). */
   int32_t pool, reserved0;
+  /* Optional second GEMM accumulated into the same output tile before the epilogue -- the projection shortcut of a
+   * bottleneck block, out = relu(bn3(conv3(h)) + bn_d(conv_d(x))) (ACT/models/resnet.py:94-114 with `downsample`,
+   * :170-181): in2 = the block input x (n, h2, w2_, cin2) NHWC fp16 with pixel stride in2_stride, w2 = the 1x1
+   * stride-`stride2` downsample weights packed like `w` ([cout_pad][ceil(cin2/64)*64], BN scale folded in), `bias` =
+   * the sum of both folded BN biases; needs scale == NULL and residual == NULL.  The downsample output and its
+   * read-back as a residual never touch HBM.  in2 == NULL: off. */
+  const void* in2;
+  const void* w2;
+  int32_t cin2, stride2, h2, w2_;
+  int64_t in2_stride;
 } af_conv_desc;
 
 /* 1 when af_conv2d_nhwc_f16 can fold the temporal shift for this geometry (cin % 64 == 0, fold % 16 == 0,

@@ -550,6 +550,36 @@ def test_conv_with_folded_temporal_shift_bit_exact(eng, nclips, t, hw, cin, cout
     assert not eng.conv_tsm_ok(x[: n - 1], t, fold)
 
 
+@pytest.mark.parametrize("n,hw,cmid,cin2,cout,s2", [
+    (3, 32, 64, 64, 256, 1),       # layer1.0: conv3 64->256 + downsample 64->256, stride 1
+    (5, 16, 128, 256, 512, 2),     # layer2.0: + downsample 256->512 at stride 2 (block input 32x32)
+    (40, 8, 256, 512, 1024, 2),    # layer3.0, several n-blocks, more tiles than one wave per n-block
+    (2, 5, 512, 1024, 2048, 2),    # layer4.0 on a 9x9 block input (odd size: ceil at the stride)
+])
+def test_conv_with_fused_projection_shortcut(eng, n, hw, cmid, cin2, cout, s2):
+    """out = relu(bn3(conv3(h)) + bn_d(downsample(x))) as ONE kernel: the 1x1 stride-s downsample is a second GEMM
+    accumulated into conv3's TMEM tile (af_conv_desc.in2 / w2), vs torch fp32 on the fp16-rounded operands."""
+    from adafocus_b200.engine import AF_ACT_NONE, AF_ACT_RELU, pack_conv
+    torch.manual_seed(cout + hw)
+    hin = hw * s2 - (1 if (s2 == 2 and hw % 2 == 1) else 0)      # block input size that strides down to hw
+    h = torch.randn(n, hw, hw, cmid, device=DEV).half()
+    x = torch.randn(n, hin, hin, cin2, device=DEV).half()
+    w3 = torch.randn(cout, cmid, device=DEV) / math.sqrt(cmid)
+    wd = torch.randn(cout, cin2, device=DEV) / math.sqrt(cin2)
+    s3, b3 = torch.rand(cout, device=DEV) * 0.5 + 0.25, torch.randn(cout, device=DEV) * 0.1
+    sd, bd = torch.rand(cout, device=DEV) * 0.5 + 0.25, torch.randn(cout, device=DEV) * 0.1
+    c3 = pack_conv(w3, s3, b3 + bd, act=AF_ACT_RELU, device=DEV, fold_scale=True)
+    ds = pack_conv(wd, sd, None, stride=s2, act=AF_ACT_NONE, device=DEV, fold_scale=True, block_n=c3.block_n)
+    out = eng.conv(h, c3, shortcut=(x, ds))
+    torch.cuda.synchronize()
+    w3q, wdq = (w3 * s3[:, None]).half().float(), (wd * sd[:, None]).half().float()
+    ref = F.conv2d(h.float().permute(0, 3, 1, 2), w3q[:, :, None, None]) + \
+        F.conv2d(x.float().permute(0, 3, 1, 2), wdq[:, :, None, None], stride=s2) + (b3 + bd).view(1, -1, 1, 1)
+    ref = ref.clamp_min(0).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3), float((out.float() - ref).abs().max())
+
+
 def test_conv_cases_in_forced_cta_pair_mode():
     """Every convolution case above again with AF_CONV_PAIR=1: clusters of two CTAs, cta_group::2 MMAs of M = 256, each
     CTA holding half of every weight tile (conv_gemm.cu, PAIR).  The mode is a process-wide knob, hence the child
