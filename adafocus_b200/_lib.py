@@ -90,6 +90,9 @@ SIGNATURES = {
     "af_split3_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "af_gru_sequence": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                 c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_gru_sequence_tc_supported": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "af_gru_sequence_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "af_policy_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "af_policy_head_continuous": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -13,6 +13,7 @@
 #include "conv_gemm.cuh"
 #include "dwconv_tma.cuh"
 #include "kernels.cuh"
+#include "gru_tc.cuh"
 #include "mbconv_fused.cuh"
 #include "stem_gemm.cuh"
 
@@ -819,6 +820,53 @@ int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const fl
   return dispatch(ctx, stream, "af_gru_sequence", [=](cudaStream_t s) {
     return af::launch_gru_sequence(xg, w, b_hh, h0, hbuf, hs, hseq_stride, h_out, counter, B, T, Hd, sms, split, s);
   });
+}
+
+int af_gru_sequence_tc_supported(const af_ctx* ctx, int B, int Hd, int split) {
+  return (ctx != nullptr && af::gru_tc_supported(B, Hd, ctx->sm_count, split)) ? 1 : 0;
+}
+
+int af_gru_sequence_tc(af_ctx* ctx, const float* xg, const void* w_hh_f16, int64_t w_cols, const float* b_hh,
+                       const float* h0, void* hbuf, void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter,
+                       int B, int T, int Hd, int split, void* stream) {
+  if (ctx == nullptr || xg == nullptr || w_hh_f16 == nullptr || b_hh == nullptr || hbuf == nullptr ||
+      hseq_f16 == nullptr || counter == nullptr)
+    return fail(AF_ERR_INVALID, "af_gru_sequence_tc: null argument");
+  if (!af::gru_tc_supported(B, Hd, ctx->sm_count, split) || T < 1 || w_cols < (split ? 3 : 1) * static_cast<int64_t>(Hd) ||
+      hseq_stride < (split ? 3 : 1) * static_cast<int64_t>(Hd) || hseq_stride % 8 != 0)
+    return fail(AF_ERR_INVALID, "af_gru_sequence_tc: needs 1 <= B <= 64, H % 64 == 0, H / 8 <= SM count "
+                                "(af_gru_sequence_tc_supported)");
+  af::GruTcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(w_cols), static_cast<cuuint64_t>(3 * Hd)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(w_cols) * 2};
+    const cuuint32_t box[2] = {64, 8};
+    if (!encode_map(ctx, &maps.w, w_hh_f16, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  const int kh = (split ? 2 : 1) * Hd;
+  for (int i = 0; i < 2; ++i) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kh), static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kh) * 2};
+    const cuuint32_t box[2] = {64, 64};
+    const __half* base = static_cast<const __half*>(hbuf) + static_cast<size_t>(i) * B * kh;
+    if (!encode_map(ctx, &maps.h[i], base, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  af::GruTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.xg = xg;
+  p.b_hh = b_hh;
+  p.h0 = h0;
+  p.hbuf = static_cast<__half*>(hbuf);
+  p.hseq = static_cast<__half*>(hseq_f16);
+  p.hseq_stride = hseq_stride;
+  p.h_out = h_out;
+  p.counter = counter;
+  p.B = B;
+  p.T = T;
+  p.H = Hd;
+  return dispatch(ctx, stream, "af_gru_sequence_tc", [=](cudaStream_t s) { return af::launch_gru_tc(maps, p, split, s); });
 }
 
 int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,

@@ -538,6 +538,27 @@ class Engine:
         self.release(hbuf)
         self.release(counter)
 
+    def can_gru_sequence_tc(self, b, hd, split=False):
+        """Whole recurrence in one persistent tensor-core launch (af_gru_sequence_tc): up to 64 sequences."""
+        return (os.environ.get("AF_NO_GRU_TC") is None and
+                bool(self.lib.af_gru_sequence_tc_supported(self.h, int(b), int(hd), 1 if split else 0)))
+
+    def gru_sequence_tc(self, xg, pc_hh, b, t, hseq16, h0=None, h_out=None):
+        """All T steps of a GRU for up to 64 sequences in one persistent tcgen05 launch.  xg (B*T,3H) fp32, pc_hh =
+        PackedConv of W_hh (+ b_hh), plain or split-precision (then hseq16 rows are [hi | lo | hi])."""
+        split = bool(getattr(pc_hh, "split", False))
+        hd = pc_hh.cin // 3 if split else pc_hh.cin
+        assert pc_hh.w.shape[0] == 3 * hd and xg.shape == (b * t, 3 * hd)
+        hbuf = self.empty((2, b, (2 if split else 1) * hd), torch.float16)
+        counter = self.empty((1,), torch.int32)
+        check(self.lib.af_gru_sequence_tc(self.h, _ptr(xg), _ptr(pc_hh.w), pc_hh.w.shape[1], _ptr(pc_hh.bias), _ptr(h0),
+                                          _ptr(hbuf), _ptr(hseq16), hseq16.stride(0), _ptr(h_out), _ptr(counter), b, t,
+                                          hd, 1 if split else 0, self._stream()), "af_gru_sequence_tc")
+        self._count()
+        self.keep(xg, pc_hh.w, pc_hh.bias, h0, hbuf, hseq16, h_out, counter)
+        self.release(hbuf)
+        self.release(counter)
+
     def policy_head(self, logits, action_dim, h, patch, action_idx=None, action_yx=None, yx=None):
         rows = logits.shape[0]
         grid_n = int(round(math.sqrt(action_dim)))

@@ -174,6 +174,13 @@ class GRUHeadRunner:
             eng.release(xg)
             eng.release(hseq3)
             return
+        if eng.can_gru_sequence_tc(b, hd, split=True):
+            # bench batch sizes: the recurrence stays one persistent tensor-core launch (W_hh resident in smem)
+            eng.gru_sequence_tc(xg, self.gru_hh, b, t, hseq3, h0=h0, h_out=h_out)
+            eng.linear(hseq3, self.fc, out=logits, out_f32=True, out_stride=self.logit_stride)
+            eng.release(xg)
+            eng.release(hseq3)
+            return
         h = eng.empty((b, hd), torch.float32) if h_out is None else h_out
         if h0 is None:
             eng.fill(h, 0.0)

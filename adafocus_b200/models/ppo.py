@@ -150,6 +150,10 @@ class PolicyRunner:
             # small batch: the whole T-step recurrence is one persistent warp-reduction kernel
             eng.gru_sequence(xg, self.gru_hh, b, t, hseq16)
             tmps = (xg, hseq16)
+        elif eng.can_gru_sequence_tc(b, hd):
+            # up to 64 clips: one persistent tensor-core launch, W_hh resident in shared memory
+            eng.gru_sequence_tc(xg, self.gru_hh, b, t, hseq16)
+            tmps = (xg, hseq16)
         else:
             h = eng.empty((b, hd), torch.float32)
             eng.fill(h, 0.0)

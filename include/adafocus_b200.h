@@ -248,6 +248,18 @@ int af_gru_sequence(af_ctx* ctx, const float* xg, const void* w_hh_f16, const fl
                     void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter, int B, int T, int Hd,
                     int split, void* stream);
 
+/* The same recurrence for up to 64 sequences on the tensor core, still ONE persistent cooperative launch (csrc/gru_tc.cuh):
+ * CTA c keeps the 24 W_hh rows of hidden units [8c, 8c+8) in shared memory as UMMA operand tiles, streams h_{t-1}
+ * (fp16 operand rows, TMA) every step, accumulates in TMEM, applies the gates from fp32 state held in registers and
+ * meets the other CTAs at a grid barrier.  w_hh_f16: (3H, w_cols) fp16 row-major -- plain W_hh (w_cols >= H) or the
+ * split-precision packing [W_hi | W_hi | W_lo] (split != 0, w_cols >= 3H), in which case h travels as [hi | lo] and
+ * hseq_f16 rows are [hi | lo | hi] (3H wide).  hbuf: 2 * B * (split ? 2 : 1) * H halfs of scratch; counter: one uint32.
+ * Constraints (af_gru_sequence_tc_supported): 1 <= B <= 64, H % 64 == 0, H / 8 <= number of SMs. */
+int af_gru_sequence_tc_supported(const af_ctx* ctx, int B, int Hd, int split);
+int af_gru_sequence_tc(af_ctx* ctx, const float* xg, const void* w_hh_f16, int64_t w_cols, const float* b_hh,
+                       const float* h0, void* hbuf, void* hseq_f16, int64_t hseq_stride, float* h_out, uint32_t* counter,
+                       int B, int T, int Hd, int split, void* stream);
+
 /* softmax -> argmax -> standard action table -> patch origin; ACT/models/ppo.py:84,94,
  * ACT/models/gfv_net.py:272-307,345-347, ACT/models/utils.py:42.  grid_n = sqrt(action_dim). */
 int af_policy_head(af_ctx* ctx, const float* logits, int64_t logit_stride, int A, int grid_n, int rows, int H, int P,

@@ -484,6 +484,48 @@ def test_gru_sequence_and_gates_split_precision(eng, b, t, hd):
     assert torch.equal(h3[:, :hd], h.half()) and torch.equal(h3[:, hd:2 * hd], (h - h.half().float()).half())
 
 
+@pytest.mark.parametrize("b,t,hd,split", [(64, 16, 1024, False), (64, 16, 1024, True), (37, 5, 1024, True),
+                                          (9, 3, 512, False), (64, 2, 256, True)])
+def test_gru_sequence_tensor_core_kernel(eng, b, t, hd, split):
+    """Persistent tensor-core GRU recurrence (af_gru_sequence_tc: W_hh resident in smem as UMMA tiles, h streamed by TMA,
+    grid barrier between steps) against torch.nn.GRU on CPU fp32.  Plain form: same fp16-rounded W_hh, fp16 operand rows
+    of h (tolerance 2e-3 like the per-step path); split form: unrounded weights, ~fp32 operands (2e-5)."""
+    from adafocus_b200.engine import pack_conv, pack_conv_split
+    torch.manual_seed(b * 7 + t)
+    gru = torch.nn.GRU(64, hd, batch_first=True)
+    with torch.no_grad():
+        if not split:
+            gru.weight_hh_l0.copy_(gru.weight_hh_l0.half().float())
+        x = torch.randn(b, t, 64)
+        h0 = torch.randn(1, b, hd) * 0.3
+        ref, hn = gru(x, h0)
+        xg = (x.reshape(b * t, 64) @ gru.weight_ih_l0.t() + gru.bias_ih_l0).contiguous().to(DEV)
+    assert eng.can_gru_sequence_tc(b, hd, split=split)
+    if split:
+        pc = pack_conv_split(gru.weight_hh_l0, gru.bias_hh_l0, device=DEV, block_n=32)
+        hseq = torch.zeros(b * t, 3 * hd, device=DEV, dtype=torch.float16)
+    else:
+        pc = pack_conv(gru.weight_hh_l0, None, gru.bias_hh_l0, device=DEV, block_n=32)
+        hseq = torch.zeros(b * t, hd, device=DEV, dtype=torch.float16)
+    h_out = torch.zeros(b, hd, device=DEV)
+    eng.gru_sequence_tc(xg, pc, b, t, hseq, h0=h0[0].to(DEV).contiguous(), h_out=h_out)
+    torch.cuda.synchronize()
+    tol = 2e-5 if split else 2e-3
+    assert float((h_out.cpu() - hn[0]).abs().max()) <= tol
+    if split:
+        seq = (hseq[:, :hd].float() + hseq[:, hd:2 * hd].float()).cpu().view(b, t, hd)
+        assert torch.equal(hseq[:, :hd], hseq[:, 2 * hd:])
+    else:
+        seq = hseq.float().cpu().view(b, t, hd)
+    assert float((seq - ref).abs().max()) <= max(tol, 1e-3 if not split else 0)
+    # zero initial state when h0 is omitted; a second launch reuses the scratch / counter correctly
+    eng.gru_sequence_tc(xg, pc, b, t, hseq, h_out=h_out)
+    with torch.no_grad():
+        _, hn0 = gru(x)
+    torch.cuda.synchronize()
+    assert float((h_out.cpu() - hn0[0]).abs().max()) <= tol
+
+
 @pytest.mark.parametrize("a,p", [(49, 128), (25, 96), (36, 160), (64, 192), (100, 144)])
 def test_policy_head_argmax_and_coords(eng, a, p):
     from oracle import adafocus_oracle as orc
