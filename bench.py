@@ -110,7 +110,7 @@ def reference_cpu(workload, steps, warmup, clips_per_step=None, budget_s=150.0, 
     cands = sorted({max(1, min(cores, 64)), max(1, min(cores, 64) // 2)}, reverse=True)
     tree = "STH" if workload in ("cfg5", "cfg1") else "ACT"
     kind = "reference" if rl.available(tree) else "port"
-    with torch.no_grad():
+    with torch.no_grad(), rl.force_cpu():      # the reference hard-codes .cuda(): keep the CPU arm on the CPU
         if workload == "cfg1":
             args = synth.sth_args()
             if kind == "reference":

@@ -56,6 +56,23 @@ def _cpu_shims():
         torch.nn.Module.cuda = lambda self, *a, **k: self
 
 
+class force_cpu:
+    """Context manager for running the reference on the HOST cores of a machine that also has a GPU (bench.py's
+    cpu_baseline / --impl reference): inside it `.cuda()` is the identity, exactly like shim 2 above, so the
+    reference's hard-coded `.cuda()` calls (ACT/models/ppo.py:70,135; ACT/models/gfv_net.py:279,429) leave everything on
+    the CPU.  The original methods are restored on exit."""
+
+    def __enter__(self):
+        self._saved = (torch.Tensor.cuda, torch.nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda, torch.nn.Module.cuda = self._saved
+        return False
+
+
 def _stub_hydra():
     try:
         importlib.import_module("hydra")
