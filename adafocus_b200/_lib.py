@@ -45,6 +45,16 @@ class MbconvDesc(ctypes.Structure):
     ]
 
 
+class MbconvRowsDesc(ctypes.Structure):
+    """struct af_mbconv_rows_desc"""
+    _fields_ = [
+        ("in_", c_void_p), ("w1", c_void_p), ("dwp", c_void_p), ("w2", c_void_p), ("bias3", c_void_p),
+        ("residual", c_void_p), ("out", c_void_p),
+        ("n", c_int32), ("h", c_int32), ("w_", c_int32), ("cin", c_int32), ("cexp", c_int32), ("cout", c_int32),
+        ("stride", c_int32), ("res_stride", c_int64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/adafocus_b200.h
 SIGNATURES = {
     "af_version": (c_int, []),
@@ -78,6 +88,9 @@ SIGNATURES = {
     "af_conv_tsm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_fused": (c_int, [c_void_p, POINTER(MbconvDesc), c_void_p]),
+    "af_mbconv_rows_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "af_mbconv_rows_layout": (c_int, [c_int, c_int, POINTER(c_int32), c_void_p, c_void_p]),
+    "af_mbconv_rows": (c_int, [c_void_p, POINTER(MbconvRowsDesc), c_void_p]),
     "af_dwconv3x3_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "af_maxpool3x3s2_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

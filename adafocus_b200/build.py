@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libadafocus_b200.so")
-SOURCES = ["conv_gemm.cu", "gru_tc.cu", "stem_gemm.cu", "dwconv_tma.cu", "mbconv_fused.cu", "kernels.cu", "capi.cu"]
-HEADERS = ["ptx.cuh", "gru_tc.cuh", "conv_gemm.cuh", "stem_gemm.cuh", "kernels.cuh", "dwconv_tma.cuh", "dw_strip.cuh", "mbconv_fused.cuh", os.path.join("..", "..", "include", "adafocus_b200.h")]
+SOURCES = ["conv_gemm.cu", "gru_tc.cu", "stem_gemm.cu", "dwconv_tma.cu", "mbconv_fused.cu", "mbconv_rows.cu", "kernels.cu", "capi.cu"]
+HEADERS = ["ptx.cuh", "gru_tc.cuh", "conv_gemm.cuh", "stem_gemm.cuh", "kernels.cuh", "dwconv_tma.cuh", "dw_strip.cuh", "mbconv_fused.cuh", "mbconv_rows.cuh", os.path.join("..", "..", "include", "adafocus_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "gru_tc.cuh"
 #include "mbconv_fused.cuh"
+#include "mbconv_rows.cuh"
 #include "stem_gemm.cuh"
 
 namespace {
@@ -701,6 +702,82 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
     return fail(AF_ERR_CUDA, err);
   return dispatch(ctx, stream, "af_mbconv_fused",
                   [=](cudaStream_t s) { return af::launch_mbconv_fused(maps, p, sms, s); });
+}
+
+int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride) {
+  af::MrParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cexp = cexp; p.Cout = cout; p.S = stride;
+  return af::mbrows_plan(&p) ? 1 : 0;
+}
+
+int af_mbconv_rows_layout(int cexp, int spr, int32_t* nchunks, int16_t* lane_ch, int16_t* lane_kpos) {
+  if (nchunks == nullptr || lane_ch == nullptr || lane_kpos == nullptr)
+    return fail(AF_ERR_INVALID, "af_mbconv_rows_layout: null argument");
+  af::MrLayout lay;
+  if (!af::mbrows_layout(cexp, spr, &lay)) return fail(AF_ERR_INVALID, "af_mbconv_rows_layout: unsupported (cexp, spr)");
+  *nchunks = lay.nchunks;
+  memcpy(lane_ch, lay.lane_ch, sizeof(lay.lane_ch));
+  memcpy(lane_kpos, lay.lane_kpos, sizeof(lay.lane_kpos));
+  return AF_OK;
+}
+
+int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream) {
+  if (ctx == nullptr || d == nullptr) return fail(AF_ERR_INVALID, "af_mbconv_rows: null argument");
+  if (d->in == nullptr || d->w1 == nullptr || d->dwp == nullptr || d->w2 == nullptr || d->bias3 == nullptr ||
+      d->out == nullptr)
+    return fail(AF_ERR_INVALID, "af_mbconv_rows: null tensor");
+  if (d->residual != nullptr && (d->stride != 1 || d->res_stride % 8 != 0 || d->res_stride < d->cout))
+    return fail(AF_ERR_INVALID, "af_mbconv_rows: a residual needs stride 1 and res_stride % 8 == 0");
+  af::MrParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;
+  if (!af::mbrows_plan(&p)) return fail(AF_ERR_INVALID, "af_mbconv_rows: unsupported shape");
+  p.dwp = d->dwp;
+  p.bias3 = d->bias3;
+  p.residual = static_cast<const __half*>(d->residual);
+  p.res_stride = d->res_stride;
+  af::MrTensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string err;
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cin) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
+                                static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.RP), static_cast<cuuint32_t>(p.G), 1};
+    if (!encode_map(ctx, &maps.x, d->in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(p.lay.nchunks) * 128};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, 128};
+    if (!encode_map(ctx, &maps.w1, d->w1, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t kpad = static_cast<cuuint64_t>(p.lay.nchunks) * 128;
+    const cuuint64_t dims[2] = {kpad, static_cast<cuuint64_t>(p.cout_pad)};
+    const cuuint64_t strides[1] = {kpad * 2};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.cout_pad)};
+    if (!encode_map(ctx, &maps.w2, d->w2, 2, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+  }
+  {
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cout) * 2;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(p.Wo),
+                                static_cast<cuuint64_t>(p.Ho), static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t strides[3] = {pix_b, pix_b * p.Wo, pix_b * p.Wo * p.Ho};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.OWseg), static_cast<cuuint32_t>(p.OR * p.SPI), 1};
+    if (!encode_map(ctx, &maps.out, d->out, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
+    if (p.S == 1) {
+      const cuuint32_t box_rest[4] = {64, static_cast<cuuint32_t>(p.OWseg), static_cast<cuuint32_t>(p.G - 1), 1};
+      const cuuint32_t box_one[4] = {64, static_cast<cuuint32_t>(p.OWseg), 1, 1};
+      if (!encode_map(ctx, &maps.out_rest, d->out, 4, dims, strides, box_rest, &err)) return fail(AF_ERR_CUDA, err);
+      if (!encode_map(ctx, &maps.out_one, d->out, 4, dims, strides, box_one, &err)) return fail(AF_ERR_CUDA, err);
+    }
+  }
+  const int sms = ctx->sm_count;
+  return dispatch(ctx, stream, "af_mbconv_rows",
+                  [=](cudaStream_t s) { return af::launch_mbconv_rows(maps, p, sms, s); });
 }
 
 int af_stem_conv3x3s2_c32(af_ctx* ctx, const float* frames, const float* w27, const float* scale, const float* bias,

@@ -9,7 +9,7 @@ from ctypes import byref, c_void_p
 import torch
 
 from . import _lib
-from ._lib import AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6, ConvDesc, MbconvDesc, check
+from ._lib import AF_ACT_NONE, AF_ACT_RELU, AF_ACT_RELU6, ConvDesc, MbconvDesc, MbconvRowsDesc, check
 
 BLOCK_K = 64
 
@@ -188,6 +188,77 @@ def pack_mbconv(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, device=None
     d = device
     return PackedMbconv(e.w.to(d), e.bias.to(d), dw.contiguous().to(d), bias2.to(d), pj.w.to(d), pj.bias.to(d), cin,
                         cexp, cout, stride, bias_in_w1)
+
+
+class PackedMbconvRows:
+    """The same block in the layout of af_mbconv_rows (row-streaming kernel) for ONE strips-per-row value `spr`."""
+
+    def __init__(self, w1, dwp, w2, b3, cin, cexp, cout, stride, spr):
+        self.w1, self.dwp, self.w2, self.b3 = w1, dwp, w2, b3
+        self.cin, self.cexp, self.cout, self.stride, self.spr = cin, cexp, cout, stride, spr
+
+
+def mbconv_rows_spr(w, stride):
+    """Strips per row segment of af_mbconv_rows for an input of width w (None: width not handled)."""
+    if stride == 1:
+        return {14: 1, 28: 2, 56: 4}.get(int(w))
+    return {28: 2, 56: 4, 112: 4}.get(int(w))
+
+
+def mbconv_rows_supported(n, h, w, cin, cexp, cout, stride):
+    return bool(_lib.load().af_mbconv_rows_supported(int(n), int(h), int(w), int(cin), int(cexp), int(cout),
+                                                     int(stride)))
+
+
+def mbconv_rows_layout(cexp, spr):
+    """-> (nchunks, lane_ch int16 [3,128], lane_kpos int16 [3,128]) from af_mbconv_rows_layout, or None."""
+    lib = _lib.load()
+    nch = ctypes.c_int32(0)
+    lane_ch = torch.zeros(3, 128, dtype=torch.int16)
+    lane_kpos = torch.zeros(3, 128, dtype=torch.int16)
+    rc = lib.af_mbconv_rows_layout(int(cexp), int(spr), byref(nch), lane_ch.data_ptr(), lane_kpos.data_ptr())
+    if rc != 0:
+        return None
+    return nch.value, lane_ch, lane_kpos
+
+
+def pack_mbconv_rows(w_exp, s1, b1, w_dw, s2, b2, w_proj, s3, b3, stride, spr, device=None):
+    """Same arguments as pack_mbconv plus `spr`; returns a PackedMbconvRows on `device`, or None when the kernel has no
+    lane placement for (cexp, spr).  ReLU6(x) = 6 * sat(x / 6): 1/6 goes into the expand weights and both biases, 6 into
+    the project weights (include/adafocus_b200.h, af_mbconv_rows_desc)."""
+    device = device or w_exp.device
+    w_exp = host(w_exp).flatten(1).float()
+    w_proj = host(w_proj).flatten(1).float()
+    cexp, cin = w_exp.shape
+    cout = w_proj.shape[0]
+    if cin > 64 or cout > 64:
+        return None
+    lay = mbconv_rows_layout(cexp, spr)
+    if lay is None:
+        return None
+    nch, lane_ch, lane_kpos = lay
+    s1, b1, s2, b2, s3, b3 = (host(t).float() for t in (s1, b1, s2, b2, s3, b3))
+    we = w_exp * s1[:, None] / 6.0
+    wd = host(w_dw).reshape(cexp, 9).float() * s2[:, None]
+    wp = w_proj * s3[:, None] * 6.0
+    cp = round_up(cout, 16)
+    w1 = torch.zeros(nch * 128, 64, dtype=torch.float32)
+    dwp = torch.zeros(nch, 11, 128, dtype=torch.float32)
+    w2 = torch.zeros(cp, nch * 128, dtype=torch.float32)
+    for c in range(nch):
+        ch = lane_ch[c].long()
+        live = ch >= 0
+        idx = ch[live]
+        w1[c * 128:(c + 1) * 128][live, :cin] = we[idx]
+        dwp[c, :9][:, live] = wd[idx].t()
+        dwp[c, 9][live] = b1[idx] / 6.0
+        dwp[c, 10][live] = b2[idx] / 6.0
+        w2[:cout, c * 128 + lane_kpos[c].long()[live]] = wp[:, idx]
+    bias3 = torch.zeros(cp, dtype=torch.float32)
+    bias3[:cout] = b3
+    d = device
+    return PackedMbconvRows(w1.half().to(d), dwp.contiguous().to(d), w2.half().to(d), bias3.to(d), cin, cexp, cout,
+                            stride, spr)
 
 
 class Workspace:
@@ -436,6 +507,24 @@ class Engine:
         check(self.lib.af_mbconv_fused(self.h, byref(d), self._stream()), "af_mbconv_fused")
         self._count()
         self.keep(x, pm.w1, pm.b1, pm.dw, pm.b2, pm.w2, pm.b3, residual, out)
+        return out
+
+    def mbconv_rows(self, x, pr, residual=None):
+        """Row-streaming fused inverted-residual block: x NHWC fp16 (n,h,w,cin) contiguous -> (n,ho,wo,cout)."""
+        n, h, w, cin = x.shape
+        assert cin == pr.cin and x.is_contiguous() and mbconv_rows_spr(w, pr.stride) == pr.spr
+        s = pr.stride
+        ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+        out = self.empty((n, ho, wo, pr.cout), torch.float16)
+        d = MbconvRowsDesc()
+        d.in_, d.w1, d.dwp, d.w2, d.bias3 = x.data_ptr(), pr.w1.data_ptr(), pr.dwp.data_ptr(), pr.w2.data_ptr(), pr.b3.data_ptr()
+        d.out = out.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.n, d.h, d.w_, d.cin, d.cexp, d.cout, d.stride = n, h, w, cin, pr.cexp, pr.cout, s
+        d.res_stride = residual.stride(-2) if residual is not None else 0
+        check(self.lib.af_mbconv_rows(self.h, byref(d), self._stream()), "af_mbconv_rows")
+        self._count()
+        self.keep(x, pr.w1, pr.dwp, pr.w2, pr.b3, residual, out)
         return out
 
     def dwconv3x3(self, x, w9c, scale, bias, stride, act=AF_ACT_RELU6):

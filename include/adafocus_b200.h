@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AF_VERSION 200
+#define AF_VERSION 210
 
 typedef enum af_status {
   AF_OK = 0,
@@ -197,6 +197,34 @@ typedef struct af_mbconv_desc {
 } af_mbconv_desc;
 int af_mbconv_fused_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream);
+
+/* Row-streaming form of the same block for large batches (csrc/mbconv_rows.cuh): the expand GEMM runs transposed
+ * (TMEM lane = expanded channel, column = pixel), every thread of the depthwise warps owns one expanded channel, reads
+ * its image rows straight out of TMEM and rolls them through registers while the CTA walks down whole frames; the
+ * 6x expanded tensor touches neither HBM nor shared memory.  Shapes: cin, cout <= 64; stride 1 with w in {14, 28, 56};
+ * stride 2 with w in {28, 56, 112}; cexp % 16 == 0 with at most three 128-lane chunks (af_mbconv_rows_supported).
+ * The placement of expanded channels on TMEM lanes depends on cexp and on the number of 14-output column strips per
+ * row (spr = 1, 2 or 4: stride 1 -> w / 14, stride 2 -> min(w / 14, 4)); af_mbconv_rows_layout returns it so that the
+ * host packs
+ *   w1  : fp16 [nchunks*128][64]   row (chunk, lane) = W1[lane_ch] * bn_scale / 6, zero rows for lane_ch < 0
+ *   dwp : fp32 [nchunks][11][128]  per lane: 9 depthwise taps (BN scale folded), bias1 / 6, bias2 / 6
+ *   w2  : fp16 [ceil(cout/16)*16][nchunks*128]   column chunk*128 + lane_kpos = 6 * W2[:, lane_ch] * bn_scale
+ *   bias3: fp32 [ceil(cout/16)*16]
+ * (ReLU6 is evaluated as 6 * saturate(x / 6)).  lane_ch / lane_kpos: int16 [3][128]. */
+typedef struct af_mbconv_rows_desc {
+  const void* in;
+  const void* w1;
+  const float* dwp;
+  const void* w2;
+  const float* bias3;
+  const void* residual;
+  void* out;
+  int32_t n, h, w_, cin, cexp, cout, stride;
+  int64_t res_stride;
+} af_mbconv_rows_desc;
+int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
+int af_mbconv_rows_layout(int cexp, int spr, int32_t* nchunks, int16_t* lane_ch, int16_t* lane_kpos);
+int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream);
 
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).

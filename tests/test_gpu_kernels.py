@@ -351,6 +351,48 @@ def test_mbconv_fused(eng, cin, cexp, cout, stride, hw, n, res):
     assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3 * max(1.0, ref.abs().max().item())), err
 
 
+@pytest.mark.parametrize("cin,cexp,cout,stride,hw,n,res", [
+    (32, 96, 24, 2, 112, 3, False), (24, 144, 24, 1, 56, 5, True), (24, 144, 32, 2, 56, 3, False),
+    (32, 192, 32, 1, 28, 7, True), (32, 192, 64, 2, 28, 4, False), (64, 384, 64, 1, 14, 9, True),
+    (32, 96, 24, 2, 112, 160, False), (24, 144, 24, 1, 56, 310, True), (24, 144, 32, 2, 56, 301, False),
+    (32, 192, 32, 1, 28, 450, True), (32, 192, 64, 2, 28, 333, False), (64, 384, 64, 1, 14, 600, True),
+    (16, 96, 16, 1, 28, 20, True), (8, 48, 16, 2, 28, 11, False), (64, 384, 64, 1, 14, 1, False),
+    (32, 192, 32, 1, 28, 1, True), (24, 144, 24, 1, 56, 1, True)])
+def test_mbconv_rows(eng, cin, cexp, cout, stride, hw, n, res):
+    """Row-streaming fused inverted-residual block (transposed expand GEMM, depthwise out of TMEM) against the three
+    torch convolutions: every MobileNet-V2 block shape it takes, fewer frames than SMs, frame counts that do not divide
+    by the grid (CTAs with different numbers of frames, frame-boundary steps, the closing step), single frames."""
+    from adafocus_b200.engine import mbconv_rows_spr, mbconv_rows_supported, pack_mbconv_rows
+    assert mbconv_rows_supported(n, hw, hw, cin, cexp, cout, stride)
+    torch.manual_seed(cexp + hw)
+    x = torch.randn(n, hw, hw, cin, device=DEV).half()
+    w1 = torch.randn(cexp, cin, device=DEV) / math.sqrt(cin)
+    wd = torch.randn(cexp, 1, 3, 3, device=DEV) / 3
+    w2 = torch.randn(cout, cexp, device=DEV) / math.sqrt(cexp)
+    s1, b1 = torch.rand(cexp, device=DEV) + 0.5, torch.randn(cexp, device=DEV) * 0.2
+    s2, b2 = torch.rand(cexp, device=DEV) + 0.5, torch.randn(cexp, device=DEV) * 0.2
+    s3, b3 = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV) * 0.2
+    pr = pack_mbconv_rows(w1, s1, b1, wd, s2, b2, w2, s3, b3, stride, mbconv_rows_spr(hw, stride), device=DEV)
+    assert pr is not None
+    out = eng.mbconv_rows(x, pr, residual=x if res else None)
+    torch.cuda.synchronize()
+    xf = x.float().permute(0, 3, 1, 2)
+    # the kernel folds BN scale and the 1/6, 6 of its ReLU6 form into fp16 weights: mirror that rounding
+    w1q = (w1 * s1[:, None] / 6).half().float() * 6
+    w2q = (w2 * s3[:, None] * 6).half().float() / 6
+    e = (F.conv2d(xf, w1q[:, :, None, None]) + b1.view(1, -1, 1, 1)).clamp(0, 6)
+    wdq = wd * s2.view(-1, 1, 1, 1)
+    d = (F.conv2d(e, wdq, None, stride, 1, 1, cexp) + b2.view(1, -1, 1, 1)).clamp(0, 6)
+    d = (d / 6).half().float() * 6
+    ref = F.conv2d(d, w2q[:, :, None, None]) + b3.view(1, -1, 1, 1)
+    if res:
+        ref = ref + xf
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    err = (out.float() - ref).abs().max().item()
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3 * max(1.0, ref.abs().max().item())), err
+
+
 @pytest.mark.parametrize("hw", [64, 72, 9])
 def test_maxpool_bit_exact(eng, hw):
     x = torch.randn(4, hw, hw, 64, device=DEV).half()
