@@ -91,6 +91,7 @@ SIGNATURES = {
     "af_mbconv_rows_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "af_mbconv_rows_layout": (c_int, [c_int, c_int, POINTER(c_int32), c_void_p, c_void_p]),
     "af_mbconv_rows": (c_int, [c_void_p, POINTER(MbconvRowsDesc), c_void_p]),
+    "af_debug_mbconv_rows_prof": (c_int, [c_void_p]),
     "af_dwconv3x3_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "af_maxpool3x3s2_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -704,6 +704,14 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
                   [=](cudaStream_t s) { return af::launch_mbconv_fused(maps, p, sms, s); });
 }
 
+static long long* g_mbrows_prof = nullptr;
+/* debug hook (tools/mbrows_debug.py): device buffer of 32 x 8 int64 that CTA 0 of af_mbconv_rows fills with per-warp
+ * cycle counters (total, wait for E, TMEM load, wait for an A2 buffer | expand issuers: total, wait X, wait slot) */
+int af_debug_mbconv_rows_prof(void* buf) {
+  g_mbrows_prof = static_cast<long long*>(buf);
+  return AF_OK;
+}
+
 int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride) {
   af::MrParams p;
   memset(&p, 0, sizeof(p));
@@ -737,6 +745,7 @@ int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream) {
   p.bias3 = d->bias3;
   p.residual = static_cast<const __half*>(d->residual);
   p.res_stride = d->res_stride;
+  p.prof = g_mbrows_prof;
   af::MrTensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   std::string err;

@@ -15,13 +15,13 @@ namespace {
 
 constexpr int kD2Col = 384;            // TMEM column of the project accumulators (2 x 64 columns)
 constexpr int kFirstDwWarp = 8;        // warp 0: TMA producer, 1: expand MMAs, 2: project MMAs, 3: idle, 4-7: epilogue, 8..: depthwise
-constexpr int kMaxSlots = 24;          // E ring: one slot = one image row segment (RP columns) of one chunk; 384 columns
+constexpr int kSlots = 6;              // E ring: six 64-column slots (64 / RP image rows of one chunk each); 384 columns
 constexpr int kEpiBarrier = 1;
 
 struct __align__(8) MrCtrl {
   uint64_t x_full[3], x_empty[3];
   uint64_t w_full;
-  uint64_t e_full[kMaxSlots], e_free[kMaxSlots];   // slot s belongs to chunk s % nchunks
+  uint64_t e_full[kSlots], e_free[kSlots];   // slot s belongs to chunk s % nchunks
   uint64_t a2_full[kMrMaxBufs], a2_free[kMrMaxBufs];
   uint64_t d2_full[2], d2_free[2];
   uint32_t tmem_base;
@@ -98,21 +98,27 @@ __device__ __forceinline__ void dw_row_s1(const float (&r0)[16], const float (&r
   }
 }
 
-// stride 2: one output row (a, c, d) of 7 columns; a = input row 2r-1, c = 2r, d = 2r+1
-__device__ __forceinline__ void dw_row_s2(const float (&a)[16], const float (&c)[16], const float (&d)[16],
-                                          const float (&w)[9], float b2, uint32_t ob) {
+// stride 2: one output row (a, c, d) of 7 columns; a = input row 2r-1, c = 2r, d = 2r+1.  Two phases, so that the
+// taps of rows a and c run while the GEMM of row d may still be in flight (the E ring holds three rows per chunk).
+__device__ __forceinline__ void dw_row_s2_ac(const float (&a)[16], const float (&c)[16], const float (&w)[9], float b2,
+                                             float (&o)[7]) {
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
-    float o = fmaf(a[2 * j], w[0], b2);
-    o = fmaf(a[2 * j + 1], w[1], o);
-    o = fmaf(a[2 * j + 2], w[2], o);
-    o = fmaf(c[2 * j], w[3], o);
-    o = fmaf(c[2 * j + 1], w[4], o);
-    o = fmaf(c[2 * j + 2], w[5], o);
-    o = fmaf(d[2 * j], w[6], o);
-    o = fmaf(d[2 * j + 1], w[7], o);
-    o = fma_sat(d[2 * j + 2], w[8], o);
-    st_half((ob ^ static_cast<uint32_t>((j & 7) << 4)) + j * 128, o);
+    float v = fmaf(a[2 * j], w[0], b2);
+    v = fmaf(a[2 * j + 1], w[1], v);
+    v = fmaf(a[2 * j + 2], w[2], v);
+    v = fmaf(c[2 * j], w[3], v);
+    v = fmaf(c[2 * j + 1], w[4], v);
+    o[j] = fmaf(c[2 * j + 2], w[5], v);
+  }
+}
+__device__ __forceinline__ void dw_row_s2_d(const float (&d)[16], const float (&w)[9], const float (&o)[7], uint32_t ob) {
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    float v = fmaf(d[2 * j], w[6], o[j]);
+    v = fmaf(d[2 * j + 1], w[7], v);
+    v = fma_sat(d[2 * j + 2], w[8], v);
+    st_half((ob ^ static_cast<uint32_t>((j & 7) << 4)) + j * 128, v);
   }
 }
 
@@ -129,7 +135,9 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_dw_warps = 4 * p.lay.WQ;
   const int nch = p.lay.nchunks;
-  const int NSc = (384 / p.RP) / nch;                     // E ring slots (rows in flight) per chunk
+  const int NSc = kSlots / nch;                           // E ring slots per chunk (6, 3 or 2)
+  const int RPI = 64 / p.RP;                              // image rows per slot: 1, 2 or 4
+  const int g_log2 = p.G == 2 ? 1 : (p.G == 4 ? 2 : 3);
 
   // contiguous range of frame segments of this CTA
   const int units = p.N * p.segs;
@@ -148,7 +156,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       mbar_init(&ctrl->x_empty[i], nch > 1 ? 2 : 1);      // one commit per expand issuer warp
     }
     mbar_init(&ctrl->w_full, 1);
-    for (int i = 0; i < kMaxSlots; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       mbar_init(&ctrl->e_full[i], 1);
       mbar_init(&ctrl->e_free[i], static_cast<uint32_t>(p.lay.warps[i % nch]));
     }
@@ -217,41 +225,59 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       }
     }
   } else if (warp == 1 || (warp == 3 && nch > 1)) {
-    // ============================ expand MMA issuers: one GEMM per (input row, chunk) into the E ring ============================
-    // E[slot] (128 lanes x RP columns) = W1[chunk] * X[row]^T; chunk c owns slots c, c + nch, ..: NSc rows of every
-    // chunk are in flight, so the GEMM of a row is issued while the depthwise warps work two or more rows behind it.
-    // Warp 1 issues chunk 0 (and 2), warp 3 chunk 1: the issue stream of ONE warp (~20 instructions per GEMM, one
-    // instruction every few cycles next to the depthwise warps of its scheduler) was what bounded the kernel.
+    // ============================ expand MMA issuers: one GEMM per (64 pixels = RPI image rows, chunk) ============================
+    // E[slot] (128 lanes x 64 columns) = W1[chunk] * X[rows]^T; chunk c owns slots c, c + nch, ..: NSc slots of every
+    // chunk are in flight, so a GEMM is issued while the depthwise warps still work on the slots before it.
+    // Warp 1 issues chunks 0 and 2, warp 3 chunk 1: a single issuing warp spends ~500 cycles of dependent instruction
+    // latency per GEMM next to the busy depthwise warps of its scheduler, which bounded the first version.
     const int c_first = warp == 1 ? 0 : 1, c_step = nch > 1 ? 2 : 1;
-    const uint32_t idesc1 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.RP));
-    const int G = p.G, XS = p.XS, k1 = p.k1steps;
-    const uint32_t row_lo = static_cast<uint32_t>(p.RP * 128) >> 4;        // descriptor step between input rows
-    const uint32_t slot_cols = static_cast<uint32_t>(p.RP);
+    const uint32_t idesc1 = make_idesc_f16_f32(128, 64);
+    const int IPS = p.G / RPI, XS = p.XS;                                    // items per step
+    const uint32_t k1 = static_cast<uint32_t>(p.k1steps);
+    const uint32_t item_lo = static_cast<uint32_t>(64 * 128) >> 4;           // descriptor step between items of a stage
     const uint32_t x_lo0 = smem_desc_lo(smem_u32(s_x));
     const uint32_t w_lo0 = smem_desc_lo(smem_u32(s_w1));
+    const uint32_t full0 = smem_u32(&ctrl->e_full[0]), free0 = smem_u32(&ctrl->e_free[0]);
+    const uint32_t ring_slots = static_cast<uint32_t>(NSc * nch);
     wait_sleep(&ctrl->w_full, 0);
     tc_fence_after();
-    int stage = 0, j = 0;
+    int stage = 0;
+    uint32_t row_slot = 0;          // first slot (chunk 0) of the current ring position
     uint32_t ph = 0, fph = 0;       // fph: parity that says "the previous use of this slot has been released"
     bool first_lap = true;
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long prof_x = 0, prof_f = 0, prof_m = 0;
+    const long long prof_t0 = prof_on ? clock64() : 0;
     for (int t = 0; t < T; ++t) {
+      const long long cx0 = prof_on ? clock64() : 0;
       wait_sleep(&ctrl->x_full[stage], ph);
+      if (prof_on) prof_x += clock64() - cx0;
       uint32_t lb = x_lo0 + static_cast<uint32_t>(stage) * (16384u >> 4);
-      for (int g = 0; g < G; ++g, lb += row_lo) {
+      for (int g = 0; g < IPS; ++g, lb += item_lo) {
         for (int c = c_first; c < nch; c += c_step) {
-          const int slot = c + nch * j;
-          if (!first_lap) wait_spin(&ctrl->e_free[slot], fph);
+          const uint32_t slot = row_slot + static_cast<uint32_t>(c);
+          const long long cf0 = prof_on ? clock64() : 0;
+          if (!first_lap) {
+            const uint32_t fb = free0 + slot * 8u;
+            uint32_t done;
+            do {
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                  : "=r"(done)
+                  : "r"(fb), "r"(fph)
+                  : "memory");
+            } while (!done);
+          }
+          const long long cf1 = prof_on ? clock64() : 0;
+          if (prof_on) prof_f += cf1 - cf0;
           tc_fence_after();
-          const uint32_t la = w_lo0 + static_cast<uint32_t>(c) * (16384u >> 4);
-          const uint32_t d = tmem_base + static_cast<uint32_t>(slot) * slot_cols;
-          umma_f16_ss_lo_elect(d, la, lb, idesc1, 0u);
-          if (k1 > 1) umma_f16_ss_lo_elect(d, la + 2u, lb + 2u, idesc1, 1u);
-          if (k1 > 2) umma_f16_ss_lo_elect(d, la + 4u, lb + 4u, idesc1, 1u);
-          if (k1 > 3) umma_f16_ss_lo_elect(d, la + 6u, lb + 6u, idesc1, 1u);
-          umma_commit_elect(&ctrl->e_full[slot]);
+          umma_group_commit_elect(tmem_base + slot * 64u, w_lo0 + static_cast<uint32_t>(c) * (16384u >> 4), lb, idesc1, k1,
+                                  full0 + slot * 8u);
+          if (prof_on) prof_m += clock64() - cf1;
         }
-        if (++j == NSc) {
-          j = 0;
+        row_slot += static_cast<uint32_t>(nch);
+        if (row_slot == ring_slots) {
+          row_slot = 0;
           if (first_lap) first_lap = false;
           else fph ^= 1u;
         }
@@ -261,6 +287,12 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
         stage = 0;
         ph ^= 1u;
       }
+    }
+    if (prof_on && lane == 0) {
+      p.prof[warp * 8 + 0] = clock64() - prof_t0;
+      p.prof[warp * 8 + 1] = prof_x;
+      p.prof[warp * 8 + 2] = prof_f;
+      p.prof[warp * 8 + 3] = prof_m;
     }
   } else if (warp == 2) {
     // ============================ project MMA issuer: D2[item] = sum over chunks A2[chunk] * W2[chunk]^T ============================
@@ -402,7 +434,6 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
     const uint32_t kcol = static_cast<uint32_t>((kpos >> 6) * 16384 + (((kpos & 63) >> 3) << 4) + (kpos & 7) * 2);
     const uint32_t e_col0 = tmem_base + lane_sel + static_cast<uint32_t>(strip * 14);
     const uint32_t smem_base = smem_u32(smem);
-    const int g_log2 = p.G == 2 ? 1 : (p.G == 4 ? 2 : 3);
     const bool last_strip = strip == p.SPR - 1;
 
     // per-step state (set by the first row of a step)
@@ -423,18 +454,25 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
                 static_cast<uint32_t>((sub * 64 + strip * 16) * 128) + kcol;
       if (sub == 0) wait_spin(&ctrl->a2_free[a2_buf], ((static_cast<uint32_t>(ts) >> 1) & 1u) ^ 1u);
     };
-    // next input row of this warp's chunk: wait for its GEMM, read the strip, hand the slot back
+    // next input row of this warp's chunk: wait for its GEMM (first row of a slot), read the strip, hand the slot back
+    // after its last row
+    int e_ri = 0;
     auto next_row = [&](bool zero_last, bool zero_row, float (&r)[16]) {
       const int slot = chunk + nch * e_j;
-      wait_spin(&ctrl->e_full[slot], e_ph);
-      tc_fence_after();
-      load_row(e_col0 + static_cast<uint32_t>(slot * p.RP), b1, zero_first, zero_last, zero_row, r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctrl->e_free[slot]);
-      if (++e_j == NSc) {
-        e_j = 0;
-        e_ph ^= 1u;
+      if (e_ri == 0) {
+        wait_spin(&ctrl->e_full[slot], e_ph);
+        tc_fence_after();
+      }
+      load_row(e_col0 + static_cast<uint32_t>(slot * 64 + e_ri * p.RP), b1, zero_first, zero_last, zero_row, r);
+      if (++e_ri == RPI) {
+        e_ri = 0;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->e_free[slot]);
+        if (++e_j == NSc) {
+          e_j = 0;
+          e_ph ^= 1u;
+        }
       }
     };
     auto step_end = [&]() {
@@ -483,9 +521,11 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) a[i] = 0.f;        // input row -1 of a new frame
         }
+        float o[7];
         next_row(false, false, c);
+        dw_row_s2_ac(a, c, w, b2, o);
         next_row(false, false, d);
-        dw_row_s2(a, c, d, w, b2, a2_base + static_cast<uint32_t>(pi * p.RP * 128));
+        dw_row_s2_d(d, w, o, a2_base + static_cast<uint32_t>(pi * p.RP * 128));
         if (pi == PPS - 1) step_end();
       };
       for (int pp = 0; pp < P; pp += 2) {

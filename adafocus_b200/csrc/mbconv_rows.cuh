@@ -57,6 +57,7 @@ struct MrParams {
   const float* bias3;            // [cout_pad]
   const __half* residual;        // NHWC (N, H, W, Cout) with pixel stride res_stride, or nullptr (stride 1 only)
   long long res_stride;
+  long long* prof;               // debug: per-warp cycle counters of CTA 0 ([warp][8]), or nullptr
   int off_w1, off_w2, off_a2, off_out, off_ctrl, smem;
 };
 

@@ -54,6 +54,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Wait with a suspend-time hint: the hardware parks the warp (no issue slots taken from the other warps of its
+// scheduler) until the phase completes or `ns` nanoseconds have passed.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (ok == 0);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -224,6 +240,41 @@ __device__ __forceinline__ void umma_f16_ss_lo_elect(uint32_t tmem_d, uint32_t l
       "}\n"
       :
       : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+// One accumulator tile in one go: k_steps (1..4) MMAs over consecutive 16-wide K slices (32 B apart in both operand
+// tiles), the first one overwriting D, then a commit on `bar_addr`; a single election for the whole group.
+__device__ __forceinline__ void umma_group_commit_elect(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc,
+                                                        uint32_t k_steps, uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, p2, p3, p4, pt, pf;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.eq.u32 pt, %4, %4;\n\t"
+      "setp.ne.u32 pf, %4, %4;\n\t"
+      "setp.gt.u32 p2, %4, 1;\n\t"
+      "setp.gt.u32 p3, %4, 2;\n\t"
+      "setp.gt.u32 p4, %4, 3;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "and.pred p3, p3, pe;\n\t"
+      "and.pred p4, p4, pe;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pf;\n\t"
+      "add.u64 da, da, 2;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u64 da, da, 2;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u64 da, da, 2;\n\t"
+      "add.u64 db, db, 2;\n\t"
+      "@p4 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(k_steps), "r"(kDescHiSw128), "r"(bar_addr)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {

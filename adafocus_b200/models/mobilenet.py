@@ -10,7 +10,8 @@ import torch
 from torch import nn
 
 from ..packcache import cached_runner
-from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_supported, pack_conv, pack_mbconv,
+from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_rows_spr, mbconv_rows_supported,
+                      mbconv_supported, pack_conv, pack_mbconv, pack_mbconv_rows,
                       pack_stem)
 
 # Experiment knob: blocks whose input is smaller than this run unfused (1x1 conv -> depthwise -> 1x1 conv).  Measured
@@ -108,6 +109,31 @@ class _PackState:
         self.probes = ()
 
 
+_ROWS_MODE = os.environ.get("AF_MBROWS", "auto")      # "0": never, "force": whenever supported, "auto": heuristic below
+
+
+def _rows_choice(eng, e, y):
+    """The row-streaming packing of block e for input y (N,H,W,C), or None to use the tiled kernel.  The row kernel gives
+    every CTA whole frames: it needs at least one frame (segment) per SM; with five depthwise warps per lane quarter
+    (cexp = 144 at stride 1) its 72-register budget spills and the tiled kernel stays faster (profiles/README.md)."""
+    if _ROWS_MODE == "0" or not e["rows"]:
+        return None
+    n, h, w, cin = y.shape
+    if h != w:
+        return None
+    pr = e["rows"].get(mbconv_rows_spr(w, e["stride"]))
+    if pr is None or not mbconv_rows_supported(n, h, w, cin, pr.cexp, pr.cout, pr.stride):
+        return None
+    if _ROWS_MODE == "force":
+        return pr
+    units = n * (2 if (pr.stride == 2 and w == 112) else 1)
+    if units < eng.ctx.sm_count:
+        return None
+    if pr.stride == 1 and pr.cexp % 128 == 16:
+        return None
+    return pr
+
+
 def _pack_state(module):
     st = module.__dict__.get("_af_pack_state")
     if st is None:
@@ -200,12 +226,17 @@ class MobileNetV2Runner:
         self.fuse_blocks = os.environ.get("AF_NO_MBCONV_FUSED") is None
         for e in self.blocks:
             e["fused"] = None
+            e["rows"] = {}
             if self.fuse_blocks and e["_exp"] is not None and e["project"] is not None:
                 we, se, be = e["_exp"]
                 wp, sp, bp = e["_proj"]
                 if mbconv_supported(1, 32, 32, we.shape[1], we.shape[0], wp.shape[0], e["stride"]):
                     e["fused"] = pack_mbconv(we, se, be, e["_dw_raw"], e["_dw_sb"][0], e["_dw_sb"][1], wp, sp, bp,
                                              e["stride"], device=dev)
+                    # row-streaming form (large batches), one packing per strips-per-row value the kernel has a lane
+                    # placement for
+                    e["rows"] = {spr: pack_mbconv_rows(we, se, be, e["_dw_raw"], e["_dw_sb"][0], e["_dw_sb"][1], wp, sp,
+                                                       bp, e["stride"], spr, device=dev) for spr in (1, 2, 4)}
         for e in self.blocks:
             e.pop("_proj"), e.pop("_exp"), e.pop("_dw_raw"), e.pop("_dw_sb")
         cl, bl = f[-1][0], f[-1][1]
@@ -241,6 +272,13 @@ class MobileNetV2Runner:
             y = x
             if tsm is not None and e["res"]:
                 y = eng.tsm_shift(y, tsm[0], y.shape[-1] // tsm[1])
+            pr = _rows_choice(eng, e, y)
+            if pr is not None:
+                x = eng.mbconv_rows(y, pr, residual=inp if e["res"] else None)
+                if y is not inp:
+                    eng.release(y)
+                eng.release(inp)
+                continue
             if (e["fused"] is not None and y.shape[1] >= _FUSE_MIN_HW
                     and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"])):
                 x = eng.mbconv(y, e["fused"], residual=inp if e["res"] else None)

@@ -225,6 +225,8 @@ typedef struct af_mbconv_rows_desc {
 int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_rows_layout(int cexp, int spr, int32_t* nchunks, int16_t* lane_ch, int16_t* lane_kpos);
 int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream);
+/* debug: device buffer (32 x 8 int64) that CTA 0 of af_mbconv_rows fills with per-warp cycle counters, or NULL */
+int af_debug_mbconv_rows_prof(void* buf);
 
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from
  * the fp32 NCHW frames to NHWC fp16 on the FMA pipes (K = 27 is too thin for a tensor-core k-block).
