@@ -213,8 +213,8 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       const bool is_flush = flush && t == T - 1;
       const int n = is_flush ? p.N : unit >> (p.segs - 1);   // the closing step reads past the batch: all zeros
       const int seg = is_flush ? 0 : unit & (p.segs - 1);    // segs is 1 or 2
-      mbar_arrive_expect_tx_elect(&ctrl->x_full[stage], 16384u);
-      tma_load_4d_elect(s_x + stage * 16384, &maps.x, &ctrl->x_full[stage], 0, seg * p.OWseg * S - 1, k * p.G, n);
+      mbar_arrive_expect_tx_elect(&ctrl->x_full[stage], static_cast<uint32_t>(p.x_stage));
+      tma_load_4d_elect(s_x + stage * p.x_stage, &maps.x, &ctrl->x_full[stage], 0, seg * p.OWseg * S - 1, k * p.G, n);
       if (++stage == p.XS) {
         stage = 0;
         ph ^= 1u;
@@ -252,7 +252,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       const long long cx0 = prof_on ? clock64() : 0;
       wait_sleep(&ctrl->x_full[stage], ph);
       if (prof_on) prof_x += clock64() - cx0;
-      uint32_t lb = x_lo0 + static_cast<uint32_t>(stage) * (16384u >> 4);
+      uint32_t lb = x_lo0 + static_cast<uint32_t>(stage) * (static_cast<uint32_t>(p.x_stage) >> 4);
       for (int g = 0; g < IPS; ++g, lb += item_lo) {
         for (int c = c_first; c < nch; c += c_step) {
           const uint32_t slot = row_slot + static_cast<uint32_t>(c);
@@ -312,7 +312,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
         const uint32_t sub_b = static_cast<uint32_t>(p.cout_pad) * 128u;
         for (int ks = 0; ks < p.lay.ksteps[c]; ++ks) {
           const uint32_t sub = static_cast<uint32_t>(ks >> 2), kk = static_cast<uint32_t>(ks & 3);
-          umma_f16_ss_lo_elect(d2, la + ((sub * 16384u) >> 4) + kk * 2u, lb + ((sub * sub_b) >> 4) + kk * 2u, idesc2,
+          umma_f16_ss_lo_elect(d2, la + ((sub * static_cast<uint32_t>(p.a2_sub)) >> 4) + kk * 2u, lb + ((sub * sub_b) >> 4) + kk * 2u, idesc2,
                                (c | ks) != 0 ? 1u : 0u);
         }
         umma_commit_elect(&ctrl->a2_free[buf]);
@@ -431,7 +431,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
     const float b2 = __ldg(p.dwp + (chunk * 11 + 10) * 128 + l128);
     const int kpos = p.lay.lane_kpos[chunk][l128];
     // byte offset of this lane's K column inside an A2 buffer (bits 4-6 = 16-byte chunk, XORed with pixel & 7 per store)
-    const uint32_t kcol = static_cast<uint32_t>((kpos >> 6) * 16384 + (((kpos & 63) >> 3) << 4) + (kpos & 7) * 2);
+    const uint32_t kcol = static_cast<uint32_t>((kpos >> 6) * p.a2_sub + (((kpos & 63) >> 3) << 4) + (kpos & 7) * 2);
     const uint32_t e_col0 = tmem_base + lane_sel + static_cast<uint32_t>(strip * 14);
     const uint32_t smem_base = smem_u32(smem);
     const bool last_strip = strip == p.SPR - 1;
@@ -651,20 +651,28 @@ bool mbrows_plan(MrParams* p) {
   p->SPR = wo_seg / p->OW;
   if (p->SPR != 1 && p->SPR != 2 && p->SPR != 4) return false;
   p->RP = p->SPR * 16;
-  p->G = 128 / p->RP;
   p->OWseg = wo_seg;
-  p->OR = p->S == 1 ? p->G : p->G / 2;
-  p->SPF = (p->H + p->G - 1) / p->G;
-  p->SPI = (p->S == 2 && p->OR * p->RP == 64 && p->SPF % 2 == 0) ? 2 : 1;
   p->k1steps = (p->Cin + 15) / 16;
   p->cout_pad = (p->Cout + 15) / 16 * 16;
   if (!mbrows_layout(p->Cexp, p->SPR, &p->lay)) return false;
   const int nc = p->lay.nchunks;
-  // two A2 buffers per chunk (a ring shared by all chunks would serialise the chunks inside a step: the warps of the
-  // last chunk could only start once the project GEMM of the first one has drained its buffer)
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    const int xs = attempt == 0 ? 3 : 2;
-    int off = xs * 16384;
+  // Steps of 128 pixels (G = 128 / RP rows); when the two A2 buffers per chunk do not fit next to the weights (three
+  // chunks at 14 x 14), steps of 64 pixels: the project GEMM then reads 128-row operand tiles whose upper half is
+  // whatever follows in shared memory -- rows of M do not mix, those accumulator rows are never stored.
+  // (One ring of buffers shared by all chunks would serialise the chunks inside a step: the warps of the last chunk
+  // could only start once the project GEMM of the first one has drained its buffer.)
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    const int xs = (attempt & 1) == 0 ? 3 : 2;
+    p->G = (attempt < 2 ? 128 : 64) / p->RP;
+    if (p->G < 64 / p->RP || p->G < 2) continue;
+    if (attempt >= 2 && p->S == 2) continue;
+    p->OR = p->S == 1 ? p->G : p->G / 2;
+    p->SPF = (p->H + p->G - 1) / p->G;
+    p->SPI = (p->S == 2 && p->OR * p->RP == 64 && p->SPF % 2 == 0) ? 2 : 1;
+    p->x_stage = p->G * p->RP * 128;
+    p->a2_sub = (p->S == 1 ? p->G * p->RP : 128) * 128;
+    int off = xs * p->x_stage;
+    off = (off + 1023) & ~1023;
     p->off_w1 = off;
     off += nc * 16384;
     p->off_w2 = off;
@@ -679,7 +687,7 @@ bool mbrows_plan(MrParams* p) {
       for (int par = 0; par < 2; ++par) {
         p->a2_off[c * 2 + par] = off;
         p->a2_cnt[c * 2 + par] = p->lay.warps[c] * p->SPI;
-        off += p->lay.a2_bytes[c];
+        off += (p->lay.a2_bytes[c] >> 14) * p->a2_sub;
       }
     p->off_out = off;
     off += 16384;

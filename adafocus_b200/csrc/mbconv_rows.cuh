@@ -8,7 +8,8 @@
 // has to hand tiles over.  Its fp16 result is written as the K-major A operand of the project GEMM
 // (D2[pixel, cout] += A2 * W2^T), whose epilogue adds bias (+ residual) and stores through TMA.
 //
-//   TMA        : G = 128 / RP input rows x RP pixels x 64 channels per step -> smem (B operand of the expand GEMM)
+//   TMA        : G input rows (128 / RP, or 64 / RP when shared memory is short) x RP pixels x 64 channels per step
+//                -> smem (B operand of the expand GEMM)
 //   tcgen05.mma: E[chunk] (128 lanes x 128 columns, fp32) = W1[chunk] * X^T      one MMA group per 128-lane chunk
 //   dw warps   : warp = (lane quarter, chunk, 14-output column strip): rows -> +bias, ReLU6 -> 3x3 -> +bias, ReLU6 -> A2
 //   tcgen05.mma: D2 += A2[chunk] * W2[chunk]^T
@@ -50,6 +51,7 @@ struct MrParams {
   int SPF, SPI;                  // steps per frame segment, steps per A2 item (2 when a step fills half of the 128 rows)
   int k1steps, cout_pad;
   int XS, NB;                    // input stages, A2 buffers (two per chunk)
+  int x_stage, a2_sub;           // bytes per input stage (G * RP pixels), bytes per 64-channel A2 sub-tile (G * RP rows)
   int a2_off[kMrMaxBufs], a2_cnt[kMrMaxBufs];
   int w2_off[kMrMaxChunks];
   MrLayout lay;

@@ -357,7 +357,8 @@ def test_mbconv_fused(eng, cin, cexp, cout, stride, hw, n, res):
     (32, 96, 24, 2, 112, 160, False), (24, 144, 24, 1, 56, 310, True), (24, 144, 32, 2, 56, 301, False),
     (32, 192, 32, 1, 28, 450, True), (32, 192, 64, 2, 28, 333, False),
     (16, 96, 16, 1, 28, 20, True), (8, 48, 16, 2, 28, 11, False),
-    (32, 192, 32, 1, 28, 1, True), (24, 144, 24, 1, 56, 1, True)])
+    (32, 192, 32, 1, 28, 1, True), (24, 144, 24, 1, 56, 1, True),
+    (64, 384, 64, 1, 14, 9, True), (64, 384, 64, 1, 14, 600, True), (64, 384, 64, 1, 14, 1, False)])
 def test_mbconv_rows(eng, cin, cexp, cout, stride, hw, n, res):
     """Row-streaming fused inverted-residual block (transposed expand GEMM, depthwise out of TMEM) against the three
     torch convolutions: every MobileNet-V2 block shape it takes, fewer frames than SMs, frame counts that do not divide

@@ -93,10 +93,6 @@ def prof(names):
         lib.af_debug_mbconv_rows_prof(None)
         b = buf.cpu()
         print(name, "expand issuers (total, wait X, wait slot, fence+MMA group+commit):", b[1, :4].tolist(), b[3, :4].tolist())
-        for w in range(8, 32):
-            if b[w, 0] > 0:
-                tot = b[w, 0].item()
-                print(f"  dw warp {w}: total {tot}  wait E {100 * b[w, 1].item() / tot:.0f}%  TMEM load {100 * b[w, 2].item() / tot:.0f}%  wait A2 {100 * b[w, 3].item() / tot:.0f}%")
 
 
 if len(sys.argv) > 1 and sys.argv[1] == "prof":
