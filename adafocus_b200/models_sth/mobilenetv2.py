@@ -6,9 +6,9 @@ import torch
 from torch import nn
 
 from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_supported, pack_conv,
-                      pack_conv_split, pack_mbconv, pack_stem)
+                      pack_conv_split, pack_mbconv, pack_mbconv_rows, pack_stem)
 from ..packcache import cached_runner
-from ..models.mobilenet import _FUSE_MIN_HW, _MBV2_SETTING, MobileNetV2Runner, _param_key
+from ..models.mobilenet import _FUSE_MIN_HW, _MBV2_SETTING, MobileNetV2Runner, _param_key, _rows_choice
 
 
 def conv_bn(inp, oup, stride):
@@ -112,11 +112,15 @@ class SthGlancerRunner(MobileNetV2Runner):
             s, b = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             e["project"] = pack_conv(pw.weight, s, b, act=AF_ACT_NONE, device=dev, fold_scale=e["res"])
             e["fused"] = None
+            e["rows"] = {}
             if (fuse and blk.expand != 1 and
                     mbconv_supported(1, 32, 32, cv.weight.shape[1], cv.weight.shape[0], pw.weight.shape[0], blk.stride)):
                 # expand -> depthwise -> project as one launch (adafocus_b200/csrc/mbconv_fused.cu)
                 e["fused"] = pack_mbconv(cv.weight, s1, b1, dw.weight, dw_s, dw_b, pw.weight, s, b, blk.stride,
                                          device=dev)
+                # row-streaming form for large batches (adafocus_b200/csrc/mbconv_rows.cu)
+                e["rows"] = {spr: pack_mbconv_rows(cv.weight, s1, b1, dw.weight, dw_s, dw_b, pw.weight, s, b, blk.stride,
+                                                   spr, device=dev) for spr in (1, 2, 4)}
             self.blocks.append(e)
         cl, bl = f[-1][0], f[-1][1]
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
@@ -134,6 +138,13 @@ class SthGlancerRunner(MobileNetV2Runner):
             inp, y = x, x
             if e["shift"]:
                 y = eng.tsm_shift(x, self.tsm[0], x.shape[-1] // self.tsm[1])
+            pr = _rows_choice(eng, e, y)
+            if pr is not None:
+                x = eng.mbconv_rows(y, pr, residual=inp if e["res"] else None)
+                if y is not inp:
+                    eng.release(y)
+                eng.release(inp)
+                continue
             if (e["fused"] is not None and y.shape[1] >= _FUSE_MIN_HW
                     and mbconv_supported(*y.shape, e["fused"].cexp, e["fused"].cout, e["stride"])):
                 x = eng.mbconv(y, e["fused"], residual=inp if e["res"] else None)

@@ -97,6 +97,26 @@ def test_sth_fused_plan(golden_dir, tag, over, batch):
     assert torch.equal(pred, pred2)
 
 
+def test_sth_fused_plan_row_streaming_blocks(golden_dir, monkeypatch):
+    """Same golden comparison with the glancer's MobileNet-V2 blocks forced through af_mbconv_rows, the kernel that
+    bench-size batches take (with the temporal shift applied to the block input, the residual un-shifted)."""
+    import adafocus_b200.models.mobilenet as mb
+    from adafocus_b200 import synth
+    monkeypatch.setattr(mb, "_ROWS_MODE", "force")
+    tag, over, batch = CASES[0]
+    gold = np.load(os.path.join(golden_dir, f"sth_{tag}.npz"))
+    args, model, ck = _build(over)
+    gi = synth.synth_clips(batch, args.num_segments_glancer, 224, synth.SEED + 1).to(DEV)
+    fi = synth.synth_clips(batch, args.num_segments_focuser, 224, synth.SEED + 2).to(DEV)
+    pred = model.forward_eval(gi, fi, args)
+    plan = model.last_plan
+    assert np.array_equal(plan.yx.view(batch, args.video_div, 2).cpu().numpy(), gold["coords"])
+    assert np.abs(plan.action.view(batch, args.video_div, 2).cpu().numpy() - gold["actions"]).max() <= 2e-3
+    s = max(1.0, float(np.abs(gold["pred_stage3"][-1]).max()))
+    assert np.abs(pred.cpu().numpy() - gold["pred_stage3"][-1]).max() <= STH_TOL * s
+    assert np.array_equal(pred.argmax(1).cpu().numpy(), gold["pred_stage3"][-1].argmax(1))
+
+
 def test_temporal_shift_public_api_bit_exact():
     from adafocus_b200.models_sth.temporal_shift import TemporalShift
     from oracle import adafocus_oracle as orc
