@@ -52,6 +52,7 @@ class MbconvRowsDesc(ctypes.Structure):
         ("residual", c_void_p), ("out", c_void_p),
         ("n", c_int32), ("h", c_int32), ("w_", c_int32), ("cin", c_int32), ("cexp", c_int32), ("cout", c_int32),
         ("stride", c_int32), ("res_stride", c_int64),
+        ("in_pix_stride", c_int64), ("in_row_stride", c_int64), ("in_img_stride", c_int64),
     ]
 
 

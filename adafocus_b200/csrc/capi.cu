@@ -737,6 +737,8 @@ int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream) {
     return fail(AF_ERR_INVALID, "af_mbconv_rows: null tensor");
   if (d->residual != nullptr && (d->stride != 1 || d->res_stride % 8 != 0 || d->res_stride < d->cout))
     return fail(AF_ERR_INVALID, "af_mbconv_rows: a residual needs stride 1 and res_stride % 8 == 0");
+  if (d->in_pix_stride % 8 != 0 || d->in_row_stride % 8 != 0 || d->in_img_stride % 8 != 0)
+    return fail(AF_ERR_INVALID, "af_mbconv_rows: input view strides must be multiples of 8 elements");
   af::MrParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->n; p.H = d->h; p.W = d->w_; p.Cin = d->cin; p.Cexp = d->cexp; p.Cout = d->cout; p.S = d->stride;
@@ -750,10 +752,12 @@ int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream) {
   memset(&maps, 0, sizeof(maps));
   std::string err;
   {
-    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->cin) * 2;
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->in_pix_stride > 0 ? d->in_pix_stride : d->cin) * 2;
+    const cuuint64_t row_b = d->in_row_stride > 0 ? static_cast<cuuint64_t>(d->in_row_stride) * 2 : pix_b * d->w_;
+    const cuuint64_t img_b = d->in_img_stride > 0 ? static_cast<cuuint64_t>(d->in_img_stride) * 2 : row_b * d->h;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w_),
                                 static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
-    const cuuint64_t strides[3] = {pix_b, pix_b * d->w_, pix_b * d->w_ * d->h};
+    const cuuint64_t strides[3] = {pix_b, row_b, img_b};
     const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.RP), static_cast<cuuint32_t>(p.G), 1};
     if (!encode_map(ctx, &maps.x, d->in, 4, dims, strides, box, &err)) return fail(AF_ERR_CUDA, err);
   }

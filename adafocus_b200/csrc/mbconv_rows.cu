@@ -348,11 +348,13 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       if (et == 0) tma_store_wait_read0();     // the previous item's stores have released the staging tile
       named_barrier_sync(kEpiBarrier, 128);
       // output pixel of this accumulator row
-      int on = n, oy;
+      const int pn = (unit - 1) >> (p.segs - 1), pseg = (unit - 1) & (p.segs - 1);   // the frame segment before this one
+      int on = n, oseg = seg, oy;
       if (S == 1) {
         oy = k0 * p.G - 1 + oi;
-        if (oy < 0) {              // first row of a frame's first step: the last row of the previous frame
-          on = n - 1;
+        if (oy < 0) {              // first row of a segment's first step: the last row of the previous segment
+          on = unit > 0 ? pn : -1;
+          oseg = pseg;
           oy = p.SPF * p.G - 1;
         }
       } else {
@@ -360,7 +362,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
       }
       const __half* rp = nullptr;
       if (S == 1 && lane_valid && p.residual != nullptr && on >= 0 && on < p.N && oy < p.H)
-        rp = p.residual + ((static_cast<long long>(on) * p.H + oy) * p.W + ox_seg) * p.res_stride;
+        rp = p.residual + ((static_cast<long long>(on) * p.H + oy) * p.W + oseg * p.OWseg + ox_seg) * p.res_stride;
       const int sr = (S == 1 && k0 == 0) ? srow_first : srow;
       uint8_t* srow_p = s_out + sr * 128;
       for (int cg = 0; cg < ncg; ++cg) {
@@ -406,10 +408,10 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
         if (S == 1) {
           if (k0 == 0) {
             if (ts > 0 && p.SPF * p.G - 1 < p.H)
-              tma_store_4d(&maps.out_one, s_out + first_base * 128, 0, 0, p.SPF * p.G - 1, n - 1);
-            if (!is_flush) tma_store_4d(&maps.out_rest, s_out, 0, 0, 0, n);
+              tma_store_4d(&maps.out_one, s_out + first_base * 128, 0, pseg * p.OWseg, p.SPF * p.G - 1, pn);
+            if (!is_flush) tma_store_4d(&maps.out_rest, s_out, 0, seg * p.OWseg, 0, n);
           } else {
-            tma_store_4d(&maps.out, s_out, 0, 0, k0 * p.G - 1, n);
+            tma_store_4d(&maps.out, s_out, 0, seg * p.OWseg, k0 * p.G - 1, n);
           }
         } else {
           tma_store_4d(&maps.out, s_out, 0, seg * p.OWseg, k0 * p.OR, n);
@@ -440,7 +442,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
     int k = 0, unit = u0;
     uint32_t a2_base = 0;
     int a2_buf = 0;
-    bool step_flush = false, zero_first = false;
+    bool step_flush = false, zero_first = false, zero_last_col = false;
 
     // E ring position of this warp's chunk: slot = chunk + nch * e_j, parity e_ph
     int e_j = 0;
@@ -448,6 +450,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
     auto step_begin = [&](int t) {
       step_flush = flush && t == T - 1;
       zero_first = strip == 0 && (unit & (p.segs - 1)) == 0;
+      zero_last_col = last_strip && (unit & (p.segs - 1)) == p.segs - 1;
       const int ts = t >> spi_log2, sub = t & (p.SPI - 1);
       a2_buf = chunk * 2 + (ts & 1);
       a2_base = smem_base + static_cast<uint32_t>(p.a2_off[a2_buf]) +
@@ -495,7 +498,7 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
         const int pi = rr & (p.G - 1);
         if (pi == 0) step_begin(rr >> g_log2);
         const int y = step_flush ? p.H : k * p.G + pi;
-        next_row(last_strip, y >= p.H, r2);
+        next_row(zero_last_col, y >= p.H, r2);
         const uint32_t ob = a2_base + static_cast<uint32_t>(pi * p.RP * 128);
         if (k == 0 && pi < 2) {
           if (pi == 0) dw_row_s1<1>(r0, r1, r2, w, b2, ob);
@@ -646,6 +649,9 @@ bool mbrows_plan(MrParams* p) {
       p->segs = 2;
       wo_seg = 28;
     }
+  } else if (p->Wo == 112) {
+    p->segs = 2;                 // two 56-pixel segments per row, each with its own halo columns
+    wo_seg = 56;
   }
   if (wo_seg % p->OW != 0) return false;
   p->SPR = wo_seg / p->OW;

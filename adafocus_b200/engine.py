@@ -134,6 +134,15 @@ def pack_stem_s2d(w, scale, bias, act, device):
     2x2 space-to-depth input written by af_stem_s2d: view channel sx*16 + (dy*2+dx)*3 + c at view pixel (Y, X) is
     padded[c][2Y+dy][2(X+sx)+dx], so tap (r, s) of the original filter lands on vertical tap r//2 and view channel
     (s//2)*16 + ((r%2)*2 + s%2)*3 + c."""
+    w64, vt = stem_s2d_weights(w)
+    pc = pack_conv(w64, scale, bias, 1, 0, act, device=device)
+    pc.vt = vt
+    return pc
+
+
+def stem_s2d_weights(w):
+    """-> (w64 fp32 (cout, 64, R // vt, 1), vt): the stem filter re-indexed for the window view (pack_stem_s2d)."""
+    w = host(w)
     cout, _, k, _ = w.shape
     R = (k + 1) // 2
     vt = 2 if R == 2 else 1   # 3x3: fold the two vertical taps into the pixel too -> one k-block, a 1x1 conv
@@ -142,9 +151,7 @@ def pack_stem_s2d(w, scale, bias, act, device):
         for s_ in range(k):
             ch = (s_ // 2) * 16 * vt + ((r // 2) % vt) * 16 + ((r % 2) * 2 + (s_ % 2)) * 3
             w64[:, ch:ch + 3, (r // 2) // vt, 0] = w[:, :, r, s_]
-    pc = pack_conv(w64, scale, bias, 1, 0, act, device=device)
-    pc.vt = vt
-    return pc
+    return w64, vt
 
 
 class PackedMbconv:
@@ -201,7 +208,7 @@ class PackedMbconvRows:
 def mbconv_rows_spr(w, stride):
     """Strips per row segment of af_mbconv_rows for an input of width w (None: width not handled)."""
     if stride == 1:
-        return {14: 1, 28: 2, 56: 4}.get(int(w))
+        return {14: 1, 28: 2, 56: 4, 112: 4}.get(int(w))
     return {28: 2, 56: 4, 112: 4}.get(int(w))
 
 
@@ -478,6 +485,32 @@ class Engine:
         self.release(col)
         return out
 
+    def stem_front_ok(self, pc, front, frames):
+        """Can stem_front() run features[0..1] of MobileNet-V2 as one row-streaming launch on these frames?"""
+        n, c, h, w = frames.shape
+        q = getattr(pc, "s2d", None)
+        return (front is not None and self.s2d_stem and q is not None and q.vt == 2 and q.kh == 1 and h == w and h % 2 == 0
+                and mbconv_rows_spr(h // 2, 1) == front.spr
+                and mbconv_rows_supported(n, h // 2, w // 2, 64, front.cexp, front.cout, 1))
+
+    def stem_front(self, frames, pc, front):
+        """frames (N,3,H,W) fp32 -> features[1] output (N,H/2,W/2,cout) NHWC fp16: space-to-depth prepass, then the 3x3/2
+        stem conv (a 1x1 conv over the 64-channel window view, pack_stem_s2d) as the EXPAND GEMM of af_mbconv_rows,
+        followed by block 1's depthwise 3x3 and 1x1 project -- the 32-channel stem output never reaches HBM."""
+        n, c, h, w = frames.shape
+        s, q = pc.stem, pc.s2d
+        ho, wo = h // 2, w // 2
+        pe = 16 * q.vt
+        hs, ws = ho + q.kh - 1, wo + 64 // pe - 1
+        buf = self.empty((n * hs * ws + ws, pe), torch.float16)
+        check(self.lib.af_stem_s2d(self.h, _ptr(frames), None, 1, _ptr(buf), n, h, w, h, s["pad"], hs, ws, q.vt,
+                                   self._stream()), "af_stem_s2d")
+        self._count()
+        self.keep(frames, buf)
+        out = self.mbconv_rows(buf, front, view=(n, ho, wo, 64, pe, ws * pe, hs * ws * pe))
+        self.release(buf)
+        return out
+
     def stem_conv3x3s2_c32(self, frames, w27, scale, bias, act=AF_ACT_RELU6):
         """frames (N,3,H,W) fp32 NCHW -> (N,H/2,W/2,32) NHWC fp16 (MobileNet-V2 features[0])."""
         n, c, h, w = frames.shape
@@ -509,10 +542,16 @@ class Engine:
         self.keep(x, pm.w1, pm.b1, pm.dw, pm.b2, pm.w2, pm.b3, residual, out)
         return out
 
-    def mbconv_rows(self, x, pr, residual=None):
-        """Row-streaming fused inverted-residual block: x NHWC fp16 (n,h,w,cin) contiguous -> (n,ho,wo,cout)."""
-        n, h, w, cin = x.shape
-        assert cin == pr.cin and x.is_contiguous() and mbconv_rows_spr(w, pr.stride) == pr.spr
+    def mbconv_rows(self, x, pr, residual=None, view=None):
+        """Row-streaming fused inverted-residual block: x NHWC fp16 (n,h,w,cin) contiguous -> (n,ho,wo,cout).
+        view = (n, h, w, cin, pix_stride, row_stride, img_stride): x is a buffer read through that (possibly
+        overlapping-pixel) view instead (af_mbconv_rows_desc.in_*_stride)."""
+        if view is not None:
+            n, h, w, cin = view[:4]
+        else:
+            n, h, w, cin = x.shape
+            assert x.is_contiguous()
+        assert cin == pr.cin and mbconv_rows_spr(w, pr.stride) == pr.spr
         s = pr.stride
         ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
         out = self.empty((n, ho, wo, pr.cout), torch.float16)
@@ -522,6 +561,8 @@ class Engine:
         d.residual = residual.data_ptr() if residual is not None else None
         d.n, d.h, d.w_, d.cin, d.cexp, d.cout, d.stride = n, h, w, cin, pr.cexp, pr.cout, s
         d.res_stride = residual.stride(-2) if residual is not None else 0
+        if view is not None:
+            d.in_pix_stride, d.in_row_stride, d.in_img_stride = int(view[4]), int(view[5]), int(view[6])
         check(self.lib.af_mbconv_rows(self.h, byref(d), self._stream()), "af_mbconv_rows")
         self._count()
         self.keep(x, pr.w1, pr.dwp, pr.w2, pr.b3, residual, out)

