@@ -115,7 +115,7 @@ _ROWS_MODE = os.environ.get("AF_MBROWS", "auto")      # "0": never, "force": whe
 
 def _rows_choice(eng, e, y):
     """The row-streaming packing of block e for input y (N,H,W,C), or None to use the tiled kernel.  The row kernel gives
-    every CTA whole frames: it needs at least two frames (segments) per SM; with five depthwise warps per lane quarter
+    every CTA whole frames: it needs at least one frame (segment) per SM; with five depthwise warps per lane quarter
     (cexp = 144 at stride 1) its 72-register budget spills and the tiled kernel stays faster (profiles/README.md)."""
     if _ROWS_MODE == "0" or not e["rows"]:
         return None
@@ -128,7 +128,7 @@ def _rows_choice(eng, e, y):
     if _ROWS_MODE == "force":
         return pr
     units = n * (2 if (pr.stride == 2 and w == 112) else 1)
-    if units < 2 * eng.ctx.sm_count:         # CTAs own whole frames: below two per SM the tail round costs too much
+    if units < eng.ctx.sm_count:             # CTAs own whole frames (cfg5: 256 frames on 148 SMs still gains 2 %)
         return None
     if pr.stride == 1 and pr.cexp % 128 == 16:
         return None
