@@ -705,8 +705,7 @@ int af_mbconv_fused(af_ctx* ctx, const af_mbconv_desc* d, void* stream) {
 }
 
 static long long* g_mbrows_prof = nullptr;
-/* debug hook (tools/mbrows_debug.py): device buffer of 32 x 8 int64 that CTA 0 of af_mbconv_rows fills with per-warp
- * cycle counters (total, wait for E, TMEM load, wait for an A2 buffer | expand issuers: total, wait X, wait slot) */
+/* bring-up hook: device buffer of 32 x 8 int64 for per-warp cycle counters of CTA 0 (instrumented builds only) */
 int af_debug_mbconv_rows_prof(void* buf) {
   g_mbrows_prof = static_cast<long long*>(buf);
   return AF_OK;

@@ -4,6 +4,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "ptx.cuh"
 
@@ -14,7 +15,7 @@ using namespace ptx;
 namespace {
 
 constexpr int kD2Col = 384;            // TMEM column of the project accumulators (2 x 64 columns)
-constexpr int kFirstDwWarp = 8;        // warp 0: TMA producer, 1: expand MMAs, 2: project MMAs, 3: idle, 4-7: epilogue, 8..: depthwise
+constexpr int kFirstDwWarp = 8;        // warp 0: TMA producer, 1 and 3: expand MMAs, 2: project MMAs, 4-7: epilogue, 8..: depthwise
 constexpr int kSlots = 6;              // E ring: six 64-column slots (64 / RP image rows of one chunk each); 384 columns
 constexpr int kEpiBarrier = 1;
 
@@ -245,55 +246,48 @@ mbconv_rows_kernel(const __grid_constant__ MrTensorMaps maps, const __grid_const
     uint32_t row_slot = 0;          // first slot (chunk 0) of the current ring position
     uint32_t ph = 0, fph = 0;       // fph: parity that says "the previous use of this slot has been released"
     bool first_lap = true;
-    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
-    long long prof_x = 0, prof_f = 0, prof_m = 0;
-    const long long prof_t0 = prof_on ? clock64() : 0;
-    for (int t = 0; t < T; ++t) {
-      const long long cx0 = prof_on ? clock64() : 0;
-      wait_sleep(&ctrl->x_full[stage], ph);
-      if (prof_on) prof_x += clock64() - cx0;
-      uint32_t lb = x_lo0 + static_cast<uint32_t>(stage) * (static_cast<uint32_t>(p.x_stage) >> 4);
-      for (int g = 0; g < IPS; ++g, lb += item_lo) {
-        for (int c = c_first; c < nch; c += c_step) {
-          const uint32_t slot = row_slot + static_cast<uint32_t>(c);
-          const long long cf0 = prof_on ? clock64() : 0;
-          if (!first_lap) {
-            const uint32_t fb = free0 + slot * 8u;
-            uint32_t done;
-            do {
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                  : "=r"(done)
-                  : "r"(fb), "r"(fph)
-                  : "memory");
-            } while (!done);
+    // the loop body per K-step count: the issuing warp's instruction stream is the critical resource
+    auto run = [&](auto kc) {
+      constexpr int K1 = decltype(kc)::value;
+      for (int t = 0; t < T; ++t) {
+        wait_sleep(&ctrl->x_full[stage], ph);
+        uint32_t lb = x_lo0 + static_cast<uint32_t>(stage) * (static_cast<uint32_t>(p.x_stage) >> 4);
+        for (int g = 0; g < IPS; ++g, lb += item_lo) {
+          for (int c = c_first; c < nch; c += c_step) {
+            const uint32_t slot = row_slot + static_cast<uint32_t>(c);
+            if (!first_lap) {
+              const uint32_t fb = free0 + slot * 8u;
+              uint32_t done;
+              do {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                    : "=r"(done)
+                    : "r"(fb), "r"(fph)
+                    : "memory");
+              } while (!done);
+            }
+            tc_fence_after();
+            umma_group_commit_elect<K1>(tmem_base + slot * 64u, w_lo0 + static_cast<uint32_t>(c) * (16384u >> 4), lb, idesc1,
+                                        full0 + slot * 8u);
           }
-          const long long cf1 = prof_on ? clock64() : 0;
-          if (prof_on) prof_f += cf1 - cf0;
-          tc_fence_after();
-          umma_group_commit_elect(tmem_base + slot * 64u, w_lo0 + static_cast<uint32_t>(c) * (16384u >> 4), lb, idesc1, k1,
-                                  full0 + slot * 8u);
-          if (prof_on) prof_m += clock64() - cf1;
+          row_slot += static_cast<uint32_t>(nch);
+          if (row_slot == ring_slots) {
+            row_slot = 0;
+            if (first_lap) first_lap = false;
+            else fph ^= 1u;
+          }
         }
-        row_slot += static_cast<uint32_t>(nch);
-        if (row_slot == ring_slots) {
-          row_slot = 0;
-          if (first_lap) first_lap = false;
-          else fph ^= 1u;
+        umma_commit_elect(&ctrl->x_empty[stage]);
+        if (++stage == XS) {
+          stage = 0;
+          ph ^= 1u;
         }
       }
-      umma_commit_elect(&ctrl->x_empty[stage]);
-      if (++stage == XS) {
-        stage = 0;
-        ph ^= 1u;
-      }
-    }
-    if (prof_on && lane == 0) {
-      p.prof[warp * 8 + 0] = clock64() - prof_t0;
-      p.prof[warp * 8 + 1] = prof_x;
-      p.prof[warp * 8 + 2] = prof_f;
-      p.prof[warp * 8 + 3] = prof_m;
-    }
+    };
+    if (k1 == 1) run(std::integral_constant<int, 1>{});
+    else if (k1 == 2) run(std::integral_constant<int, 2>{});
+    else if (k1 == 3) run(std::integral_constant<int, 3>{});
+    else run(std::integral_constant<int, 4>{});
   } else if (warp == 2) {
     // ============================ project MMA issuer: D2[item] = sum over chunks A2[chunk] * W2[chunk]^T ============================
     const uint32_t idesc2 = make_idesc_f16_f32(128, static_cast<uint32_t>(p.cout_pad));

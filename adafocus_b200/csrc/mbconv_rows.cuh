@@ -10,7 +10,8 @@
 //
 //   TMA        : G input rows (128 / RP, or 64 / RP when shared memory is short) x RP pixels x 64 channels per step
 //                -> smem (B operand of the expand GEMM)
-//   tcgen05.mma: E[chunk] (128 lanes x 128 columns, fp32) = W1[chunk] * X^T      one MMA group per 128-lane chunk
+//   tcgen05.mma: E[slot] (128 lanes x 64 columns, fp32) = W1[chunk] * X[64 pixels]^T   ring of six slots in TMEM, one
+//                MMA group per (64 / RP image rows, 128-lane chunk), two issuing warps
 //   dw warps   : warp = (lane quarter, chunk, 14-output column strip): rows -> +bias, ReLU6 -> 3x3 -> +bias, ReLU6 -> A2
 //   tcgen05.mma: D2 += A2[chunk] * W2[chunk]^T
 //   epilogue   : D2 -> +bias (+ residual) -> fp16 -> staging -> TMA store (rows of the frame as they complete)
@@ -59,7 +60,7 @@ struct MrParams {
   const float* bias3;            // [cout_pad]
   const __half* residual;        // NHWC (N, H, W, Cout) with pixel stride res_stride, or nullptr (stride 1 only)
   long long res_stride;
-  long long* prof;               // debug: per-warp cycle counters of CTA 0 ([warp][8]), or nullptr
+  long long* prof;               // reserved (debug hook af_debug_mbconv_rows_prof), unused by the kernel
   int off_w1, off_w2, off_a2, off_out, off_ctrl, smem;
 };
 

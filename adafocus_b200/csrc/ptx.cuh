@@ -242,40 +242,77 @@ __device__ __forceinline__ void umma_f16_ss_lo_elect(uint32_t tmem_d, uint32_t l
       : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
       : "memory");
 }
-// One accumulator tile in one go: k_steps (1..4) MMAs over consecutive 16-wide K slices (32 B apart in both operand
-// tiles), the first one overwriting D, then a commit on `bar_addr`; a single election for the whole group.
+// One accumulator tile in one go: K_STEPS (1..4) MMAs over consecutive 16-wide K slices (32 B apart in both operand
+// tiles), the first one overwriting D, then a commit on `bar_addr`; a single election for the whole group.  K_STEPS is
+// a template parameter so that the issuing warp sets up exactly the descriptors it uses (its instruction stream is the
+// critical resource: ~10 cycles per instruction next to busy compute warps).
+template <int K_STEPS>
 __device__ __forceinline__ void umma_group_commit_elect(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc,
-                                                        uint32_t k_steps, uint32_t bar_addr) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pe, p2, p3, p4, pt, pf;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.eq.u32 pt, %4, %4;\n\t"
-      "setp.ne.u32 pf, %4, %4;\n\t"
-      "setp.gt.u32 p2, %4, 1;\n\t"
-      "setp.gt.u32 p3, %4, 2;\n\t"
-      "setp.gt.u32 p4, %4, 3;\n\t"
-      "and.pred p2, p2, pe;\n\t"
-      "and.pred p3, p3, pe;\n\t"
-      "and.pred p4, p4, pe;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pf;\n\t"
-      "add.u64 da, da, 2;\n\t"
-      "add.u64 db, db, 2;\n\t"
-      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
-      "add.u64 da, da, 2;\n\t"
-      "add.u64 db, db, 2;\n\t"
-      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
-      "add.u64 da, da, 2;\n\t"
-      "add.u64 db, db, 2;\n\t"
-      "@p4 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
-      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-      "}\n"
-      :
-      : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(k_steps), "r"(kDescHiSw128), "r"(bar_addr)
-      : "memory");
+                                                        uint32_t bar_addr) {
+  static_assert(K_STEPS >= 1 && K_STEPS <= 4, "K_STEPS");
+  if (K_STEPS == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pf;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.u32 pf, %3, %3;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pf;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(kDescHiSw128), "r"(bar_addr)
+        : "memory");
+  } else if (K_STEPS == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pt, pf;\n\t"
+        ".reg .b64 da, db, da1, db1;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.u32 pt, %3, %3;\n\t"
+        "setp.ne.u32 pf, %3, %3;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "mov.b64 da1, {%6, %4};\n\t"
+        "mov.b64 db1, {%7, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pf;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %3, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(kDescHiSw128), "r"(bar_addr), "r"(lo_a + 2u), "r"(lo_b + 2u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, p4, pt, pf;\n\t"
+        ".reg .b64 da, db, da1, db1, da2, db2, da3, db3;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.u32 pt, %3, %3;\n\t"
+        "setp.ne.u32 pf, %3, %3;\n\t"
+        "setp.ne.u32 p4, %12, 0;\n\t"
+        "and.pred p4, p4, pe;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "mov.b64 da1, {%6, %4};\n\t"
+        "mov.b64 db1, {%7, %4};\n\t"
+        "mov.b64 da2, {%8, %4};\n\t"
+        "mov.b64 db2, {%9, %4};\n\t"
+        "mov.b64 da3, {%10, %4};\n\t"
+        "mov.b64 db3, {%11, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pf;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da2, db2, %3, pt;\n\t"
+        "@p4 tcgen05.mma.cta_group::1.kind::f16 [%0], da3, db3, %3, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(kDescHiSw128), "r"(bar_addr), "r"(lo_a + 2u), "r"(lo_b + 2u),
+          "r"(lo_a + 4u), "r"(lo_b + 4u), "r"(lo_a + 6u), "r"(lo_b + 6u), "r"(K_STEPS == 4 ? 1u : 0u)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(

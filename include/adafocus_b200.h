@@ -230,7 +230,8 @@ typedef struct af_mbconv_rows_desc {
 int af_mbconv_rows_supported(int n, int h, int w, int cin, int cexp, int cout, int stride);
 int af_mbconv_rows_layout(int cexp, int spr, int32_t* nchunks, int16_t* lane_ch, int16_t* lane_kpos);
 int af_mbconv_rows(af_ctx* ctx, const af_mbconv_rows_desc* d, void* stream);
-/* debug: device buffer (32 x 8 int64) that CTA 0 of af_mbconv_rows fills with per-warp cycle counters, or NULL */
+/* bring-up hook: device buffer (32 x 8 int64) for per-warp cycle counters of CTA 0 of af_mbconv_rows (only filled by
+ * instrumented builds of csrc/mbconv_rows.cu; the shipped kernel ignores it), or NULL */
 int af_debug_mbconv_rows_prof(void* buf);
 
 /* MobileNet-V2 features[0]: Conv2d(3,32,3,stride 2,pad 1) + BN + ReLU6 (ACT/models/mobilenet.py:105) directly from

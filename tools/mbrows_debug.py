@@ -1,4 +1,4 @@
-"""Debug / timing driver of af_mbconv_rows: python tools/mbrows_debug.py [time]"""
+"""Correctness / timing driver of af_mbconv_rows: python tools/mbrows_debug.py [time | b2 b3 ...]"""
 import math, os, sys
 import torch
 import torch.nn.functional as F
@@ -36,9 +36,7 @@ def ref_fn(x, ws, stride, res):
     return r.permute(0, 2, 3, 1)
 
 
-if len(sys.argv) > 1 and sys.argv[1] == "prof":
-    pass
-elif len(sys.argv) > 1 and sys.argv[1] == "time":
+if len(sys.argv) > 1 and sys.argv[1] == "time":
     n = 1024
     for name, (cin, cexp, cout, stride, hw, res) in CASES.items():
         x, ws = make(cin, cexp, cout, stride, hw, res, n)
@@ -74,26 +72,3 @@ else:
                 print("  first bad (n,y,x,c):", idx[:5].tolist(), " rows:", sorted(set(idx[:, 1].tolist()))[:20], " cols:", sorted(set(idx[:, 2].tolist()))[:20],
                       " frames:", sorted(set(idx[:, 0].tolist()))[:10], " ch:", sorted(set(idx[:, 3].tolist()))[:20])
 
-
-def prof(names):
-    from adafocus_b200 import _lib
-    lib = _lib.load()
-    buf = torch.zeros(32, 8, dtype=torch.int64, device=dev)
-    for name in names:
-        cin, cexp, cout, stride, hw, res = CASES[name]
-        x, ws = make(cin, cexp, cout, stride, hw, res, 1024)
-        pr = pack_mbconv_rows(*ws, stride, mbconv_rows_spr(hw, stride), device=dev)
-        for _ in range(2):
-            eng.release(eng.mbconv_rows(x, pr, residual=x if res else None))
-        torch.cuda.synchronize()
-        buf.zero_()
-        lib.af_debug_mbconv_rows_prof(buf.data_ptr())
-        eng.release(eng.mbconv_rows(x, pr, residual=x if res else None))
-        torch.cuda.synchronize()
-        lib.af_debug_mbconv_rows_prof(None)
-        b = buf.cpu()
-        print(name, "expand issuers (total, wait X, wait slot, fence+MMA group+commit):", b[1, :4].tolist(), b[3, :4].tolist())
-
-
-if len(sys.argv) > 1 and sys.argv[1] == "prof":
-    prof(sys.argv[2:] or ["b2", "b5"])
