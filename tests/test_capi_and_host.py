@@ -122,6 +122,71 @@ def test_fused_block_packing_carries_the_expand_bias_in_two_weight_columns():
     assert not wide.bias1_in_w1          # no spare K columns at cin = 64: bias stays in the epilogue
 
 
+@pytest.mark.parametrize("cexp,spr", [(96, 4), (144, 4), (192, 2), (384, 1), (32, 4), (96, 2), (48, 2), (16, 4)])
+def test_row_kernel_lane_placement(cexp, spr):
+    """af_mbconv_rows_layout (host query, no device work): every expanded channel sits on at least one TMEM lane, a
+    channel's K column is the same wherever it is replicated, and K columns inside a chunk are distinct per channel."""
+    from adafocus_b200.engine import mbconv_rows_layout
+    lay = mbconv_rows_layout(cexp, spr)
+    assert lay is not None
+    nch, lane_ch, lane_kpos = lay
+    assert 1 <= nch <= 3
+    seen = set()
+    for c in range(nch):
+        ch, kp = lane_ch[c].tolist(), lane_kpos[c].tolist()
+        col_of = {}
+        for lane in range(128):
+            if ch[lane] >= 0:
+                assert 0 <= kp[lane] < 128
+                assert col_of.setdefault(ch[lane], kp[lane]) == kp[lane]          # replicas share the column
+                seen.add(ch[lane])
+        assert len(set(col_of.values())) == len(col_of)                           # distinct channels, distinct columns
+        dead = [kp[lane] for lane in range(128) if ch[lane] < 0]
+        assert not (set(dead) & set(col_of.values()))                             # idle lanes never alias a live column
+    for c in range(nch, 3):
+        assert all(v == -1 for v in lane_ch[c].tolist()) or nch == 3
+    assert seen == set(range(cexp))
+    assert mbconv_rows_layout(576, 1) is None and mbconv_rows_layout(192, 4) is None and mbconv_rows_layout(24, 4) is None
+
+
+@pytest.mark.parametrize("cin,cexp,cout,stride,spr", [(24, 144, 24, 1, 4), (32, 96, 24, 2, 4), (64, 384, 64, 1, 1)])
+def test_row_kernel_packing_reproduces_the_block(cin, cexp, cout, stride, spr):
+    """pack_mbconv_rows on the host: evaluating the block FROM THE PACKED TENSORS (lane-ordered expand weights with the
+    1/6 of the saturating ReLU6 folded in, per-lane depthwise taps and biases, K-column-ordered project weights with the
+    6) gives the three reference convolutions (ACT/models/mobilenet.py:42-68) up to fp16 weight rounding."""
+    import torch.nn.functional as F
+    from adafocus_b200.engine import mbconv_rows_layout, pack_mbconv_rows
+    torch.manual_seed(cexp)
+    w1, wd, w2 = torch.randn(cexp, cin) / cin ** 0.5, torch.randn(cexp, 1, 3, 3) / 3, torch.randn(cout, cexp) / cexp ** 0.5
+    s1, b1 = torch.rand(cexp) + 0.5, torch.randn(cexp) * 0.2
+    s2, b2 = torch.rand(cexp) + 0.5, torch.randn(cexp) * 0.2
+    s3, b3 = torch.rand(cout) + 0.5, torch.randn(cout) * 0.2
+    pr = pack_mbconv_rows(w1, s1, b1, wd, s2, b2, w2, s3, b3, stride, spr, device="cpu")
+    nch, lane_ch, lane_kpos = mbconv_rows_layout(cexp, spr)
+    assert pr.w1.shape == (nch * 128, 64) and pr.dwp.shape == (nch, 11, 128) and pr.w2.shape[1] == nch * 128
+    x = torch.randn(2, cin, 12, 12).half().float()
+    out = torch.zeros(2, pr.w2.shape[0], (12 - 1) // stride + 1, (12 - 1) // stride + 1)
+    done = set()
+    for c in range(nch):
+        for lane in range(128):
+            ch = int(lane_ch[c, lane])
+            if ch < 0 or ch in done:
+                continue
+            done.add(ch)
+            e = F.conv2d(x, pr.w1[c * 128 + lane, :cin].float().view(1, cin, 1, 1)) + pr.dwp[c, 9, lane]
+            e = e.clamp(0, 1)                                                   # add.sat: ReLU6(x) / 6
+            d = F.conv2d(e, pr.dwp[c, :9, lane].view(1, 1, 3, 3), None, stride, 1) + pr.dwp[c, 10, lane]
+            d = d.clamp(0, 1)
+            col = c * 128 + int(lane_kpos[c, lane])
+            out += d * pr.w2[:, col].float().view(1, -1, 1, 1)
+    out = out[:, :cout] + pr.b3[:cout].view(1, -1, 1, 1)
+    e = (F.conv2d(x, (w1 * s1[:, None])[:, :, None, None]) + b1.view(1, -1, 1, 1)).clamp(0, 6)
+    d = (F.conv2d(e, wd * s2.view(-1, 1, 1, 1), None, stride, 1, 1, cexp) + b2.view(1, -1, 1, 1)).clamp(0, 6)
+    ref = F.conv2d(d, (w2 * s3[:, None])[:, :, None, None]) + b3.view(1, -1, 1, 1)
+    assert float((out - ref).abs().max()) <= 4e-3 * max(1.0, float(ref.abs().max()))
+    assert float(pr.w2[cout:].abs().max() if pr.w2.shape[0] > cout else 0) == 0
+
+
 def test_standard_action_table_matches_reference_literals():
     from adafocus_b200.models.gfv_net import standard_action_table
     t49 = standard_action_table(49)
