@@ -128,7 +128,10 @@ def _rows_choice(eng, e, y):
     if _ROWS_MODE == "force":
         return pr
     units = n * (2 if (pr.stride == 2 and w == 112) else 1)
-    if units < eng.ctx.sm_count:             # CTAs own whole frames (cfg5: 256 frames on 148 SMs still gains 2 %)
+    # CTAs own whole frames: the launch lasts ceil(units / SMs) frame times, and a frame costs ~0.75 of what it costs
+    # the tiled kernel -- so skip the counts just above a multiple of the SM count (cfg5: 256 frames on 148 SMs gains 2 %)
+    sms = eng.ctx.sm_count
+    if units < sms or units < 0.75 * sms * ((units + sms - 1) // sms):
         return None
     if pr.stride == 1 and pr.cexp % 128 == 16:
         return None
