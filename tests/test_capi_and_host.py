@@ -187,6 +187,42 @@ def test_row_kernel_packing_reproduces_the_block(cin, cexp, cout, stride, spr):
     assert float(pr.w2[cout:].abs().max() if pr.w2.shape[0] > cout else 0) == 0
 
 
+def test_row_kernel_choice_heuristic(monkeypatch):
+    """models/mobilenet.py:_rows_choice on a 148-SM device: whole frames per CTA, so the row kernel is taken from one
+    frame per SM, skipped just above a multiple of the SM count, never for the 144-channel stride-1 block (28 warps at 72
+    registers spill) and never when switched off."""
+    import types
+    import adafocus_b200.models.mobilenet as mb
+    from adafocus_b200.engine import PackedMbconvRows
+    eng = types.SimpleNamespace(ctx=types.SimpleNamespace(sm_count=148))
+
+    def entry(cin, cexp, cout, stride):
+        packs = {spr: PackedMbconvRows(None, None, None, None, cin, cexp, cout, stride, spr) for spr in (1, 2, 4)}
+        return {"rows": packs, "stride": stride}
+
+    def y(n, hw, c):
+        return types.SimpleNamespace(shape=(n, hw, hw, c))
+
+    monkeypatch.setattr(mb, "mbconv_rows_supported", lambda *a: True)
+    monkeypatch.setattr(mb, "_ROWS_MODE", "auto")
+    b5 = entry(32, 192, 32, 1)
+    assert mb._rows_choice(eng, b5, y(1024, 28, 32)) is b5["rows"][2]
+    assert mb._rows_choice(eng, b5, y(147, 28, 32)) is None              # fewer frames than SMs
+    assert mb._rows_choice(eng, b5, y(148, 28, 32)) is not None
+    assert mb._rows_choice(eng, b5, y(150, 28, 32)) is None              # two rounds for 1.01 frames per SM
+    assert mb._rows_choice(eng, b5, y(256, 28, 32)) is not None          # cfg5
+    b2 = entry(32, 96, 24, 2)
+    assert mb._rows_choice(eng, b2, y(74, 112, 32)) is b2["rows"][4]     # 112-wide stride 2: two half-row units per frame
+    b3 = entry(24, 144, 24, 1)
+    assert mb._rows_choice(eng, b3, y(1024, 56, 24)) is None
+    assert mb._rows_choice(eng, entry(24, 144, 32, 2), y(1024, 56, 24)) is not None
+    assert mb._rows_choice(eng, b5, types.SimpleNamespace(shape=(1024, 28, 30, 32))) is None      # square frames only
+    monkeypatch.setattr(mb, "_ROWS_MODE", "force")
+    assert mb._rows_choice(eng, b3, y(2, 56, 24)) is b3["rows"][4]
+    monkeypatch.setattr(mb, "_ROWS_MODE", "0")
+    assert mb._rows_choice(eng, b5, y(1024, 28, 32)) is None
+
+
 def test_standard_action_table_matches_reference_literals():
     from adafocus_b200.models.gfv_net import standard_action_table
     t49 = standard_action_table(49)
